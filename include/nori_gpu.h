@@ -1,0 +1,233 @@
+/* nori_gpu.h -- the C-ABI boundary of the B200-native rendering hot path.
+ *
+ * This header is the drop-in seam for the reference renderer (francois141/nori-ray-tracer).
+ * The reference has no C API: its seam is the body of the render-thread lambda in
+ * src/render.cpp:173-284 (spp-major loop -> tbb::parallel_for over 32x32 blocks -> renderBlock()
+ * src/render.cpp:80-133 -> ImageBlock::put / merge), consuming a `const Scene*`
+ * (include/nori/scene.h:44-115) and producing the full-image `ImageBlock m_block`
+ * (include/nori/block.h:48, row-major Color4f (r,g,b,weight), (H+2b) x (W+2b)).
+ * Everything below replaces exactly that: plain pointers and sizes in, the same film array out.
+ * No C++ types, no torch types, no exceptions cross this boundary (status code + last_error).
+ *
+ * Every struct is plain-old-data with natural alignment; all arrays are HOST pointers owned by the
+ * caller and are copied during nori_gpu_upload_scene().  Layouts follow the reference's own
+ * containers (cited per field) so that the reference-side exporter is a memcpy.
+ */
+#ifndef NORI_GPU_H
+#define NORI_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NORI_GPU_ABI_VERSION 1
+#define NORI_FILTER_RESOLUTION 32          /* include/nori/rfilter.h:25 */
+#define NORI_BLOCK_SIZE 32                 /* include/nori/block.h:30   */
+
+typedef struct nori_gpu_ctx nori_gpu_ctx;  /* opaque; owns all device memory */
+
+/* ---- enumerations (values are part of the ABI) ------------------------------------------- */
+enum { NORI_SHAPE_MESH = 0, NORI_SHAPE_SPHERE = 1 };                     /* src/mesh.cpp, src/sphere.cpp */
+enum { NORI_BSDF_DIFFUSE = 0, NORI_BSDF_MIRROR = 1, NORI_BSDF_DIELECTRIC = 2,
+       NORI_BSDF_MICROFACET = 3, NORI_BSDF_DISNEY = 4, NORI_BSDF_COUNT = 5 };
+enum { NORI_EMITTER_AREA = 0, NORI_EMITTER_POINT = 1, NORI_EMITTER_SPOT = 2, NORI_EMITTER_ENVMAP = 3 };
+enum { NORI_CAMERA_PERSPECTIVE = 0, NORI_CAMERA_THINLENS = 1 };
+enum { NORI_INTEGRATOR_NORMALS = 0, NORI_INTEGRATOR_PATH_MIS = 1, NORI_INTEGRATOR_PATH_MATS = 2,
+       NORI_INTEGRATOR_DIRECT_EMS = 3, NORI_INTEGRATOR_DIRECT_MATS = 4, NORI_INTEGRATOR_DIRECT_MIS = 5,
+       NORI_INTEGRATOR_DIRECT = 6, NORI_INTEGRATOR_AV = 7, NORI_INTEGRATOR_VOLUMETRIC = 8 };
+enum { NORI_TEXTURE_CONSTANT = 0, NORI_TEXTURE_CHECKERBOARD = 1 };
+
+/* ---- BVH: the reference's 32-byte node, verbatim (include/nori/bvh.h:127-164) ------------ *
+ * data[0]: bit 0 = leaf flag, bits 1..31 = leaf size (leaf) or split axis (inner, unused)
+ * data[1]: leaf: first index into `indices`; inner: index of the right child (left = self+1)   */
+typedef struct {
+    uint32_t data[2];
+    float    bmin[3];
+    float    bmax[3];
+} nori_gpu_bvh_node;
+
+/* ---- shapes (include/nori/mesh.h:121-124; src/sphere.cpp:30-37) -------------------------- */
+typedef struct {
+    int32_t  type;              /* NORI_SHAPE_*                                             */
+    int32_t  bsdf;              /* index into scene.bsdfs                                    */
+    int32_t  emitter;           /* index into scene.emitters, or -1 (Shape::isEmitter)       */
+    uint32_t n_vertices;        /* mesh: columns of m_V                                      */
+    uint32_t n_triangles;       /* mesh: columns of m_F; sphere: 1 primitive                 */
+    uint32_t reserved;
+    const float    *V;          /* 3*n_vertices, column-major m_V: vertex i = V[3i..3i+2]    */
+    const float    *N;          /* 3*n_vertices or NULL (m_N)                                */
+    const float    *UV;         /* 2*n_vertices or NULL (m_UV)                               */
+    const uint32_t *F;          /* 3*n_triangles, column-major m_F                           */
+    const float    *area_cdf;   /* n_triangles+1 floats: DiscretePDF::m_cdf (dpdf.h:194)     */
+    float    area_normalization;/* DiscretePDF::getNormalization() = 1/total area            */
+    float    center[3];         /* sphere                                                    */
+    float    radius;            /* sphere                                                    */
+    uint32_t reserved2[3];
+} nori_gpu_shape;
+
+/* ---- BSDFs (src/diffuse.cpp, mirror.cpp, dielectric.cpp, microfacet.cpp, disney.cpp) ----- */
+typedef struct {
+    int32_t type;               /* NORI_BSDF_*                                               */
+    int32_t albedo_texture;     /* NORI_TEXTURE_* for the diffuse albedo                     */
+    float   albedo[3];          /* diffuse: constant albedo / checkerboard value1            */
+    float   albedo2[3];         /* checkerboard value2 (src/checkerboard.cpp:31-37)          */
+    float   tex_scale[2];       /* checkerboard scale                                        */
+    float   tex_delta[2];       /* checkerboard delta                                        */
+    float   intIOR, extIOR;     /* dielectric.cpp:26-29, microfacet.cpp:31-34                */
+    float   alpha;              /* microfacet.cpp:28 ; disney: m_alpha (disney.cpp:59)       */
+    float   kd[3];              /* microfacet.cpp:37                                         */
+    float   ks;                 /* microfacet.cpp:48 : 1 - max(kd)                           */
+    float   baseColor[3];       /* disney.cpp:57                                             */
+    float   metallic, specular, roughness, sheen, sheenTint, specularTint; /* disney.cpp:50-55 */
+    float   reserved[2];
+} nori_gpu_bsdf;
+
+/* ---- emitters (src/arealight.cpp, pointlight.cpp, spotlight.cpp, envmap.cpp) ------------- */
+typedef struct {
+    int32_t type;               /* NORI_EMITTER_*                                            */
+    int32_t shape;              /* area / envmap: index of the shape it is attached to, else -1 */
+    float   radiance[3];        /* area: m_radiance; point: power; spot: "color"             */
+    float   position[3];        /* point / spot                                              */
+    float   direction[3];       /* spot (normalised, spotlight.cpp:14)                       */
+    float   cosFalloffStart;    /* spotlight.cpp:16                                          */
+    float   cosTotalWidth;      /* spotlight.cpp:17                                          */
+    float   weight;             /* envmap m_weight (envmap.cpp:14)                           */
+    int32_t env_rows;           /* envmap "m_width"  = bitmap rows (envmap.cpp:33, sic)      */
+    int32_t env_cols;           /* envmap "m_height" = bitmap cols (envmap.cpp:32, sic)      */
+    const float *env_image;     /* rows*cols*3 row-major RGB (Bitmap, bitmap.h:32)           */
+    const float *env_pdf;       /* rows*cols      row-major  m_pdf       (envmap.cpp:36)     */
+    const float *env_cdf;       /* rows*(cols+1)  row-major  m_cdf       (envmap.cpp:37)     */
+    const float *env_pmarginal; /* rows                     m_pmarginal  (envmap.cpp:38)     */
+    const float *env_cmarginal; /* rows+1                   m_cmarginal  (envmap.cpp:39)     */
+} nori_gpu_emitter;
+
+/* ---- camera (src/perspective.cpp:53-112, src/thinlens.cpp:66-171) ------------------------ */
+typedef struct {
+    int32_t type;               /* NORI_CAMERA_*                                             */
+    int32_t width, height;      /* m_outputSize                                              */
+    float   sampleToCamera[16]; /* row-major 4x4 (m_sampleToCamera.getMatrix())              */
+    float   cameraToWorld[16];  /* row-major 4x4 (m_cameraToWorld.getMatrix())               */
+    float   invOutputSize[2];
+    float   nearClip, farClip;
+    float   lensRadius, focalDistance;   /* thinlens.cpp:49-50                               */
+} nori_gpu_camera;
+
+/* ---- reconstruction filter, pre-tabulated by the host exactly as ImageBlock::init does
+ *      (src/block.cpp:54-64): table[i] = filter->eval(radius*i/32), table[32] = 0 ---------- */
+typedef struct {
+    float radius;
+    float table[NORI_FILTER_RESOLUTION + 1];
+} nori_gpu_filter;
+
+/* ---- homogeneous medium (src/medium.cpp:8-20) -------------------------------------------- */
+typedef struct {
+    int32_t present;
+    float   sigma_a[3], sigma_s[3];
+    float   bounds_min[3], bounds_max[3];
+} nori_gpu_medium;
+
+/* ---- the whole scene --------------------------------------------------------------------- */
+typedef struct {
+    uint32_t abi_version;       /* NORI_GPU_ABI_VERSION                                      */
+    int32_t  integrator;        /* NORI_INTEGRATOR_*                                         */
+    float    av_length;         /* averagevisibility.cpp:13 "length"                         */
+    uint32_t n_nodes;
+    uint32_t n_indices;         /* == total primitive count                                  */
+    uint32_t n_shapes, n_bsdfs, n_emitters;
+    const nori_gpu_bvh_node *nodes;        /* BVH::m_nodes (bvh.h:168)                       */
+    const uint32_t          *indices;      /* BVH::m_indices (bvh.h:169)                     */
+    const uint32_t          *shape_offset; /* BVH::m_shapeOffset, n_shapes+1 entries (bvh.h:167) */
+    const nori_gpu_shape    *shapes;       /* in BVH::m_shapes order                         */
+    const nori_gpu_bsdf     *bsdfs;
+    const nori_gpu_emitter  *emitters;     /* in Scene::m_emitters order (scene.cpp:63-76)   */
+    nori_gpu_camera camera;
+    nori_gpu_filter filter;
+    nori_gpu_medium medium;
+} nori_gpu_scene;
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+typedef struct {                /* Ray3f (include/nori/ray.h:43-47) without dRcp              */
+    float o[3]; float mint;
+    float d[3]; float maxt;
+} nori_gpu_ray;
+
+typedef struct {                /* what BVH::rayIntersect decides before setHitInformation     */
+    float    t;                 /* its.t, +inf if no hit                                      */
+    float    u, v;              /* barycentric (u,v) of the winning triangle; 0 for spheres   */
+    uint32_t shape;             /* index into scene.shapes, 0xffffffff if no hit              */
+    uint32_t prim;              /* primitive index local to the shape (findShape, bvh.h:105)  */
+    uint32_t nodes_visited;     /* BVHNode fetches (bvh.cpp:421)                              */
+    uint32_t prims_tested;      /* Shape::rayIntersect calls (bvh.cpp:440)                    */
+    uint32_t reserved;
+} nori_gpu_hit;
+
+typedef struct {
+    uint64_t samples;           /* camera paths started (render.cpp:98-130 iterations)        */
+    uint64_t rays;              /* BVH::rayIntersect queries, closest + shadow                */
+    uint64_t shadow_rays;       /* the any-hit subset                                         */
+    uint64_t nodes_visited;     /* only counted when stats collection is on                   */
+    uint64_t prims_tested;      /*   "                                                        */
+    uint64_t invalid_samples;   /* dropped like block.cpp:94-98                               */
+    uint64_t iterations;        /* wavefront iterations executed                              */
+    double   render_ms;         /* device time of the last nori_gpu_render (CUDA events)      */
+    double   trace_ms;          /* device time of the last nori_gpu_trace kernel              */
+} nori_gpu_stats;
+
+/* ---- entry points ---------------------------------------------------------------------------
+ * All return 0 on success, non-zero on error (then nori_gpu_last_error() explains).
+ * One host thread per ctx; a ctx is bound to one CUDA device.                                  */
+
+/* Create a context on CUDA device `device`. Replaces nothing in the reference (there is no device). */
+int nori_gpu_init(int device, nori_gpu_ctx **out);
+void nori_gpu_destroy(nori_gpu_ctx *ctx);
+const char *nori_gpu_last_error(const nori_gpu_ctx *ctx);   /* ctx may be NULL: last init error */
+
+/* Copy + flatten the scene to the device.  Replaces Scene ownership by the render thread
+ * (render.cpp:147-156: loadFromXML -> m_block.init(size, filter)); also (re)allocates and clears
+ * the film. */
+int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
+
+/* Tunables: "pool" (resident path slots), "spp_chunk" (samples per pixel per film batch),
+ * "stats" (1: count node visits / primitive tests), "flush_l2" (bench only). */
+int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);
+
+/* Render sample indices [spp_begin, spp_begin+spp_count) for every pixel and ACCUMULATE them into
+ * the film.  Replaces `for k in spp: tbb::parallel_for(blocks, renderBlock + m_block.put)`
+ * (render.cpp:194-233).  Callable repeatedly (progress / cancel between calls, render.cpp:195-197).
+ * Path (pixel p=(x,y), sample k) uses pcg32.seed(initstate = seed + k, initseq = y*W + x). */
+int nori_gpu_render(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed);
+
+/* Same paths, but return the per-sample radiance instead of splatting: out[(k*H + y)*W + x] =
+ * (r,g,b,valid).  The test hook behind the t-test fixtures (ttest.cpp:151-193). */
+int nori_gpu_render_samples(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed,
+                            float *out_rgba);
+
+int nori_gpu_clear_film(nori_gpu_ctx *ctx);                      /* ImageBlock::clear (render.cpp:155) */
+/* (H+2b)*(W+2b)*4 floats, row-major (r,g,b,w) -- the exact memory image of ImageBlock m_block. */
+int nori_gpu_download_film(nori_gpu_ctx *ctx, float *rgbaw);
+int nori_gpu_upload_film(nori_gpu_ctx *ctx, const float *rgbaw); /* resume / multi-GPU merge      */
+/* Device address of that same array, for zero-copy collectives (torch.distributed / NCCL). */
+int nori_gpu_film_device_ptr(nori_gpu_ctx *ctx, void **dptr, uint64_t *n_floats);
+int nori_gpu_film_dims(const nori_gpu_ctx *ctx, int32_t *rows, int32_t *cols, int32_t *border);
+/* ImageBlock::toBitmap (block.cpp:76-82): H*W*3 floats = rgb / w (0 where w == 0). */
+int nori_gpu_resolve(nori_gpu_ctx *ctx, float *rgb);
+
+/* BVH::rayIntersect on a caller-supplied ray batch (bvh.cpp:404-462), shadow != 0 => any-hit.
+ * For shadow rays only `t` (0 = occluded, +inf = free) and the counters are meaningful. */
+int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out);
+
+/* n floats of pcg32(initstate, initseq).nextFloat() generated on the device (pcg32.h:51-110). */
+int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out);
+/* n raw nextUInt() outputs, for the published pcg32-demo known answers. */
+int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out);
+
+int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out);
+int nori_gpu_reset_stats(nori_gpu_ctx *ctx);
+int nori_gpu_synchronize(nori_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NORI_GPU_H */

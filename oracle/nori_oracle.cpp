@@ -1,0 +1,1121 @@
+/* nori_oracle.cpp -- CPU restatement of the reference's rendering hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped product (the CUDA library behind
+ * include/nori_gpu.h) links, loads or calls this file; only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may.
+ *
+ * What it is: a plain scalar C++ re-statement (no Eigen, no TBB, no virtual dispatch) of the
+ * algorithm the reference (francois141/nori-ray-tracer) runs per camera sample, consuming the same
+ * flat scene description (include/nori_gpu.h) the GPU path consumes.  Every function cites the
+ * reference file:line it follows.  Float arithmetic follows the reference build (x86-64 SSE2, no
+ * FMA: compile with -ffp-contract=off) including Eigen 3.2.90's evaluation order for 3-vectors:
+ * dot(a,b) = a0*b0 + (a1*b1 + a2*b2)  (Redux.h redux_novec_unroller), cross as OrthoMethods.h:36-38,
+ * normalized() = v / sqrt(squaredNorm) with true division (Dot.h:114-120).
+ *
+ * Pinning (see tests/test_oracle_vs_reference.py, tests/golden/):
+ *   - traversal: bit-exact (t,u,v,shape,prim,#nodes,#prims) against ray batches answered by the real
+ *     reference (oracle/_ref/nori_export);
+ *   - pcg32: ext/pcg32/pcg32-demo.out known answers;
+ *   - whole renders: RNG mode 1 below replays the reference's block-sequential sampler mapping
+ *     (one pcg32 per 32x32 block, seeded with the block offset, independent.cpp:48-53,
+ *     render.cpp:96-99) so an oracle render is comparable PIXEL BY PIXEL with a render of the real
+ *     reference binary (oracle/_ref/nori_ref);
+ *   - the reference's t-test known answers (scenes/pa4/tests/*.xml, scenes/pa3/tests/*.xml).
+ * RNG mode 0 is the GPU path's mapping (one stream per camera path), which makes oracle and GPU
+ * comparable SAMPLE BY SAMPLE.
+ */
+#include "nori_gpu.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <atomic>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr float kEps = 1e-4f;                         /* common.h:52 */
+constexpr float kPi = 3.14159265358979323846f;        /* common.h:57 -- M_PI is a FLOAT literal in the reference */
+constexpr float kInvPi = 0.31830988618379067154f;     /* common.h:58 */
+constexpr float kInvFourPi = 0.07957747154594766788f; /* common.h:60 */
+constexpr float kInf = std::numeric_limits<float>::infinity();
+
+
+/* minimal work-sharing loop (std::thread; no OpenMP/TBB dependency). NORI_ORACLE_THREADS overrides. */
+inline int oracleThreads() {
+    const char *e = getenv("NORI_ORACLE_THREADS");
+    int n = e ? atoi(e) : (int) std::thread::hardware_concurrency();
+    return n < 1 ? 1 : n;
+}
+template <typename F> void parallelFor(int64_t n, int64_t grain, F fn) {
+    int nt = oracleThreads();
+    if (nt == 1 || n <= grain) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> ts;
+    for (int t = 0; t < nt; ++t) ts.emplace_back([&]() {
+        for (;;) { int64_t b = next.fetch_add(grain); if (b >= n) break; for (int64_t i = b; i < std::min(n, b + grain); ++i) fn(i); }
+    });
+    for (auto &t : ts) t.join();
+}
+
+/* ------------------------------------------------------------------ 3-vectors, Eigen order --- */
+struct V3 { float x = 0, y = 0, z = 0; V3() {} V3(float a, float b, float c) : x(a), y(b), z(c) {} explicit V3(float a) : x(a), y(a), z(a) {}
+            float operator[](int i) const { return i == 0 ? x : i == 1 ? y : z; } };
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline V3 &operator+=(V3 &a, V3 b) { a = a + b; return a; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+inline float sqnorm(V3 a) { return dot(a, a); }
+inline float norm(V3 a) { return std::sqrt(sqnorm(a)); }
+inline V3 normalized(V3 a) { return a / norm(a); }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 load3(const float *p) { return {p[0], p[1], p[2]}; }
+
+struct P2 { float x = 0, y = 0; };
+
+/* ------------------------------------------------------------------ pcg32 (ext/pcg32/pcg32.h:38-110) */
+struct Pcg32 {
+    uint64_t state, inc;
+    void seed(uint64_t initstate, uint64_t initseq) {         /* pcg32.h:51-57 */
+        state = 0; inc = (initseq << 1) | 1u; nextUInt(); state += initstate; nextUInt();
+    }
+    uint32_t nextUInt() {                                      /* pcg32.h:60-66 */
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xs = (uint32_t) (((old >> 18) ^ old) >> 27), rot = (uint32_t) (old >> 59);
+        return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+    }
+    float nextFloat() {                                        /* pcg32.h:101-110 */
+        uint32_t u = (nextUInt() >> 9) | 0x3f800000u; float f; memcpy(&f, &u, 4); return f - 1.0f;
+    }
+    float next1D() { return nextFloat(); }                     /* independent.cpp:58-60 */
+    /* independent.cpp:62-67 builds Point2f(nextFloat(), nextFloat()); the order of the two calls is
+     * unspecified in C++ and GCC (the reference's and this build's compiler) evaluates constructor
+     * arguments right to left: the FIRST draw lands in y.  Measured with nori_export --seq. */
+    P2 next2D() { P2 p; p.y = nextFloat(); p.x = nextFloat(); return p; }
+};
+
+/* ------------------------------------------------------------------ scene copy ---------------- */
+struct Shape {
+    nori_gpu_shape pod;
+    std::vector<float> V, N, UV, cdf; std::vector<uint32_t> F;
+};
+struct Emitter {
+    nori_gpu_emitter pod;
+    std::vector<float> image, pdf, cdf, pm, cm;
+};
+struct Scene {
+    nori_gpu_scene pod;
+    std::vector<nori_gpu_bvh_node> nodes; std::vector<uint32_t> indices, shapeOffset;
+    std::vector<Shape> shapes; std::vector<nori_gpu_bsdf> bsdfs; std::vector<Emitter> emitters;
+    int border = 0; float lookupFactor = 0;
+    /* counters (single-threaded use or relaxed adds; only used for reporting) */
+    uint64_t rays = 0, shadowRays = 0, nodesVisited = 0, primsTested = 0, samples = 0, invalid = 0;
+};
+
+struct Ray {                                /* ray.h:38-100 */
+    V3 o, d, dRcp; float mint = kEps, maxt = kInf;
+    Ray() {}
+    Ray(V3 o_, V3 d_) : o(o_), d(d_) { update(); }
+    Ray(V3 o_, V3 d_, float a, float b) : o(o_), d(d_), mint(a), maxt(b) { update(); }
+    void update() { dRcp = V3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }     /* cwiseInverse, ray.h:73-75 */
+    V3 at(float t) const { return o + t * d; }
+};
+
+struct Frame { V3 s, t, n; };               /* frame.h:33-60 */
+struct Its {                                /* shape.h:38-67 */
+    V3 p; float t = kInf; P2 uv; Frame sh, geo; int shape = -1; uint32_t prim = 0;
+    float baryU = 0, baryV = 0; uint32_t nodes = 0, prims = 0;
+};
+
+/* common.cpp:274-283 */
+inline void coordinateSystem(V3 a, V3 &b, V3 &c) {
+    if (std::abs(a.x) > std::abs(a.y)) {
+        float invLen = 1.0f / std::sqrt(a.x * a.x + a.z * a.z);
+        c = V3(a.z * invLen, 0.0f, -a.x * invLen);
+    } else {
+        float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z);
+        c = V3(0.0f, a.z * invLen, -a.y * invLen);
+    }
+    b = cross(c, a);
+}
+inline Frame makeFrame(V3 n) { Frame f; f.n = n; coordinateSystem(n, f.s, f.t); return f; }   /* frame.h:49-51 */
+inline V3 toLocal(const Frame &f, V3 v) { return {dot(v, f.s), dot(v, f.t), dot(v, f.n)}; }   /* frame.h:54-58 */
+inline V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }          /* frame.h:61-63 */
+
+/* ------------------------------------------------------------------ intersection kernels ------ */
+/* bbox.h:336-363 */
+inline bool boxHit(const nori_gpu_bvh_node &nd, const Ray &r) {
+    float nearT = -kInf, farT = kInf;
+    for (int i = 0; i < 3; i++) {
+        float origin = r.o[i], minVal = nd.bmin[i], maxVal = nd.bmax[i];
+        if (r.d[i] == 0) { if (origin < minVal || origin > maxVal) return false; }
+        else {
+            float t1 = (minVal - origin) * r.dRcp[i], t2 = (maxVal - origin) * r.dRcp[i];
+            if (t1 > t2) std::swap(t1, t2);
+            nearT = std::max(t1, nearT); farT = std::min(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return r.mint <= farT && nearT <= r.maxt;
+}
+
+/* mesh.cpp:83-120 */
+inline bool triHit(const Shape &m, uint32_t index, const Ray &ray, float &u, float &v, float &t) {
+    uint32_t i0 = m.F[3 * index], i1 = m.F[3 * index + 1], i2 = m.F[3 * index + 2];
+    V3 p0 = load3(&m.V[3 * i0]), p1 = load3(&m.V[3 * i1]), p2 = load3(&m.V[3 * i2]);
+    V3 edge1 = p1 - p0, edge2 = p2 - p0;
+    V3 pvec = cross(ray.d, edge2);
+    float det = dot(edge1, pvec);
+    if (det > -1e-8f && det < 1e-8f) return false;
+    float inv_det = 1.0f / det;
+    V3 tvec = ray.o - p0;
+    u = dot(tvec, pvec) * inv_det;
+    if (u < 0.0 || u > 1.0) return false;
+    V3 qvec = cross(tvec, edge1);
+    v = dot(ray.d, qvec) * inv_det;
+    if (v < 0.0 || u + v > 1.0) return false;
+    t = dot(edge2, qvec) * inv_det;
+    return t >= ray.mint && t <= ray.maxt;
+}
+
+/* sphere.cpp:43-76 (b is formed in double: 2.0 * float, exact) */
+inline bool sphereHit(const Shape &s, const Ray &ray, float &t) {
+    V3 oc = ray.o - load3(s.pod.center);
+    float a = dot(ray.d, ray.d);
+    float b = (float) (2.0 * dot(oc, ray.d));
+    float c = dot(oc, oc) - s.pod.radius * s.pod.radius;
+    float discriminant = (b * b - 4 * a * c);
+    if (!(discriminant > 0)) return false;
+    float delta = std::sqrt(b * b - 4 * a * c);
+    float t1 = (-b - delta) / (2 * a), t2 = (-b + delta) / (2 * a);
+    if (ray.mint <= t1 && t1 <= ray.maxt) { t = t1; return true; }
+    if (ray.mint <= t2 && t2 <= ray.maxt) { t = t2; return true; }
+    return false;
+}
+
+/* bvh.h:105-109 */
+inline uint32_t findShape(const Scene &sc, uint32_t &idx) {
+    auto it = std::lower_bound(sc.shapeOffset.begin(), sc.shapeOffset.end(), idx + 1) - 1;
+    idx -= *it;
+    return (uint32_t) (it - sc.shapeOffset.begin());
+}
+
+/* mesh.cpp:122-170, sphere.cpp:78-93 */
+void setHitInformation(const Scene &sc, const Ray &ray, Its &its) {
+    const Shape &m = sc.shapes[its.shape];
+    if (m.pod.type == NORI_SHAPE_MESH) {
+        float b1 = its.baryU, b2 = its.baryV, b0 = 1 - (b1 + b2);
+        uint32_t i0 = m.F[3 * its.prim], i1 = m.F[3 * its.prim + 1], i2 = m.F[3 * its.prim + 2];
+        V3 p0 = load3(&m.V[3 * i0]), p1 = load3(&m.V[3 * i1]), p2 = load3(&m.V[3 * i2]);
+        its.p = (b0 * p0 + b1 * p1) + b2 * p2;
+        its.uv.x = b1; its.uv.y = b2;
+        if (!m.UV.empty()) {
+            its.uv.x = (b0 * m.UV[2 * i0] + b1 * m.UV[2 * i1]) + b2 * m.UV[2 * i2];
+            its.uv.y = (b0 * m.UV[2 * i0 + 1] + b1 * m.UV[2 * i1 + 1]) + b2 * m.UV[2 * i2 + 1];
+        }
+        its.geo = makeFrame(normalized(cross(p1 - p0, p2 - p0)));
+        if (!m.N.empty()) {
+            V3 n = (b0 * load3(&m.N[3 * i0]) + b1 * load3(&m.N[3 * i1])) + b2 * load3(&m.N[3 * i2]);
+            its.sh = makeFrame(normalized(n));
+        } else its.sh = its.geo;
+    } else {
+        /* by now ray.maxt == its.t (bvh.cpp:444) */
+        V3 c = load3(m.pod.center);
+        its.p = ray.o + its.t * ray.d;
+        V3 n = normalized(its.p - c);
+        its.sh = its.geo = makeFrame(n);
+        /* sphericalCoordinates, common.cpp:264-272 */
+        float th = std::acos(n.z), ph = std::atan2(n.y, n.x);
+        if (ph < 0) ph += 2 * kPi;
+        its.uv.x = (float) (0.5 + th / (2 * kPi));
+        its.uv.y = ph / kPi;
+    }
+}
+
+/* bvh.cpp:404-462 */
+bool rayIntersect(Scene &sc, const Ray &_ray, Its &its, bool shadowRay, bool count = true) {
+    uint32_t node_idx = 0, stack_idx = 0, stack[64];
+    its.t = kInf; its.shape = -1; its.nodes = its.prims = 0;
+    Ray ray(_ray);
+    if (count) { __atomic_fetch_add(&sc.rays, 1, __ATOMIC_RELAXED); if (shadowRay) __atomic_fetch_add(&sc.shadowRays, 1, __ATOMIC_RELAXED); }
+    if (ray.mint == kEps)
+        ray.mint = std::max(ray.mint, ray.mint * std::max(std::abs(ray.o.x), std::max(std::abs(ray.o.y), std::abs(ray.o.z))));
+    if (sc.nodes.empty() || ray.maxt < ray.mint) return false;
+    bool found = false;
+    while (true) {
+        const nori_gpu_bvh_node &node = sc.nodes[node_idx];
+        ++its.nodes;
+        if (!boxHit(node, ray)) {
+            if (stack_idx == 0) break;
+            node_idx = stack[--stack_idx];
+            continue;
+        }
+        if (!(node.data[0] & 1u)) {                       /* inner: left child first, always */
+            stack[stack_idx++] = node.data[1];
+            node_idx++;
+        } else {
+            uint32_t start = node.data[1], end = start + (node.data[0] >> 1);
+            for (uint32_t i = start; i < end; ++i) {
+                uint32_t idx = sc.indices[i];
+                uint32_t s = findShape(sc, idx);
+                float u = 0, v = 0, t = 0;
+                ++its.prims;
+                const Shape &shp = sc.shapes[s];
+                bool hit = shp.pod.type == NORI_SHAPE_MESH ? triHit(shp, idx, ray, u, v, t) : sphereHit(shp, ray, t);
+                if (hit) {
+                    if (shadowRay) { its.t = 0; goto done_shadow; }
+                    found = true;
+                    ray.maxt = its.t = t;
+                    its.baryU = shp.pod.type == NORI_SHAPE_MESH ? u : 0.f;
+                    its.baryV = shp.pod.type == NORI_SHAPE_MESH ? v : 0.f;
+                    its.shape = (int) s; its.prim = idx;
+                }
+            }
+            if (stack_idx == 0) break;
+            node_idx = stack[--stack_idx];
+        }
+    }
+    if (count) { __atomic_fetch_add(&sc.nodesVisited, its.nodes, __ATOMIC_RELAXED); __atomic_fetch_add(&sc.primsTested, its.prims, __ATOMIC_RELAXED); }
+    if (found) setHitInformation(sc, ray, its);
+    return found;
+done_shadow:
+    if (count) { __atomic_fetch_add(&sc.nodesVisited, its.nodes, __ATOMIC_RELAXED); __atomic_fetch_add(&sc.primsTested, its.prims, __ATOMIC_RELAXED); }
+    return true;
+}
+inline bool occluded(Scene &sc, const Ray &r) { Its tmp; return rayIntersect(sc, r, tmp, true); }   /* scene.h:112-115 */
+
+/* ------------------------------------------------------------------ warps (src/warp.cpp) ------- */
+inline V3 squareToUniformSphere(P2 s) {                       /* warp.cpp:86-91 */
+    float theta = std::acos(1 - 2 * (1 - s.x));
+    float phi = 2.f * kPi * s.y;
+    return V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+}
+inline V3 squareToCosineHemisphere(P2 s) {                    /* warp.cpp:110-115 */
+    float theta = std::acos(std::sqrt(1 - (1 - s.x)));
+    float phi = 2.f * kPi * s.y;
+    return V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+}
+inline V3 squareToBeckmann(P2 s, float alpha) {               /* warp.cpp:122-127 */
+    float theta = (float) std::atan(std::sqrt(-std::pow((double) alpha, 2) * std::log(1 - s.x)));
+    float phi = 2 * kPi * s.y;
+    return V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+}
+inline V3 squareToUniformTriangle(P2 s) {                     /* warp.cpp:135-140 */
+    float su1 = sqrtf(s.x); float u = 1.f - su1, v = s.y * su1;
+    return V3(u, v, 1.f - u - v);
+}
+inline P2 squareToConcentricDisk(P2 s) {                      /* warp.cpp:143-162 */
+    float ox = 2.f * s.x - 1.f, oy = 2.f * s.y - 1.f; P2 r;
+    if (ox == 0 && oy == 0) return r;
+    float theta, rad;
+    if (std::abs(ox) > std::abs(oy)) { rad = ox; theta = kPi * 0.25f * (oy / ox); }
+    else { rad = oy; theta = kPi * 0.5f - kPi * 0.25f * (ox / oy); }
+    r.x = rad * std::cos(theta); r.y = rad * std::sin(theta); return r;
+}
+inline V3 squareToGTR2(P2 s, float alpha) {                   /* warp.cpp:180-185 */
+    float a2 = (float) std::pow((double) alpha, 2);
+    float theta = std::acos(std::sqrt((1.0f - s.x) / (1.0f + (a2 - 1.0f) * s.x)));
+    float phi = 2 * kPi * s.y;
+    return V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+}
+inline float squareToGTR2Pdf(V3 m, float alpha) {             /* warp.cpp:187-193 */
+    float a2 = (float) std::pow((double) alpha, 2);
+    float cosTheta = m.z;
+    float pdf = (float) (a2 * cosTheta * kInvPi / std::pow(1 + (a2 - 1.0f) * std::pow((double) cosTheta, 2), 2));
+    return (cosTheta >= 0 && std::abs(sqnorm(m) - 1.0f) < 1.0f) ? pdf : 0.0f;
+}
+
+/* common.cpp:285-314 */
+float fresnel(float cosThetaI, float extIOR, float intIOR) {
+    float etaI = extIOR, etaT = intIOR;
+    if (extIOR == intIOR) return 0.0f;
+    if (cosThetaI < 0.0f) { std::swap(etaI, etaT); cosThetaI = -cosThetaI; }
+    float eta = etaI / etaT, sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
+    if (sinThetaTSqr > 1.0f) return 1.0f;
+    float cosThetaT = std::sqrt(1.0f - sinThetaTSqr);
+    float Rs = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    float Rp = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    return (Rs * Rs + Rp * Rp) / 2.0f;
+}
+
+inline float tanTheta(V3 v) { float temp = 1 - v.z * v.z; if (temp <= 0.0f) return 0.0f; return std::sqrt(temp) / v.z; }  /* frame.h:81-86 */
+
+/* ------------------------------------------------------------------ BSDFs ---------------------- */
+enum Measure { EUnknown = 0, ESolidAngle = 1, EDiscrete = 2 };
+struct BRec { V3 wi, wo; float eta = 0; int measure = EUnknown; P2 uv; };     /* bsdf.h:30-58 */
+
+inline V3 albedoAt(const nori_gpu_bsdf &b, P2 uv) {
+    if (b.albedo_texture == NORI_TEXTURE_CHECKERBOARD) {                      /* checkerboard.cpp:31-37 */
+        int x = (int) std::abs(std::floor(uv.x / b.tex_scale[0] - b.tex_delta[0]));
+        int y = (int) std::abs(std::floor(uv.y / b.tex_scale[1] - b.tex_delta[1]));
+        return x % 2 == y % 2 ? load3(b.albedo) : load3(b.albedo2);
+    }
+    return load3(b.albedo);                                                   /* consttexture.cpp:30-32 */
+}
+
+/* microfacet.cpp:52-82 */
+inline float evalBeckmann(float alpha, V3 m) {
+    float temp = tanTheta(m) / alpha, ct = m.z, ct2 = ct * ct;
+    return std::exp(-temp * temp) / (kPi * alpha * alpha * ct2 * ct2);
+}
+inline float smithBeckmannG1(float alpha, V3 v, V3 m) {
+    float tt = tanTheta(v);
+    if (tt == 0.0f) return 1.0f;
+    if (dot(m, v) * v.z <= 0) return 0.0f;
+    float a = 1.0f / (alpha * tt);
+    if (a >= 1.6f) return 1.0f;
+    float a2 = a * a;
+    return (3.535f * a + 2.181f * a2) / (1.0f + 2.276f * a + 2.577f * a2);
+}
+
+/* disney.cpp:26-44 */
+inline float schlickFresnel(float u) { float m = std::min(1.0f, std::max(0.0f, 1 - u)); return (float) std::pow((double) m, 5); }
+inline float ggx(float NdotV, float alphaG) { float a = alphaG * alphaG, b = NdotV * NdotV; return 1 / (NdotV + std::sqrt(a + b - a * b)); }
+inline V3 lerp3(float t, V3 a, V3 b) { return (1.0f - t) * a + t * b; }
+inline float luminance(V3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }   /* common.cpp:233-235 */
+
+V3 bsdfEval(const nori_gpu_bsdf &b, const BRec &r) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE:                                                   /* diffuse.cpp:72-82 */
+        if (r.measure != ESolidAngle || r.wi.z <= 0 || r.wo.z <= 0) return V3(0.f);
+        return albedoAt(b, r.uv) * kInvPi;
+    case NORI_BSDF_MICROFACET: {                                              /* microfacet.cpp:84-94 */
+        V3 n = normalized(r.wi + r.wo);
+        float D = evalBeckmann(b.alpha, n);
+        float F = fresnel(dot(n, r.wi), b.extIOR, b.intIOR);
+        float G = smithBeckmannG1(b.alpha, r.wi, n) * smithBeckmannG1(b.alpha, r.wo, n);
+        float denom = 4.0f * r.wi.z * r.wo.z;
+        float spec = b.ks * D * F * G / denom;
+        V3 kd = load3(b.kd) * kInvPi;
+        return V3(kd.x + spec, kd.y + spec, kd.z + spec);
+    }
+    case NORI_BSDF_DISNEY: {                                                  /* disney.cpp:63-105 */
+        float NdotV = r.wi.z, NdotL = r.wo.z;
+        if (NdotV < 0 || NdotL < 0) return V3(0.f);
+        V3 wh = normalized(r.wi + r.wo);
+        float LdotH = dot(r.wo, wh), VdotH = dot(r.wi, wh);
+        V3 base = load3(b.baseColor), white(1.f);
+        float lum = luminance(base);
+        V3 Ctint = lum > 0.f ? V3(base.x / lum, base.y / lum, base.z / lum) : V3(1.0f);
+        V3 CtintMix = (float) (b.specular * 0.08) * lerp3(b.specularTint, white, Ctint);
+        V3 Cspec = lerp3(b.metallic, CtintMix, base);
+        float fd90 = (float) (0.5 + 2 * b.roughness * std::pow((double) VdotH, 2));
+        float fl = schlickFresnel(NdotL), fv = schlickFresnel(NdotV);
+        V3 diffuse = base * kInvPi * (1.f + (fd90 - 1.f) * fl) * (1.f + (fd90 - 1.f) * fv);
+        float alpha = std::max(0.001f, b.roughness * b.roughness);
+        float Ds = squareToGTR2Pdf(wh, alpha);
+        float FH = schlickFresnel(LdotH);
+        V3 Fs = lerp3(FH, Cspec, white);
+        float Gs = ggx(NdotL, alpha) * ggx(NdotV, alpha);
+        V3 specular = Gs * Fs * Ds;
+        V3 Fsheen = FH * b.sheen * lerp3(b.sheenTint, white, Ctint);
+        return (1 - b.metallic) * (diffuse + Fsheen) + specular;
+    }
+    default: return V3(0.f);                                                  /* mirror.cpp:29-32, dielectric.cpp:35-38 */
+    }
+}
+
+float bsdfPdf(const nori_gpu_bsdf &b, const BRec &r) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE:                                                   /* diffuse.cpp:85-101 */
+        if (r.measure != ESolidAngle || r.wi.z <= 0 || r.wo.z <= 0) return 0.0f;
+        return kInvPi * r.wo.z;
+    case NORI_BSDF_MICROFACET: {                                              /* microfacet.cpp:97-111 */
+        float c = r.wo.z; if (c <= 0.0f) return 0.0f;
+        V3 n = normalized(r.wi + r.wo);
+        float metallicTerm = evalBeckmann(b.alpha, n) * n.z / (4.0f * std::abs(dot(n, r.wo)));
+        return b.ks * metallicTerm + (1 - b.ks) * (c * kInvPi);
+    }
+    case NORI_BSDF_DISNEY: {                                                  /* disney.cpp:108-121 */
+        float c = r.wo.z; if (c <= 0.0f) return 0.0f;
+        V3 n = normalized(r.wi + r.wo);
+        float metallicTerm = squareToGTR2Pdf(n, b.alpha) * n.z / (4.0f * std::abs(dot(n, r.wo)));
+        return (1 - b.metallic) * (c * kInvPi) + b.metallic * metallicTerm;
+    }
+    default: return 0.0f;
+    }
+}
+
+V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE:                                                   /* diffuse.cpp:104-120 */
+        if (r.wi.z <= 0) return V3(0.f);
+        r.measure = ESolidAngle; r.wo = squareToCosineHemisphere(s); r.eta = 1.0f;
+        return albedoAt(b, r.uv);
+    case NORI_BSDF_MIRROR:                                                    /* mirror.cpp:39-55 */
+        if (r.wi.z <= 0) return V3(0.f);
+        r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z); r.measure = EDiscrete; r.eta = 1.0f;
+        return V3(1.f);
+    case NORI_BSDF_DIELECTRIC: {                                              /* dielectric.cpp:45-73 */
+        float theta = r.wi.z; V3 nv(0, 0, 1.0f);
+        if (fresnel(theta, b.extIOR, b.intIOR) > s.x) { r.eta = 1.0f; r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z); }
+        else {
+            float factor = b.extIOR / b.intIOR;
+            if (theta < 0.0f) { factor = 1 / factor; nv.z *= -1; }
+            float win = dot(r.wi, nv);
+            V3 part1 = -factor * (r.wi - win * nv);
+            V3 part2 = -nv * (float) std::sqrt(1 - std::pow((double) factor, 2) * (1 - std::pow((double) win, 2)));
+            r.wo = normalized(part1 + part2);
+            r.eta = b.extIOR / b.intIOR;
+        }
+        r.measure = EDiscrete;
+        return V3(1.f);
+    }
+    case NORI_BSDF_MICROFACET: {                                              /* microfacet.cpp:114-137 */
+        if (r.wi.z <= 0.0f) return V3(0.f);
+        if (s.x < b.ks) {
+            P2 ns; ns.x = s.x / b.ks; ns.y = s.y;
+            V3 n = squareToBeckmann(ns, b.alpha);
+            r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
+        } else {
+            P2 ns; ns.x = (s.x - b.ks) / (1.f - b.ks); ns.y = s.y;
+            r.wo = squareToCosineHemisphere(ns);
+        }
+        float c = r.wo.z; if (c <= 0.f) return V3(0.f);
+        return bsdfEval(b, r) * c / bsdfPdf(b, r);
+    }
+    case NORI_BSDF_DISNEY: {                                                  /* disney.cpp:124-145 */
+        if (r.wi.z <= 0.0f) return V3(0.f);
+        if (s.x <= b.metallic) {
+            P2 ns; ns.x = s.x / b.metallic; ns.y = s.y;
+            V3 n = squareToGTR2(ns, b.alpha);
+            r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
+        } else {
+            P2 ns; ns.x = (s.x - b.metallic) / (1 - b.metallic); ns.y = s.y;
+            r.wo = squareToCosineHemisphere(ns);
+        }
+        float c = r.wo.z; if (c <= 0.0f) return V3(0.f);
+        return bsdfEval(b, r) * c / bsdfPdf(b, r);
+    }
+    }
+    return V3(0.f);
+}
+
+/* ------------------------------------------------------------------ emitters ------------------- */
+struct ERec { V3 ref, p, n, wi; float pdf = 0; Ray shadowRay; };               /* emitter.h:31-59 */
+inline ERec makeERec(V3 ref, V3 p, V3 n) { ERec e; e.ref = ref; e.p = p; e.n = n; e.wi = normalized(p - ref); return e; }
+
+/* dpdf.h:119-157 */
+inline size_t cdfSampleReuse(const std::vector<float> &cdf, float &s) {
+    auto entry = std::lower_bound(cdf.begin(), cdf.end(), s);
+    size_t index = (size_t) std::max((ptrdiff_t) 0, entry - cdf.begin() - 1);
+    index = std::min(index, cdf.size() - 2);
+    s = (s - cdf[index]) / (cdf[index + 1] - cdf[index]);
+    return index;
+}
+
+/* mesh.cpp:40-61, sphere.cpp:95-105 */
+void sampleSurface(const Shape &m, P2 s, V3 &p, V3 &n, float &pdf) {
+    if (m.pod.type == NORI_SHAPE_MESH) {
+        size_t idT = cdfSampleReuse(m.cdf, s.x);
+        V3 bc = squareToUniformTriangle(s);
+        uint32_t i0 = m.F[3 * idT], i1 = m.F[3 * idT + 1], i2 = m.F[3 * idT + 2];
+        V3 p0 = load3(&m.V[3 * i0]), p1 = load3(&m.V[3 * i1]), p2 = load3(&m.V[3 * i2]);
+        p = (bc.x * p0 + bc.y * p1) + bc.z * p2;
+        if (!m.N.empty()) n = normalized((bc.x * load3(&m.N[3 * i0]) + bc.y * load3(&m.N[3 * i1])) + bc.z * load3(&m.N[3 * i2]));
+        else n = normalized(cross(p1 - p0, p2 - p0));
+        pdf = m.pod.area_normalization;
+    } else {
+        V3 q = squareToUniformSphere(s);
+        p = load3(m.pod.center) + m.pod.radius * q; n = q;
+        pdf = (float) (std::pow((double) (1.f / m.pod.radius), 2) * (0.25f * kInvPi));
+    }
+}
+inline float pdfSurface(const Shape &m) {
+    return m.pod.type == NORI_SHAPE_MESH ? m.pod.area_normalization
+        : (float) (std::pow((double) (1.f / m.pod.radius), 2) * (0.25f * kInvPi));
+}
+
+/* envmap.cpp:60-88 */
+inline P2 envMapIntersect(const Emitter &e, V3 vec) {
+    float th = std::acos(vec.z), ph = std::atan2(vec.y, vec.x);
+    if (ph < 0) ph += 2 * kPi;
+    P2 r; r.x = th * (e.pod.env_rows - 1) * kInvPi; r.y = (float) (ph * 0.5 * (e.pod.env_cols - 1) * kInvPi);
+    if (std::isnan(r.x) || std::isnan(r.y)) { r.x = r.y = 0; }
+    return r;
+}
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+V3 emitterEval(const Scene &sc, const Emitter &e, const ERec &l) {
+    switch (e.pod.type) {
+    case NORI_EMITTER_AREA:                                                   /* arealight.cpp:39-44 */
+        return dot(l.n, -l.wi) > 0.0f ? load3(e.pod.radiance) : V3(0.f);
+    case NORI_EMITTER_POINT:                                                  /* pointlight.cpp:26-29 */
+        return load3(e.pod.radiance) / (4.f * kPi * sqnorm(load3(e.pod.position) - l.ref));
+    case NORI_EMITTER_SPOT: {                                                 /* spotlight.cpp:38-42 */
+        V3 c = load3(e.pod.radiance) / (4.f * kPi);
+        return c * 2 * kPi * (float) (1 - 0.5 * (e.pod.cosFalloffStart + e.pod.cosTotalWidth));
+    }
+    case NORI_EMITTER_ENVMAP: {                                               /* envmap.cpp:124-156 */
+        P2 uv = envMapIntersect(e, normalized(l.wi));
+        int W = e.pod.env_rows, H = e.pod.env_cols;
+        int u = clampi((int) uv.x, 0, W - 1), v = clampi((int) uv.y, 0, H - 1);
+        int us = (u + 1) % W, vs = (v + 1) % H;
+        auto px = [&](int i, int j) { return load3(&e.image[((size_t) i * H + j) * 3]); };
+        V3 BL = px(u, v), UL = px(u, vs), BR = px(us, v), UR = px(us, vs);
+        int dusu = us - u, dvsv = vs - v;
+        float dusum = us - uv.x, dumu = uv.x - u, dvmv = uv.y - v, dvsvm = vs - uv.y;
+        float k = (float) (1.0 / (dusu * dvsv));
+        return e.pod.weight * (k * ((BL * dusum * dvsvm) + (BR * dumu * dvsvm) + (UL * dusum * dvmv) + (UR * dumu * dvmv)));
+    }
+    }
+    return V3(0.f);
+}
+
+float emitterPdf(const Scene &sc, const Emitter &e, const ERec &l) {
+    switch (e.pod.type) {
+    case NORI_EMITTER_AREA:                                                   /* arealight.cpp:64-76 */
+        return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.pod.shape]) : 0.0f;
+    case NORI_EMITTER_POINT: return 1.0f;                                     /* pointlight.cpp:30-33 */
+    case NORI_EMITTER_SPOT: return l.pdf;                                     /* spotlight.cpp:44-47 */
+    case NORI_EMITTER_ENVMAP: {                                               /* envmap.cpp:184-192 */
+        P2 its = envMapIntersect(e, normalized(l.wi));
+        int i = clampi((int) its.x, 0, e.pod.env_rows - 1), j = clampi((int) its.y, 0, e.pod.env_cols - 1);
+        return e.pm[i] * e.pdf[(size_t) i * e.pod.env_cols + j];
+    }
+    }
+    return 0.f;
+}
+
+/* envmap.cpp:112-121; reads one past the table in the reference when no interval matches -- here the
+ * search stops at the last valid interval instead (documented deviation) */
+inline void envSample1D(const float *pfRow, const float *PfRow, int nPf, float s, float &x, float &prob) {
+    int i;
+    for (i = 0; i < nPf - 2; i++)
+        if (PfRow[i] <= s && s < PfRow[i + 1]) break;
+    float t = (PfRow[i + 1] - s) / (PfRow[i + 1] - PfRow[i]);
+    x = (1 - t) * i + t * (i + 1);
+    prob = pfRow[i];
+}
+
+V3 emitterSample(const Scene &sc, const Emitter &e, ERec &l, P2 s) {
+    switch (e.pod.type) {
+    case NORI_EMITTER_AREA: {                                                 /* arealight.cpp:46-62 */
+        float spdf;
+        sampleSurface(sc.shapes[e.pod.shape], s, l.p, l.n, spdf);
+        l.wi = normalized(l.p - l.ref);
+        l.shadowRay = Ray(l.ref, l.wi, kEps, norm(l.p - l.ref) - kEps);
+        l.pdf = emitterPdf(sc, e, l);
+        float att = dot(l.n, -l.wi) / sqnorm(l.p - l.ref);
+        return l.pdf > 0.0f ? emitterEval(sc, e, l) * att / emitterPdf(sc, e, l) : V3(0.f);
+    }
+    case NORI_EMITTER_POINT: {                                                /* pointlight.cpp:15-24 */
+        V3 pos = load3(e.pod.position);
+        l.wi = normalized(pos - l.ref); l.p = pos; l.pdf = 1.0f;
+        l.shadowRay = Ray(l.ref, l.wi, kEps, norm(pos - l.ref) - kEps);
+        return load3(e.pod.radiance) / (4.f * kPi * sqnorm(pos - l.ref));
+    }
+    case NORI_EMITTER_SPOT: {                                                 /* spotlight.cpp:19-36 */
+        V3 pos = load3(e.pod.position), dir = load3(e.pod.direction);
+        l.wi = normalized(pos - l.ref); l.p = pos; l.pdf = 1.0f; l.n = dir;
+        l.shadowRay = Ray(l.ref, l.wi, kEps, norm(pos - l.ref) - kEps);
+        float cosTheta = dot(dir, normalized(-l.wi)), fall;
+        if (cosTheta < e.pod.cosTotalWidth) fall = 0;
+        else if (cosTheta > e.pod.cosFalloffStart) fall = 1;
+        else fall = (std::acos(e.pod.cosTotalWidth) - std::acos(cosTheta)) / (std::acos(e.pod.cosTotalWidth) - std::acos(e.pod.cosFalloffStart));
+        return load3(e.pod.radiance) * fall / (4.f * kPi * sqnorm(l.ref - l.p));
+    }
+    case NORI_EMITTER_ENVMAP: {                                               /* envmap.cpp:158-181 */
+        int W = e.pod.env_rows, H = e.pod.env_cols;
+        float st2 = 1.0f - l.wi.z * l.wi.z, sinTheta = st2 <= 0.0f ? 0.0f : std::sqrt(st2);   /* lRec.wi still 0 => 1 */
+        float jacobian = (float) ((H - 1) * (W - 1) / (2 * std::pow((double) kPi, 2) * sinTheta));
+        float u, v, up, vp;
+        envSample1D(e.pm.data(), e.cm.data(), W + 1, s.x, u, up);
+        int row = clampi((int) u, 0, W - 1);                                  /* reference indexes row (int)u unclamped */
+        envSample1D(&e.pdf[(size_t) row * H], &e.cdf[(size_t) row * (H + 1)], H + 1, s.y, v, vp);
+        float theta = u * kPi / (W - 1), phi = v * 2 * kPi / (H - 1);
+        l.wi = normalized(V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)));
+        l.shadowRay = Ray(l.ref, l.wi, kEps, 100000.f);
+        vp = emitterPdf(sc, e, l) * jacobian;
+        return emitterEval(sc, e, l) / vp;
+    }
+    }
+    return V3(0.f);
+}
+
+/* ------------------------------------------------------------------ cameras -------------------- */
+inline V3 xfPoint(const float *m, V3 p) {                                     /* transform.h:78-81 */
+    float r[4];
+    for (int i = 0; i < 4; ++i) r[i] = ((m[4 * i] * p.x + m[4 * i + 1] * p.y) + m[4 * i + 2] * p.z) + m[4 * i + 3] * 1.0f;
+    return V3(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
+}
+inline V3 xfVector(const float *m, V3 v) {                                    /* transform.h:68-70 */
+    return V3((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+}
+
+/* perspective.cpp:90-112, thinlens.cpp:126-171 */
+void sampleRay(const nori_gpu_camera &c, Ray &ray, P2 ps, P2 as) {
+    V3 nearP = xfPoint(c.sampleToCamera, V3(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
+    V3 d = normalized(nearP);
+    float invZ = 1.0f / d.z;
+    if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
+        P2 disk = squareToConcentricDisk(as);
+        float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
+        float ft = c.focalDistance / d.z;
+        V3 pFocus = V3(0.f) + ft * d;
+        V3 o(lx, ly, 0.0f);
+        V3 dir = normalized(pFocus - o);
+        ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+    } else {
+        ray.o = xfPoint(c.cameraToWorld, V3(0, 0, 0)); ray.d = xfVector(c.cameraToWorld, d);
+    }
+    ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
+    ray.update();
+}
+
+/* ------------------------------------------------------------------ integrators ---------------- */
+inline const Emitter &randomEmitter(const Scene &sc, float rnd) {            /* scene.h:68-74 */
+    size_t n = sc.emitters.size();
+    size_t index = std::min(static_cast<size_t>(std::floor(n * rnd)), n - 1);
+    return sc.emitters[index];
+}
+inline const nori_gpu_bsdf &bsdfOf(const Scene &sc, const Its &its) { return sc.bsdfs[sc.shapes[its.shape].pod.bsdf]; }
+inline int emitterOf(const Scene &sc, const Its &its) { return sc.shapes[its.shape].pod.emitter; }
+
+V3 LiPathMis(Scene &sc, Pcg32 &rng, const Ray &ray) {                         /* path_mis.cpp:17-101 */
+    V3 color(0.f), att(1.f); Ray cur = ray; float w_mats = 1.0f; Its its;
+    if (!rayIntersect(sc, cur, its, false)) return color;
+    const size_t nLights = sc.emitters.size();
+    while (true) {
+        if (emitterOf(sc, its) >= 0) {
+            ERec e = makeERec(cur.o, its.p, its.sh.n);
+            color += att * w_mats * emitterEval(sc, sc.emitters[emitterOf(sc, its)], e);
+        }
+        const Emitter &light = randomEmitter(sc, rng.next1D());
+        ERec e; e.ref = its.p;
+        V3 Li = emitterSample(sc, light, e, rng.next2D()) * (float) nLights;
+        float pdf_em = emitterPdf(sc, light, e);
+        if (!occluded(sc, e.shadowRay)) {
+            float theta = std::max(0.0f, toLocal(its.sh, e.wi).z);
+            BRec b; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle; b.uv = its.uv;
+            V3 f = bsdfEval(bsdfOf(sc, its), b);
+            float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
+            float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+            color += att * w_ems * f * theta * Li;
+        }
+        float p = std::min(att.x, 0.99f);
+        if (rng.next1D() > p) return color;
+        att = att / p;
+        BRec b; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
+        V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
+        att = att * w;
+        cur = Ray(its.p, toWorld(its.sh, b.wo));
+        float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
+        V3 origin = its.p;
+        if (!rayIntersect(sc, cur, its, false)) return color;
+        if (emitterOf(sc, its) >= 0) {
+            ERec e2 = makeERec(origin, its.p, its.sh.n);
+            float pdf_em2 = emitterPdf(sc, sc.emitters[emitterOf(sc, its)], e2);
+            w_mats = pdf_mat + pdf_em2 > 0.f ? pdf_mat / (pdf_mat + pdf_em2) : pdf_mat;
+        }
+        if (b.measure == EDiscrete) w_mats = 1.0f;
+    }
+}
+
+V3 LiPathMats(Scene &sc, Pcg32 &rng, const Ray &ray) {                        /* path_mats.cpp:18-60 */
+    V3 color(0.f), att(1.f); Ray cur = ray;
+    while (true) {
+        Its its;
+        if (!rayIntersect(sc, cur, its, false)) return color;
+        if (emitterOf(sc, its) >= 0) {
+            ERec e = makeERec(cur.o, its.p, its.sh.n);
+            color += att * emitterEval(sc, sc.emitters[emitterOf(sc, its)], e);
+        }
+        float p = std::min(att.x, 0.99f);
+        if (rng.next1D() > p) return color;
+        att = att / p;
+        BRec b; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
+        V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
+        att = att * w;
+        cur = Ray(its.p, toWorld(its.sh, b.wo));
+    }
+}
+
+V3 LiDirect(Scene &sc, Pcg32 &rng, const Ray &ray, int kind) {
+    Its its;
+    if (!rayIntersect(sc, ray, its, false)) return V3(0.f);
+    V3 color(0.f);
+    if (kind != NORI_INTEGRATOR_DIRECT && emitterOf(sc, its) >= 0) {          /* direct_ems.cpp:27-30 etc. */
+        ERec e = makeERec(ray.o, its.p, its.sh.n);
+        color += emitterEval(sc, sc.emitters[emitterOf(sc, its)], e);
+    }
+    if (kind == NORI_INTEGRATOR_DIRECT || kind == NORI_INTEGRATOR_DIRECT_EMS || kind == NORI_INTEGRATOR_DIRECT_MIS) {
+        for (const Emitter &light : sc.emitters) {                            /* direct.cpp:29-47, direct_ems.cpp:33-50, direct_mis.cpp:34-60 */
+            ERec e; e.ref = its.p;
+            P2 s; if (kind != NORI_INTEGRATOR_DIRECT) s = rng.next2D();       /* direct.cpp:27: zero-filled Vector2f */
+            V3 traced = emitterSample(sc, light, e, s);
+            float pdf_em = kind == NORI_INTEGRATOR_DIRECT_MIS ? emitterPdf(sc, light, e) : 0.f;
+            if (!occluded(sc, e.shadowRay)) {
+                V3 wi = toLocal(its.sh, e.wi), d = toLocal(its.sh, -ray.d);
+                BRec b; b.measure = ESolidAngle; b.uv = its.uv;
+                if (kind == NORI_INTEGRATOR_DIRECT) { b.wi = wi; b.wo = d; } else { b.wi = d; b.wo = wi; }
+                V3 f = bsdfEval(bsdfOf(sc, its), b);
+                if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
+                    float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
+                    float w_em = pdf_mat + pdf_em > 0.f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                    color += w_em * f * traced * wi.z;
+                } else color += f * wi.z * traced;
+            }
+        }
+    }
+    if (kind == NORI_INTEGRATOR_DIRECT_MATS || kind == NORI_INTEGRATOR_DIRECT_MIS) {   /* direct_mats.cpp:33-43, direct_mis.cpp:62-83 */
+        BRec b; b.wi = toLocal(its.sh, -ray.d); b.uv = its.uv;
+        V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
+        float pdf_mat = kind == NORI_INTEGRATOR_DIRECT_MIS ? bsdfPdf(bsdfOf(sc, its), b) : 0.f;
+        Ray nr(its.p, toWorld(its.sh, b.wo)); Its its2;
+        if (rayIntersect(sc, nr, its2, false) && emitterOf(sc, its2) >= 0) {
+            ERec e = makeERec(its.p, its2.p, its2.sh.n);
+            const Emitter &em = sc.emitters[emitterOf(sc, its2)];
+            V3 Le = emitterEval(sc, em, e);
+            if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
+                float pdf_em = emitterPdf(sc, em, e);
+                float w_mat = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : 0.0f;
+                color += w_mat * w * Le;
+            } else color += w * Le;
+        }
+    }
+    return color;
+}
+
+V3 LiNormals(Scene &sc, const Ray &ray) {                                     /* normals.cpp:15-23 */
+    Its its; if (!rayIntersect(sc, ray, its, false)) return V3(0.f);
+    return V3(std::abs(its.sh.n.x), std::abs(its.sh.n.y), std::abs(its.sh.n.z));
+}
+
+V3 LiAv(Scene &sc, Pcg32 &rng, const Ray &ray) {                              /* averagevisibility.cpp:16-25, warp.cpp:25-42 */
+    Its its; if (!rayIntersect(sc, ray, its, false)) return V3(1.f);
+    V3 v;
+    do { v.x = 1.f - 2.f * rng.next1D(); v.y = 1.f - 2.f * rng.next1D(); v.z = 1.f - 2.f * rng.next1D(); } while (sqnorm(v) > 1.f);
+    if (dot(v, its.sh.n) < 0.f) v = -v;
+    v = v / norm(v);
+    Ray nr(its.p, v, kEps, sc.pod.av_length);
+    return occluded(sc, nr) ? V3(0.f) : V3(1.f);
+}
+
+/* ---- homogeneous medium (medium.cpp:22-94) ---- */
+inline bool boundsHit(const nori_gpu_medium &m, const Ray &r, float &nearT, float &farT) {   /* bbox.h:366-392 */
+    nearT = -kInf; farT = kInf;
+    for (int i = 0; i < 3; i++) {
+        float origin = r.o[i], minVal = m.bounds_min[i], maxVal = m.bounds_max[i];
+        if (r.d[i] == 0) { if (origin < minVal || origin > maxVal) return false; }
+        else {
+            float t1 = (minVal - origin) * r.dRcp[i], t2 = (maxVal - origin) * r.dRcp[i];
+            if (t1 > t2) std::swap(t1, t2);
+            nearT = std::max(t1, nearT); farT = std::min(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+inline bool boundsContain(const nori_gpu_medium &m, V3 p) {                   /* bbox.h:115-123 */
+    for (int i = 0; i < 3; ++i) if (!(p[i] >= m.bounds_min[i] && p[i] <= m.bounds_max[i])) return false;
+    return true;
+}
+V3 mediumTr(const nori_gpu_medium &m, V3 src, V3 dst) {                       /* medium.cpp:22-57 */
+    float nearT, farT;
+    Ray ray(src, normalized(dst - src));
+    if (!boundsHit(m, ray, nearT, farT)) return V3(1.0f);
+    V3 sp = boundsContain(m, src) ? src : src + normalized(ray.d) * nearT;
+    V3 ep = boundsContain(m, dst) ? dst : src + normalized(ray.d) * farT;
+    float len = norm(ep - sp);
+    V3 ext = load3(m.sigma_a) + load3(m.sigma_s);
+    return V3(std::exp(-ext.x * len), std::exp(-ext.y * len), std::exp(-ext.z * len));
+}
+V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg32 &rng, float tMax, bool &hitObject, V3 &p) {   /* medium.cpp:59-90 */
+    float nearT, farT;
+    if (!boundsHit(m, ray, nearT, farT)) { hitObject = true; return V3(1.0f); }
+    V3 sp = boundsContain(m, ray.o) ? ray.o : ray.o + normalized(ray.d) * nearT;
+    V3 ext = load3(m.sigma_a) + load3(m.sigma_s);
+    float invTr = -1.0f * std::log(1 - rng.next1D()) / std::max(ext.x, std::max(ext.y, ext.z));   /* medium.cpp:92-94 */
+    float distance = norm(sp - ray.o) + invTr;
+    V3 albedo(m.sigma_s[0] / ext.x, m.sigma_s[1] / ext.y, m.sigma_s[2] / ext.z);
+    if (distance >= tMax) hitObject = true; else { p = ray.at(distance); hitObject = false; }
+    return albedo;
+}
+
+V3 LiVolumetric(Scene &sc, Pcg32 &rng, const Ray &ray) {                      /* volumetric.cpp:18-156 */
+    const nori_gpu_medium &med = sc.pod.medium;
+    V3 color(0.f), att(1.f); Ray cur = ray; float w_mats = 1.0f; Its its;
+    const size_t nLights = sc.emitters.size();
+    bool intersection = rayIntersect(sc, cur, its, false);
+    while (true) {
+        float tmax = intersection ? norm(its.p - cur.o) : its.t;
+        bool hitObject; V3 mp;
+        V3 sampled = mediumSample(med, cur, rng, tmax, hitObject, mp);
+        if (!hitObject) {
+            V3 wo = squareToUniformSphere(rng.next2D()); float pdf_mat = kInvFourPi;   /* phasefunction.cpp:13-16 */
+            const Emitter &light = randomEmitter(sc, rng.next1D());
+            ERec e; e.ref = mp;
+            V3 Li = emitterSample(sc, light, e, rng.next2D()) * (float) nLights;
+            att = att * sampled;
+            Its tmp;
+            if (!rayIntersect(sc, e.shadowRay, tmp, false))                    /* closest-hit query, volumetric.cpp:63 */
+                color += att * mediumTr(med, mp, e.p) * Li * pdf_mat;
+            float p = std::min(att.x, 0.80f);
+            if (rng.next1D() > p) return color;
+            att = att / p;
+            cur = Ray(mp, normalized(wo));
+            intersection = rayIntersect(sc, cur, its, false);
+            if (intersection && emitterOf(sc, its) >= 0) {
+                ERec l = makeERec(cur.o, its.p, its.sh.n);
+                float pdf_em = emitterPdf(sc, sc.emitters[emitterOf(sc, its)], l);
+                w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+            }
+        } else if (intersection) {
+            if (emitterOf(sc, its) >= 0) {
+                ERec e = makeERec(cur.o, its.p, its.sh.n);
+                color += att * w_mats * emitterEval(sc, sc.emitters[emitterOf(sc, its)], e) * mediumTr(med, its.p, e.p);
+            }
+            const Emitter &light = randomEmitter(sc, rng.next1D());
+            ERec e; e.ref = its.p;
+            V3 Li = emitterSample(sc, light, e, rng.next2D()) * (float) nLights;
+            if (!occluded(sc, e.shadowRay)) {
+                float pdf_em = emitterPdf(sc, light, e);
+                float theta = std::max(0.0f, toLocal(its.sh, e.wi).z);
+                BRec b; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle;   /* uv left default, :103 */
+                V3 f = bsdfEval(bsdfOf(sc, its), b);
+                float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
+                float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                color += att * w_ems * f * theta * Li * mediumTr(med, its.p, e.p);
+            }
+            float p = std::min(att.x, 0.80f);
+            if (rng.next1D() > p) return color;
+            att = att / p;
+            BRec b; b.wi = toLocal(its.sh, -cur.d);
+            V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
+            att = att * w;
+            float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
+            cur = Ray(its.p, toWorld(its.sh, b.wo));
+            intersection = rayIntersect(sc, cur, its, false);
+            if (intersection) {
+                if (emitterOf(sc, its) >= 0) {
+                    ERec l = makeERec(cur.o, its.p, its.sh.n);
+                    float pdf_em = emitterPdf(sc, sc.emitters[emitterOf(sc, its)], l);
+                    w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+                }
+                if (b.measure == EDiscrete) w_mats = 1.0f;
+            }
+        } else break;
+    }
+    return color;
+}
+
+V3 Li(Scene &sc, Pcg32 &rng, const Ray &ray) {
+    switch (sc.pod.integrator) {
+    case NORI_INTEGRATOR_NORMALS: return LiNormals(sc, ray);
+    case NORI_INTEGRATOR_PATH_MIS: return LiPathMis(sc, rng, ray);
+    case NORI_INTEGRATOR_PATH_MATS: return LiPathMats(sc, rng, ray);
+    case NORI_INTEGRATOR_AV: return LiAv(sc, rng, ray);
+    case NORI_INTEGRATOR_VOLUMETRIC: return LiVolumetric(sc, rng, ray);
+    default: return LiDirect(sc, rng, ray, sc.pod.integrator);
+    }
+}
+
+/* one iteration of renderBlock's inner loop (render.cpp:98-126) */
+inline V3 cameraSample(Scene &sc, Pcg32 &rng, int px, int py, P2 &pixelSample) {
+    P2 a = rng.next2D(); pixelSample.x = (float) px + a.x; pixelSample.y = (float) py + a.y;
+    P2 aperture = rng.next2D();
+    Ray ray; sampleRay(sc.pod.camera, ray, pixelSample, aperture);
+    return Li(sc, rng, ray);          /* camera weight is Color3f(1) for both cameras */
+}
+
+inline bool validColor(V3 c) {                                                /* common.cpp:224-231 */
+    for (int i = 0; i < 3; ++i) { float v = c[i]; if (v < 0 || !std::isfinite(v)) return false; }
+    return true;
+}
+
+/* ImageBlock::put(pos, value), block.cpp:93-122, for a block at offset (ox,oy) of size (bw,bh) */
+void blockPut(const Scene &sc, float *blk, int ox, int oy, int bw, int bh, P2 pos_, V3 value) {
+    if (!validColor(value)) return;
+    const int b = sc.border; const float r = sc.pod.filter.radius;
+    int cols = bw + 2 * b, rows = bh + 2 * b;
+    float px = pos_.x - 0.5f - (ox - b), py = pos_.y - 0.5f - (oy - b);
+    int x0 = std::max(0, (int) std::ceil(px - r)), y0 = std::max(0, (int) std::ceil(py - r));
+    int x1 = std::min(cols - 1, (int) std::floor(px + r)), y1 = std::min(rows - 1, (int) std::floor(py + r));
+    float wx[64], wy[64];
+    for (int x = x0, i = 0; x <= x1; ++x) wx[i++] = sc.pod.filter.table[(int) (std::abs(x - px) * sc.lookupFactor)];
+    for (int y = y0, i = 0; y <= y1; ++y) wy[i++] = sc.pod.filter.table[(int) (std::abs(y - py) * sc.lookupFactor)];
+    for (int y = y0, yr = 0; y <= y1; ++y, ++yr)
+        for (int x = x0, xr = 0; x <= x1; ++x, ++xr) {
+            float *c = &blk[((size_t) y * cols + x) * 4];
+            c[0] += value.x * wx[xr] * wy[yr]; c[1] += value.y * wx[xr] * wy[yr];
+            c[2] += value.z * wx[xr] * wy[yr]; c[3] += 1.0f * wx[xr] * wy[yr];
+        }
+}
+
+} // namespace
+
+/* =================================================================== C interface (ctypes) ===== */
+extern "C" {
+
+void *nori_oracle_create(const nori_gpu_scene *s) {
+    Scene *sc = new Scene();
+    sc->pod = *s;
+    sc->nodes.assign(s->nodes, s->nodes + s->n_nodes);
+    sc->indices.assign(s->indices, s->indices + s->n_indices);
+    sc->shapeOffset.assign(s->shape_offset, s->shape_offset + s->n_shapes + 1);
+    sc->bsdfs.assign(s->bsdfs, s->bsdfs + s->n_bsdfs);
+    for (uint32_t i = 0; i < s->n_shapes; ++i) {
+        Shape sh; sh.pod = s->shapes[i];
+        if (sh.pod.type == NORI_SHAPE_MESH) {
+            sh.V.assign(sh.pod.V, sh.pod.V + 3 * (size_t) sh.pod.n_vertices);
+            if (sh.pod.N) sh.N.assign(sh.pod.N, sh.pod.N + 3 * (size_t) sh.pod.n_vertices);
+            if (sh.pod.UV) sh.UV.assign(sh.pod.UV, sh.pod.UV + 2 * (size_t) sh.pod.n_vertices);
+            sh.F.assign(sh.pod.F, sh.pod.F + 3 * (size_t) sh.pod.n_triangles);
+            if (sh.pod.area_cdf) sh.cdf.assign(sh.pod.area_cdf, sh.pod.area_cdf + sh.pod.n_triangles + 1);
+        }
+        sc->shapes.push_back(std::move(sh));
+    }
+    for (uint32_t i = 0; i < s->n_emitters; ++i) {
+        Emitter e; e.pod = s->emitters[i];
+        if (e.pod.type == NORI_EMITTER_ENVMAP) {
+            size_t R = e.pod.env_rows, C = e.pod.env_cols;
+            e.image.assign(e.pod.env_image, e.pod.env_image + R * C * 3);
+            e.pdf.assign(e.pod.env_pdf, e.pod.env_pdf + R * C);
+            e.cdf.assign(e.pod.env_cdf, e.pod.env_cdf + R * (C + 1));
+            e.pm.assign(e.pod.env_pmarginal, e.pod.env_pmarginal + R);
+            e.cm.assign(e.pod.env_cmarginal, e.pod.env_cmarginal + R + 1);
+        }
+        sc->emitters.push_back(std::move(e));
+    }
+    sc->border = (int) std::ceil(s->filter.radius - 0.5f);                    /* block.cpp:57 */
+    sc->lookupFactor = NORI_FILTER_RESOLUTION / s->filter.radius;             /* block.cpp:64 */
+    return sc;
+}
+void nori_oracle_destroy(void *h) { delete (Scene *) h; }
+
+void nori_oracle_film_dims(void *h, int32_t *rows, int32_t *cols, int32_t *border) {
+    Scene *sc = (Scene *) h;
+    *rows = sc->pod.camera.height + 2 * sc->border; *cols = sc->pod.camera.width + 2 * sc->border; *border = sc->border;
+}
+
+/* optional outputs p/uv/n/ng (3,2,3,3 floats per ray) may be NULL */
+void nori_oracle_trace(void *h, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out,
+                       float *p, float *uv, float *nsh, float *ngeo) {
+    Scene *sc = (Scene *) h;
+    parallelFor((int64_t) n, 1024, [&](int64_t i) {
+        Ray r(load3(rays[i].o), load3(rays[i].d), rays[i].mint, rays[i].maxt);
+        Its its; bool hit = rayIntersect(*sc, r, its, shadow != 0);
+        nori_gpu_hit &o = out[i]; memset(&o, 0, sizeof(o));
+        o.t = its.t; o.u = its.baryU; o.v = its.baryV; o.shape = hit && !shadow ? (uint32_t) its.shape : 0xffffffffu;
+        o.prim = hit && !shadow ? its.prim : 0xffffffffu; o.nodes_visited = its.nodes; o.prims_tested = its.prims;
+        if (hit && !shadow) {
+            if (p) { p[3 * i] = its.p.x; p[3 * i + 1] = its.p.y; p[3 * i + 2] = its.p.z; }
+            if (uv) { uv[2 * i] = its.uv.x; uv[2 * i + 1] = its.uv.y; }
+            if (nsh) { nsh[3 * i] = its.sh.n.x; nsh[3 * i + 1] = its.sh.n.y; nsh[3 * i + 2] = its.sh.n.z; }
+            if (ngeo) { ngeo[3 * i] = its.geo.n.x; ngeo[3 * i + 1] = its.geo.n.y; ngeo[3 * i + 2] = its.geo.n.z; }
+        }
+    });
+}
+
+void nori_oracle_pcg32(uint64_t initstate, uint64_t initseq, uint64_t n, float *out) {
+    Pcg32 r; r.seed(initstate, initseq); for (uint64_t i = 0; i < n; ++i) out[i] = r.nextFloat();
+}
+void nori_oracle_pcg32_uint(uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out) {
+    Pcg32 r; r.seed(initstate, initseq); for (uint64_t i = 0; i < n; ++i) out[i] = r.nextUInt();
+}
+
+/* RNG mode 0 (the GPU mapping): path (x,y,k) uses pcg32.seed(seed + k, y*W + x).
+ * out_rgba[(k*H + y)*W + x] = (r,g,b,valid) */
+void nori_oracle_render_samples(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, float *out) {
+    Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height;
+    parallelFor((int64_t) spp_count * H, 4, [&](int64_t ky) {
+            int64_t k = ky / H; int y = (int) (ky % H);
+            for (int x = 0; x < W; ++x) {
+                Pcg32 rng; rng.seed(seed + spp_begin + (uint64_t) k, (uint64_t) y * W + x);
+                P2 ps; V3 v = cameraSample(*sc, rng, x, y, ps);
+                float *o = &out[(((size_t) k * H + y) * W + x) * 4];
+                bool ok = validColor(v);
+                o[0] = ok ? v.x : 0.f; o[1] = ok ? v.y : 0.f; o[2] = ok ? v.z : 0.f; o[3] = ok ? 1.f : 0.f;
+            }
+    });
+    __atomic_fetch_add(&sc->samples, (uint64_t) spp_count * W * H, __ATOMIC_RELAXED);
+}
+
+/* Accumulate into film ((H+2b)*(W+2b)*4 floats).
+ * mode 0: per-path streams (as above); mode 1: the reference's mapping -- one pcg32 per 32x32 block,
+ * seeded (offset.x, offset.y) when spp_begin == 0 and carried across passes through `block_rng`
+ * (2 x uint64 per block, caller-owned, may be NULL if a single call renders everything). */
+void nori_oracle_render(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
+                        float *film, uint64_t *block_rng) {
+    Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height, b = sc->border;
+    const int fcols = W + 2 * b, BS = NORI_BLOCK_SIZE;
+    const int nbx = (W + BS - 1) / BS, nby = (H + BS - 1) / BS;
+    std::vector<Pcg32> rngs((size_t) nbx * nby);
+    for (int by = 0; by < nby; ++by) for (int bx = 0; bx < nbx; ++bx) {
+        Pcg32 &r = rngs[(size_t) by * nbx + bx];
+        if (block_rng && spp_begin != 0) { r.state = block_rng[2 * ((size_t) by * nbx + bx)]; r.inc = block_rng[2 * ((size_t) by * nbx + bx) + 1]; }
+        else r.seed((uint64_t) bx * BS, (uint64_t) by * BS);               /* independent.cpp:48-53 */
+    }
+    for (uint32_t k = 0; k < spp_count; ++k) {
+        std::vector<std::vector<float>> blocks((size_t) nbx * nby);
+        parallelFor(nbx * nby, 1, [&](int64_t bi) {
+            int bx = bi % nbx, by = bi / nbx, ox = bx * BS, oy = by * BS;
+            int bw = std::min(BS, W - ox), bh = std::min(BS, H - oy);
+            /* the reference's per-thread block is always (32+2b)^2 (render.cpp:203) */
+            std::vector<float> &blk = blocks[bi]; blk.assign((size_t) (BS + 2 * b) * (BS + 2 * b) * 4, 0.f);
+            for (int y = 0; y < bh; ++y) for (int x = 0; x < bw; ++x) {
+                Pcg32 path; Pcg32 *rng = &rngs[bi];
+                if (mode == 0) { path.seed(seed + spp_begin + k, (uint64_t) (y + oy) * W + (x + ox)); rng = &path; }
+                P2 ps; V3 v = cameraSample(*sc, *rng, x + ox, y + oy, ps);
+                if (!validColor(v)) __atomic_fetch_add(&sc->invalid, 1, __ATOMIC_RELAXED);
+                blockPut(*sc, blk.data(), ox, oy, BS, BS, ps, v);
+            }
+        });
+        /* ImageBlock::put(block), block.cpp:124-133, in block-id order (deterministic) */
+        for (int bi = 0; bi < nbx * nby; ++bi) {
+            int bx = bi % nbx, by = bi / nbx, ox = bx * BS, oy = by * BS;
+            int bw = std::min(BS, W - ox), bh = std::min(BS, H - oy), bc = BS + 2 * b;
+            for (int y = 0; y < bh + 2 * b; ++y) for (int x = 0; x < bw + 2 * b; ++x)
+                for (int c = 0; c < 4; ++c)
+                    film[((size_t) (y + oy) * fcols + (x + ox)) * 4 + c] += blocks[bi][((size_t) y * bc + x) * 4 + c];
+        }
+    }
+    if (block_rng) for (size_t i = 0; i < rngs.size(); ++i) { block_rng[2 * i] = rngs[i].state; block_rng[2 * i + 1] = rngs[i].inc; }
+    __atomic_fetch_add(&sc->samples, (uint64_t) spp_count * W * H, __ATOMIC_RELAXED);
+}
+
+/* The first n iterations of renderBlock (render.cpp:96-126) for block (0,0) with the reference's sampler
+ * mapping; out rows = (pixelSample.x, pixelSample.y, r, g, b).  Compared with nori_export --seq. */
+void nori_oracle_block_sequence(void *h, uint64_t n, float *out) {
+    Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height;
+    int bw = std::min(NORI_BLOCK_SIZE, W), bh = std::min(NORI_BLOCK_SIZE, H);
+    Pcg32 rng; rng.seed(0, 0);
+    uint64_t done = 0;
+    while (done < n)
+        for (int y = 0; y < bh && done < n; ++y)
+            for (int x = 0; x < bw && done < n; ++x, ++done) {
+                P2 ps; V3 v = cameraSample(*sc, rng, x, y, ps);
+                float *o = &out[5 * done]; o[0] = ps.x; o[1] = ps.y; o[2] = v.x; o[3] = v.y; o[4] = v.z;
+            }
+}
+
+/* ImageBlock::toBitmap, block.cpp:76-82 + color.h:84-89 */
+void nori_oracle_resolve(void *h, const float *film, float *rgb) {
+    Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height, b = sc->border, fcols = W + 2 * b;
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const float *c = &film[((size_t) (y + b) * fcols + (x + b)) * 4];
+        for (int k = 0; k < 3; ++k) rgb[((size_t) y * W + x) * 3 + k] = c[3] != 0 ? c[k] / c[3] : 0.f;
+    }
+}
+
+void nori_oracle_stats(void *h, nori_gpu_stats *out) {
+    Scene *sc = (Scene *) h; memset(out, 0, sizeof(*out));
+    out->samples = sc->samples; out->rays = sc->rays; out->shadow_rays = sc->shadowRays;
+    out->nodes_visited = sc->nodesVisited; out->prims_tested = sc->primsTested; out->invalid_samples = sc->invalid;
+}
+void nori_oracle_reset_stats(void *h) {
+    Scene *sc = (Scene *) h; sc->samples = sc->rays = sc->shadowRays = sc->nodesVisited = sc->primsTested = sc->invalid = 0;
+}
+
+} /* extern "C" */
