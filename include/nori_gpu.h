@@ -223,6 +223,9 @@ int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint
 /* n raw nextUInt() outputs, for the published pcg32-demo known answers. */
 int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out);
 
+/* sizeof() of every ABI struct as compiled into the library (binding self-check); returns the count. */
+int nori_gpu_abi_sizes(uint32_t *out, int n);
+
 int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out);
 int nori_gpu_reset_stats(nori_gpu_ctx *ctx);
 int nori_gpu_synchronize(nori_gpu_ctx *ctx);

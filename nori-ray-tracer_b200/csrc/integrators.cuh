@@ -1,0 +1,330 @@
+// integrators.cuh -- the control flow of the reference's Integrator::Li implementations, split so
+// that the same per-vertex code serves the wavefront kernels (path_mis / path_mats: one call per
+// queue entry) and the single-thread-per-sample kernel used for the short integrators.
+#pragma once
+#include "shading.cuh"
+
+enum { PF_ALIVE = 1u, PF_SHADOW = 2u, PF_TERMINATE = 4u, PF_FIRST = 8u, PF_DISCRETE = 16u };
+
+struct PathState {
+    V3 o, d;            // current ray (origin is the previous vertex: path_mis.cpp:83 `origin`)
+    V3 thr, rad;        // `attenuation`, `color`
+    float pdf_mat;      // bsdf->pdf of the last sampled direction (path_mis.cpp:81)
+    uint32_t flags;
+    Pcg32 rng;
+};
+struct VertexOut {
+    Ray shadow; V3 contrib;       // NEE: added to rad iff the shadow ray is unoccluded
+    Ray next;                     // extension ray when the path survives
+};
+
+template <int BSDF> __device__ __forceinline__ V3 evalT(const nori_gpu_bsdf &b, const BRec &r) {
+    if constexpr (BSDF < 0) return bsdfEvalDyn(b, r); else return bsdfEval<BSDF>(b, r);
+}
+template <int BSDF> __device__ __forceinline__ float pdfT(const nori_gpu_bsdf &b, const BRec &r) {
+    if constexpr (BSDF < 0) return bsdfPdfDyn(b, r); else return bsdfPdf<BSDF>(b, r);
+}
+template <int BSDF> __device__ __forceinline__ V3 sampleT(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+    if constexpr (BSDF < 0) return bsdfSampleDyn(b, r, s); else return bsdfSample<BSDF>(b, r, s);
+}
+
+// One iteration of the while(true) body of PathMisIntegrator::Li (path_mis.cpp:32-97; MIS=true) or
+// PathMatsIntegrator::Li (path_mats.cpp:23-55; MIS=false) at a surface hit.  On return
+// st.flags has PF_TERMINATE (Russian roulette ended the path) or PF_ALIVE (out.next is the new
+// ray); PF_SHADOW is set when out.shadow / out.contrib are valid.
+template <int BSDF, bool MIS>
+__device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, PathState &st, VertexOut &out) {
+    Its its; hitInfo(sc, st.o, st.d, hit, its);
+    const DShape &shp = sc.shapes[its.shape];
+    const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+    const uint32_t inFlags = st.flags;
+    uint32_t flags = 0;
+
+    if (shp.emitter >= 0) {                                        // path_mis.cpp:35-39 / :87-97, path_mats.cpp:32-36
+        const nori_gpu_emitter &em = sc.emitters[shp.emitter].pod;
+        ERec e = makeERec(st.o, its.p, its.sh.n);
+        float w_mats = 1.0f;
+        if (MIS && !(inFlags & (PF_FIRST | PF_DISCRETE))) {
+            float pdf_em = emitterPdf(sc, em, e);
+            w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
+        }
+        V3 Le = emitterEval(sc, em, e);
+        st.rad = st.rad + (MIS ? st.thr * w_mats * Le : st.thr * Le);
+    }
+
+    const V3 wiLocal = toLocal(its.sh, -st.d);
+    if (MIS) {                                                     // path_mis.cpp:42-61
+        const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
+        ERec e = makeERec(its.p);
+        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
+        float pdf_em = emitterPdf(sc, light, e);
+        V3 woLocal = toLocal(its.sh, e.wi);
+        float theta = fmaxf(0.0f, woLocal.z);
+        BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv = its.uv;
+        V3 f = evalT<BSDF>(bsdf, b);
+        float pdf_mat = pdfT<BSDF>(bsdf, b);
+        float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+        out.shadow = e.shadow;
+        out.contrib = st.thr * w_ems * f * theta * Li;
+        flags |= PF_SHADOW;
+    }
+
+    float p = fminf(st.thr.x, 0.99f);                              // path_mis.cpp:64-69: roulette on the RED channel
+    if (st.rng.next1D() > p) { st.flags = flags | PF_TERMINATE; return; }
+    st.thr = st.thr / p;
+
+    BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv = its.uv;  // path_mis.cpp:72-81
+    V3 w = sampleT<BSDF>(bsdf, b, st.rng.next2D());
+    st.thr = st.thr * w;
+    out.next = mkray(its.p, toWorld(its.sh, b.wo));
+    if (MIS) st.pdf_mat = pdfT<BSDF>(bsdf, b);
+    st.o = out.next.o; st.d = out.next.d;
+    st.flags = flags | PF_ALIVE | (b.measure == M_DISCRETE ? PF_DISCRETE : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-thread-per-sample integrators (normals, av, direct*, volumetric; also path_* as a
+// cross-check of the wavefront scheduler).  Returns the radiance of one camera ray.
+// ---------------------------------------------------------------------------------------------
+struct RayStats { uint32_t rays, shadow; TraceCounters cnt; };
+
+template <bool COUNT>
+__device__ __forceinline__ bool closestHit(const DScene &sc, const Ray &r, Hit &h, RayStats &rs) {
+    ++rs.rays; return traverse<false, COUNT>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt);
+}
+template <bool COUNT>
+__device__ __forceinline__ bool anyHit(const DScene &sc, const Ray &r, RayStats &rs) {
+    Hit h; ++rs.rays; ++rs.shadow; return traverse<true, COUNT>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt);
+}
+
+template <bool COUNT, bool MIS>
+__device__ V3 liPath(const DScene &sc, Pcg32 &rng, Ray ray, RayStats &rs) {
+    PathState st; st.o = ray.o; st.d = ray.d; st.thr = mk(1.f); st.rad = mk(0.f); st.pdf_mat = 0.f; st.flags = PF_FIRST; st.rng = rng;
+    Ray cur = ray;
+    while (true) {
+        Hit h;
+        if (!closestHit<COUNT>(sc, cur, h, rs)) break;
+        VertexOut out;
+        pathVertex<-1, MIS>(sc, h, st, out);
+        if ((st.flags & PF_SHADOW) && !anyHit<COUNT>(sc, out.shadow, rs)) st.rad = st.rad + out.contrib;
+        if (st.flags & PF_TERMINATE) break;
+        cur = out.next;
+    }
+    rng = st.rng;
+    return st.rad;
+}
+
+// direct.cpp:18-51, direct_ems.cpp:17-54, direct_mats.cpp:17-46, direct_mis.cpp:17-87
+template <bool COUNT>
+__device__ V3 liDirect(const DScene &sc, Pcg32 &rng, const Ray &ray, int kind, RayStats &rs) {
+    Hit h;
+    if (!closestHit<COUNT>(sc, ray, h, rs)) return mk(0.f);
+    Its its; hitInfo(sc, ray.o, ray.d, h, its);
+    const DShape &shp = sc.shapes[its.shape];
+    const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+    V3 color = mk(0.f);
+    if (kind != NORI_INTEGRATOR_DIRECT && shp.emitter >= 0) {
+        ERec e = makeERec(ray.o, its.p, its.sh.n);
+        color = color + emitterEval(sc, sc.emitters[shp.emitter].pod, e);
+    }
+    const V3 dLocal = toLocal(its.sh, -ray.d);
+    if (kind == NORI_INTEGRATOR_DIRECT || kind == NORI_INTEGRATOR_DIRECT_EMS || kind == NORI_INTEGRATOR_DIRECT_MIS) {
+        for (uint32_t li = 0; li < sc.n_emitters; ++li) {
+            const nori_gpu_emitter &light = sc.emitters[li].pod;
+            ERec e = makeERec(its.p);
+            P2 s; s.x = 0.f; s.y = 0.f;                             // direct.cpp:27 passes a zero-filled Vector2f
+            if (kind != NORI_INTEGRATOR_DIRECT) s = rng.next2D();
+            V3 traced = emitterSample(sc, light, e, s);
+            float pdf_em = kind == NORI_INTEGRATOR_DIRECT_MIS ? emitterPdf(sc, light, e) : 0.f;
+            if (!anyHit<COUNT>(sc, e.shadow, rs)) {
+                V3 wi = toLocal(its.sh, e.wi);
+                BRec b; b.measure = M_SOLID_ANGLE; b.uv = its.uv;
+                if (kind == NORI_INTEGRATOR_DIRECT) { b.wi = wi; b.wo = dLocal; } else { b.wi = dLocal; b.wo = wi; }
+                V3 f = bsdfEvalDyn(bsdf, b);
+                if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
+                    float pdf_mat = bsdfPdfDyn(bsdf, b);
+                    float w_em = pdf_mat + pdf_em > 0.f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                    color = color + w_em * f * traced * wi.z;
+                } else color = color + f * wi.z * traced;
+            }
+        }
+    }
+    if (kind == NORI_INTEGRATOR_DIRECT_MATS || kind == NORI_INTEGRATOR_DIRECT_MIS) {
+        BRec b; b.wi = dLocal; b.measure = M_UNKNOWN; b.uv = its.uv;
+        V3 w = bsdfSampleDyn(bsdf, b, rng.next2D());
+        float pdf_mat = kind == NORI_INTEGRATOR_DIRECT_MIS ? bsdfPdfDyn(bsdf, b) : 0.f;
+        Ray nr = mkray(its.p, toWorld(its.sh, b.wo));
+        Hit h2;
+        if (closestHit<COUNT>(sc, nr, h2, rs)) {
+            Its its2; hitInfo(sc, nr.o, nr.d, h2, its2);
+            const DShape &shp2 = sc.shapes[its2.shape];
+            if (shp2.emitter >= 0) {
+                const nori_gpu_emitter &em = sc.emitters[shp2.emitter].pod;
+                ERec e = makeERec(its.p, its2.p, its2.sh.n);
+                V3 Le = emitterEval(sc, em, e);
+                if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
+                    float pdf_em = emitterPdf(sc, em, e);
+                    float w_mat = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : 0.0f;
+                    color = color + w_mat * w * Le;
+                } else color = color + w * Le;
+            }
+        }
+    }
+    return color;
+}
+
+// normals.cpp:15-23
+template <bool COUNT>
+__device__ V3 liNormals(const DScene &sc, const Ray &ray, RayStats &rs) {
+    Hit h; if (!closestHit<COUNT>(sc, ray, h, rs)) return mk(0.f);
+    Its its; hitInfo(sc, ray.o, ray.d, h, its);
+    return mk(fabsf(its.sh.n.x), fabsf(its.sh.n.y), fabsf(its.sh.n.z));
+}
+
+// averagevisibility.cpp:16-25 + warp.cpp:25-42
+template <bool COUNT>
+__device__ V3 liAv(const DScene &sc, Pcg32 &rng, const Ray &ray, RayStats &rs) {
+    Hit h; if (!closestHit<COUNT>(sc, ray, h, rs)) return mk(1.f);
+    Its its; hitInfo(sc, ray.o, ray.d, h, its);
+    V3 v;
+    do { v.x = 1.f - 2.f * rng.next1D(); v.y = 1.f - 2.f * rng.next1D(); v.z = 1.f - 2.f * rng.next1D(); } while (sqnorm(v) > 1.f);
+    if (dot(v, its.sh.n) < 0.f) v = -v;
+    v = v / norm(v);
+    Ray nr = mkray(its.p, v, NORI_EPS, sc.av_length);
+    return anyHit<COUNT>(sc, nr, rs) ? mk(0.f) : mk(1.f);
+}
+
+// ---- homogeneous medium (medium.cpp:22-94) --------------------------------------------------
+__device__ __forceinline__ bool boundsHit(const nori_gpu_medium &m, V3 o, V3 d, float &nearT, float &farT) {   // bbox.h:366-392
+    nearT = __int_as_float(0xff800000); farT = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float origin = comp(o, i), dd = comp(d, i), minVal = m.bounds_min[i], maxVal = m.bounds_max[i];
+        if (dd == 0) { if (origin < minVal || origin > maxVal) return false; }
+        else {
+            float rcp = 1.0f / dd;
+            float t1 = (minVal - origin) * rcp, t2 = (maxVal - origin) * rcp;
+            if (t1 > t2) { float t = t1; t1 = t2; t2 = t; }
+            nearT = std_max(t1, nearT); farT = std_min(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool boundsContain(const nori_gpu_medium &m, V3 p) {          // bbox.h:115-123
+    return p.x >= m.bounds_min[0] && p.x <= m.bounds_max[0] && p.y >= m.bounds_min[1] && p.y <= m.bounds_max[1]
+        && p.z >= m.bounds_min[2] && p.z <= m.bounds_max[2];
+}
+__device__ V3 mediumTr(const nori_gpu_medium &m, V3 src, V3 dst) {                       // medium.cpp:22-57
+    float nearT, farT;
+    V3 d = normalized(dst - src);
+    if (!boundsHit(m, src, d, nearT, farT)) return mk(1.0f);
+    V3 sp = boundsContain(m, src) ? src : src + normalized(d) * nearT;
+    V3 ep = boundsContain(m, dst) ? dst : src + normalized(d) * farT;
+    float len = norm(ep - sp);
+    V3 ext = arr3(m.sigma_a) + arr3(m.sigma_s);
+    return mk(expf(-ext.x * len), expf(-ext.y * len), expf(-ext.z * len));
+}
+__device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg32 &rng, float tMax, bool &hitObject, V3 &p) {   // medium.cpp:59-90
+    float nearT, farT;
+    if (!boundsHit(m, ray.o, ray.d, nearT, farT)) { hitObject = true; return mk(1.0f); }
+    V3 sp = boundsContain(m, ray.o) ? ray.o : ray.o + normalized(ray.d) * nearT;
+    V3 ext = arr3(m.sigma_a) + arr3(m.sigma_s);
+    float invTr = -1.0f * logf(1 - rng.next1D()) / fmaxf(ext.x, fmaxf(ext.y, ext.z));     // medium.cpp:92-94
+    float distance = norm(sp - ray.o) + invTr;
+    V3 albedo = mk(m.sigma_s[0] / ext.x, m.sigma_s[1] / ext.y, m.sigma_s[2] / ext.z);
+    if (distance >= tMax) hitObject = true; else { p = ray.o + distance * ray.d; hitObject = false; }
+    return albedo;
+}
+
+// volumetric.cpp:18-156
+template <bool COUNT>
+__device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) {
+    const nori_gpu_medium &med = sc.medium;
+    V3 color = mk(0.f), att = mk(1.f); float w_mats = 1.0f;
+    Hit h; Its its;
+    bool intersection = closestHit<COUNT>(sc, cur, h, rs);
+    if (intersection) hitInfo(sc, cur.o, cur.d, h, its);
+    while (true) {
+        float tmax = intersection ? norm(its.p - cur.o) : h.t;
+        bool hitObject; V3 mp = mk(0.f);
+        V3 sampled = mediumSample(med, cur, rng, tmax, hitObject, mp);
+        if (!hitObject) {
+            V3 wo = squareToUniformSphere(rng.next2D()); float pdf_mat = NORI_INV_FOURPI;   // phasefunction.cpp:13-16
+            const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, rng.next1D())].pod;
+            ERec e = makeERec(mp);
+            V3 Li = emitterSample(sc, light, e, rng.next2D()) * (float) sc.n_emitters;
+            att = att * sampled;
+            Hit tmp;
+            if (!closestHit<COUNT>(sc, e.shadow, tmp, rs))            // a closest-hit query in the reference (volumetric.cpp:63)
+                color = color + att * mediumTr(med, mp, e.p) * Li * pdf_mat;
+            float p = fminf(att.x, 0.80f);
+            if (rng.next1D() > p) return color;
+            att = att / p;
+            cur = mkray(mp, normalized(wo));
+            intersection = closestHit<COUNT>(sc, cur, h, rs);
+            if (intersection) {
+                hitInfo(sc, cur.o, cur.d, h, its);
+                const DShape &shp = sc.shapes[its.shape];
+                if (shp.emitter >= 0) {
+                    ERec l = makeERec(cur.o, its.p, its.sh.n);
+                    float pdf_em = emitterPdf(sc, sc.emitters[shp.emitter].pod, l);
+                    w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+                }
+            }
+        } else if (intersection) {
+            const DShape &shp = sc.shapes[its.shape];
+            const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+            if (shp.emitter >= 0) {
+                ERec e = makeERec(cur.o, its.p, its.sh.n);
+                color = color + att * w_mats * emitterEval(sc, sc.emitters[shp.emitter].pod, e) * mediumTr(med, its.p, e.p);
+            }
+            const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, rng.next1D())].pod;
+            ERec e = makeERec(its.p);
+            V3 Li = emitterSample(sc, light, e, rng.next2D()) * (float) sc.n_emitters;
+            const V3 wiLocal = toLocal(its.sh, -cur.d);
+            if (!anyHit<COUNT>(sc, e.shadow, rs)) {
+                float pdf_em = emitterPdf(sc, light, e);
+                V3 woLocal = toLocal(its.sh, e.wi);
+                float theta = fmaxf(0.0f, woLocal.z);
+                BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv.x = 0.f; b.uv.y = 0.f;   // uv not set, :103
+                V3 f = bsdfEvalDyn(bsdf, b);
+                float pdf_mat = bsdfPdfDyn(bsdf, b);
+                float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                color = color + att * w_ems * f * theta * Li * mediumTr(med, its.p, e.p);
+            }
+            float p = fminf(att.x, 0.80f);
+            if (rng.next1D() > p) return color;
+            att = att / p;
+            BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv.x = 0.f; b.uv.y = 0.f;
+            V3 w = bsdfSampleDyn(bsdf, b, rng.next2D());
+            att = att * w;
+            float pdf_mat = bsdfPdfDyn(bsdf, b);
+            cur = mkray(its.p, toWorld(its.sh, b.wo));
+            intersection = closestHit<COUNT>(sc, cur, h, rs);
+            if (intersection) {
+                hitInfo(sc, cur.o, cur.d, h, its);
+                const DShape &shp2 = sc.shapes[its.shape];
+                if (shp2.emitter >= 0) {
+                    ERec l = makeERec(cur.o, its.p, its.sh.n);
+                    float pdf_em = emitterPdf(sc, sc.emitters[shp2.emitter].pod, l);
+                    w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+                }
+                if (b.measure == M_DISCRETE) w_mats = 1.0f;
+            }
+        } else break;
+    }
+    return color;
+}
+
+template <bool COUNT>
+__device__ V3 liDispatch(const DScene &sc, Pcg32 &rng, const Ray &ray, RayStats &rs) {
+    switch (sc.integrator) {
+    case NORI_INTEGRATOR_NORMALS: return liNormals<COUNT>(sc, ray, rs);
+    case NORI_INTEGRATOR_PATH_MIS: return liPath<COUNT, true>(sc, rng, ray, rs);
+    case NORI_INTEGRATOR_PATH_MATS: return liPath<COUNT, false>(sc, rng, ray, rs);
+    case NORI_INTEGRATOR_AV: return liAv<COUNT>(sc, rng, ray, rs);
+    case NORI_INTEGRATOR_VOLUMETRIC: return liVolumetric<COUNT>(sc, rng, ray, rs);
+    default: return liDirect<COUNT>(sc, rng, ray, sc.integrator, rs);
+    }
+}

@@ -1,0 +1,359 @@
+// kernels.cuh -- the __global__ kernels of the wavefront path tracer.
+//
+//   k_generate   raygen + path regeneration: free pool slots claim the next sample index, seed their
+//                pcg32 stream, draw the film/aperture samples and write the camera ray
+//                (render.cpp:98-124, perspective.cpp:90-112, thinlens.cpp:126-171)
+//   k_extend     persistent-thread closest-hit traversal over the pool (bvh.cpp:404-462); misses are
+//                finalised, hits are binned by BSDF type into material queues with warp-aggregated
+//                atomics
+//   k_shade<B>   one launch per material queue: hit info, emission (+MIS weight), NEE sample + BSDF
+//                eval/pdf, Russian roulette, BSDF sample (path_mis.cpp:32-97 / path_mats.cpp:23-55)
+//   k_shadow     persistent-thread any-hit traversal of the NEE rays; adds the contribution and
+//                finalises paths that the roulette ended
+//   k_film       reconstruction-filter accumulation of a batch of finished samples into the film:
+//                one CTA per 32x32 film tile, samples of the tile + halo staged in shared memory,
+//                each film pixel owned by exactly one thread (gather, no atomics), one coalesced
+//                float4 read-modify-write per film pixel per batch (block.cpp:93-133)
+//   k_resolve    ImageBlock::toBitmap (block.cpp:76-82)
+//   k_mega       one thread per sample for the short integrators (normals, av, direct*, volumetric)
+//   k_trace / k_pcg32*   the ABI's test hooks
+#pragma once
+#include "integrators.cuh"
+
+#define NORI_FREE_SLOT 0xffffffffu
+
+struct Pool {
+    float4 *rayO, *rayD;      // (o.xyz, mint) (d.xyz, maxt): the 32-byte ray record
+    float4 *hit;              // (t, u, v, leafpos): the 16-byte hit record
+    float4 *thr;              // (throughput rgb, pdf_mat)
+    float4 *rad;              // (radiance rgb, -)
+    float4 *shO, *shD, *shC;  // shadow ray + its pending contribution
+    uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
+    uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
+    uint32_t *flags;          // PF_*
+    uint32_t *queue[NORI_BSDF_COUNT];
+    uint32_t P;
+};
+
+struct Counters {
+    unsigned long long next_sample, total_samples, done;
+    unsigned long long rays, shadow_rays, nodes, prims, invalid;
+    uint32_t qcount[NORI_BSDF_COUNT];
+    uint32_t work_extend, work_shadow, pad;
+};
+
+struct Batch {
+    float4 *results;          // [spp_local][H][W] (r,g,b,valid)
+    uint64_t seed;            // initstate of sample k is seed + k
+    uint32_t spp_first;       // first absolute sample index of this batch
+    uint32_t wh;              // W*H
+};
+
+__device__ __forceinline__ void warpAdd(unsigned long long *dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long) v);
+}
+
+__device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uint32_t sid, V3 rad) {
+    bool ok = validColor(rad);
+    bt.results[sid] = ok ? make_float4(rad.x, rad.y, rad.z, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!ok) atomicAdd(&ctr->invalid, 1ull);
+}
+
+// ------------------------------------------------------------------------------ raygen
+__global__ void __launch_bounds__(256) k_generate(DScene sc, Pool pool, Batch bt, Counters *ctr) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[i] = 0;
+        ctr->work_extend = 0; ctr->work_shadow = 0;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t limit = (pool.P + 31u) & ~31u;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < limit; slot += stride) {
+        bool isFree = slot < pool.P && pool.sid[slot] == NORI_FREE_SLOT;
+        uint32_t mask = __ballot_sync(0xffffffffu, isFree);
+        if (!mask) continue;
+        unsigned long long base = 0;
+        int leader = __ffs(mask) - 1;
+        if ((threadIdx.x & 31) == leader) base = atomicAdd(&ctr->next_sample, (unsigned long long) __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (!isFree) continue;
+        unsigned long long id = base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+        if (id >= ctr->total_samples) continue;                 // nothing left: the slot stays free
+        const uint32_t sid = (uint32_t) id;
+        const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
+        const int W = sc.camera.width;
+        const int py = pix / W, px = pix - py * W;
+        Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+        P2 a = rng.next2D();                                    // render.cpp:98-99
+        P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
+        P2 ap = rng.next2D();
+        Ray ray = cameraRay(sc.camera, ps, ap);
+        pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+        pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+        pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pool.rng[slot] = rng.state;
+        pool.sid[slot] = sid;
+        pool.flags[slot] = PF_ALIVE | PF_FIRST;
+    }
+}
+
+// ------------------------------------------------------------------------------ extend
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_extend, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= pool.P) break;
+        const uint32_t slot = base + lane;
+        const bool active = slot < pool.P && (pool.flags[slot] & PF_ALIVE);
+        int type = -1;
+        if (active) {
+            const float4 ro = pool.rayO[slot], rd = pool.rayD[slot];
+            Hit h;
+            ++nRays;
+            bool found = traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt);
+            if (found) {
+                pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
+                const uint32_t shape = __float_as_uint(__ldg(&sc.prims[3 * h.leafpos + 1]).w);
+                type = sc.shapes[shape].bsdf_type;
+            } else {                                             // path_mis.cpp:28-29 / :84-85: the path ends here
+                const float4 r = pool.rad[slot];
+                finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+                pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0;
+                ++nDone;
+            }
+        }
+        // bin the hits by material with one atomic per (warp, material)
+#pragma unroll
+        for (int t = 0; t < NORI_BSDF_COUNT; ++t) {
+            const uint32_t m = __ballot_sync(0xffffffffu, type == t);
+            if (!m) continue;
+            uint32_t qb = 0; const int leader = __ffs(m) - 1;
+            if (lane == leader) qb = atomicAdd(&ctr->qcount[t], (uint32_t) __popc(m));
+            qb = __shfl_sync(0xffffffffu, qb, leader);
+            if (type == t) pool.queue[t][qb + __popc(m & ((1u << lane) - 1u))] = slot;
+        }
+    }
+    warpAdd(&ctr->rays, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes, cnt.nodes); warpAdd(&ctr->prims, cnt.prims); }
+}
+
+// ------------------------------------------------------------------------------ shade
+template <int BSDF, bool MIS>
+__global__ void __launch_bounds__(128) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr) {
+    const uint32_t n = ctr->qcount[BSDF];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nDone = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t slot = pool.queue[BSDF][i];
+        const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
+        const uint32_t sid = pool.sid[slot];
+        PathState st;
+        st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
+        st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
+        st.flags = pool.flags[slot];
+        st.rng.state = pool.rng[slot]; st.rng.inc = ((uint64_t) (sid % bt.wh) << 1u) | 1u;
+        Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
+        VertexOut out;
+        pathVertex<BSDF, MIS>(sc, h, st, out);
+        if (st.flags & PF_SHADOW) {
+            pool.shO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, out.shadow.mint);
+            pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
+            pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
+        }
+        if (st.flags & PF_ALIVE) {
+            pool.rayO[slot] = make_float4(out.next.o.x, out.next.o.y, out.next.o.z, out.next.mint);
+            pool.rayD[slot] = make_float4(out.next.d.x, out.next.d.y, out.next.d.z, out.next.maxt);
+            pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
+            pool.rng[slot] = st.rng.state;
+        }
+        if (!MIS && (st.flags & PF_TERMINATE)) {                 // path_mats has no pending shadow ray
+            finalizePath(bt, ctr, sid, st.rad);
+            pool.sid[slot] = NORI_FREE_SLOT; st.flags = 0; ++nDone;
+        } else pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
+        pool.flags[slot] = st.flags;
+    }
+    if (!MIS) {
+        // all lanes must reach the shuffle
+        warpAdd(&ctr->done, nDone);
+    }
+}
+
+// ------------------------------------------------------------------------------ shadow
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(DScene sc, Pool pool, Batch bt, Counters *ctr) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= pool.P) break;
+        const uint32_t slot = base + lane;
+        if (slot >= pool.P) continue;
+        const uint32_t flags = pool.flags[slot];
+        if (!(flags & PF_SHADOW)) continue;
+        const float4 so = pool.shO[slot], sd = pool.shD[slot];
+        Hit h; ++nRays;
+        const bool occluded = traverse<true, COUNT>(sc, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), so.w, sd.w, h, cnt);
+        float4 r = pool.rad[slot];
+        if (!occluded) { const float4 c = pool.shC[slot]; r.x = __fadd_rn(r.x, c.x); r.y = __fadd_rn(r.y, c.y); r.z = __fadd_rn(r.z, c.z); }
+        if (flags & PF_TERMINATE) {
+            finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+            pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0; ++nDone;
+        } else {
+            if (!occluded) pool.rad[slot] = r;
+            pool.flags[slot] = flags & ~PF_SHADOW;
+        }
+    }
+    warpAdd(&ctr->rays, nRays); warpAdd(&ctr->shadow_rays, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes, cnt.nodes); warpAdd(&ctr->prims, cnt.prims); }
+}
+
+// ------------------------------------------------------------------------------ short integrators
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_mega(DScene sc, Batch bt, Counters *ctr, unsigned long long total) {
+    const unsigned long long id = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    RayStats rs; rs.rays = 0; rs.shadow = 0; rs.cnt.nodes = 0; rs.cnt.prims = 0;
+    if (id < total) {
+        const uint32_t sid = (uint32_t) id;
+        const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
+        const int W = sc.camera.width;
+        const int py = pix / W, px = pix - py * W;
+        Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+        P2 a = rng.next2D();
+        P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
+        P2 ap = rng.next2D();
+        Ray ray = cameraRay(sc.camera, ps, ap);
+        V3 L = liDispatch<COUNT>(sc, rng, ray, rs);
+        finalizePath(bt, ctr, sid, L);
+    }
+    warpAdd(&ctr->rays, rs.rays); warpAdd(&ctr->shadow_rays, rs.shadow);
+    if (COUNT) { warpAdd(&ctr->nodes, rs.cnt.nodes); warpAdd(&ctr->prims, rs.cnt.prims); }
+}
+
+// ------------------------------------------------------------------------------ film
+struct FilmParams {
+    float4 *film;             // (H+2b) x (W+2b) row-major (r,g,b,w): the memory image of ImageBlock m_block
+    int W, H, border, halo;   // halo == border: source pixels that can reach a film pixel
+    float radius, lookupFactor;
+    float table[NORI_FILTER_RESOLUTION + 1];
+};
+
+// smem per layer: (32+2*halo)^2 x { float4 value, float2 pos }
+__global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t nLayers) {
+    extern __shared__ float4 s_mem[];
+    const int T = 32, halo = fp.halo, S = T + 2 * halo, nS = S * S;
+    float4 *s_val = s_mem;
+    float2 *s_pos = (float2 *) (s_mem + nS);
+    __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
+    const int tid = threadIdx.y * T + threadIdx.x;
+    if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
+    const int b = fp.border;
+    const int fx = blockIdx.x * T + threadIdx.x, fy = blockIdx.y * T + threadIdx.y;   // film pixel owned by this thread
+    const int sx0 = blockIdx.x * T - b - halo, sy0 = blockIdx.y * T - b - halo;       // image coords of the staged region
+    const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < nLayers; ++k) {
+        __syncthreads();
+        for (int i = tid; i < nS; i += T * T) {
+            const int ly = i / S, lx = i - ly * S;
+            const int sx = sx0 + lx, sy = sy0 + ly;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f); float2 p = make_float2(0.f, 0.f);
+            if (sx >= 0 && sx < fp.W && sy >= 0 && sy < fp.H) {
+                const uint32_t pix = (uint32_t) sy * fp.W + sx;
+                v = bt.results[(size_t) k * bt.wh + pix];
+                Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+                P2 a = rng.next2D();
+                const float psx = (float) sx + a.x, psy = (float) sy + a.y;
+                // block.cpp:101-104 with the offset of the 32x32 block that rendered the sample
+                const int ox = sx & ~(NORI_BLOCK_SIZE - 1), oy = sy & ~(NORI_BLOCK_SIZE - 1);
+                p.x = __fsub_rn(__fsub_rn(psx, 0.5f), (float) (ox - b));
+                p.y = __fsub_rn(__fsub_rn(psy, 0.5f), (float) (oy - b));
+            }
+            s_val[i] = v; s_pos[i] = p;
+        }
+        __syncthreads();
+        if (fx < fcols && fy < frows) {
+            // staged-region coordinates of the source pixels that can reach (fx, fy)
+            const int cx = threadIdx.x + halo, cy = threadIdx.y + halo;   // own source pixel (image x = fx - b)
+            for (int dy = -halo; dy <= halo; ++dy) {
+                const int sy = sy0 + cy + dy;
+                if (sy < 0 || sy >= fp.H) continue;
+                const int oy = sy & ~(NORI_BLOCK_SIZE - 1);
+                const float yb = (float) (fy - oy);                        // pixel row in that block's coordinates
+                for (int dx = -halo; dx <= halo; ++dx) {
+                    const int sx = sx0 + cx + dx;
+                    if (sx < 0 || sx >= fp.W) continue;
+                    const int ox = sx & ~(NORI_BLOCK_SIZE - 1);
+                    const float xb = (float) (fx - ox);
+                    const int i = (cy + dy) * S + (cx + dx);
+                    const float2 p = s_pos[i];
+                    // window [ceil(p-r), floor(p+r)] of block.cpp:107-110
+                    if (xb < __fsub_rn(p.x, fp.radius) || xb > __fadd_rn(p.x, fp.radius)) continue;
+                    if (yb < __fsub_rn(p.y, fp.radius) || yb > __fadd_rn(p.y, fp.radius)) continue;
+                    const float wx = s_table[(int) __fmul_rn(fabsf(__fsub_rn(xb, p.x)), fp.lookupFactor)];
+                    const float wy = s_table[(int) __fmul_rn(fabsf(__fsub_rn(yb, p.y)), fp.lookupFactor)];
+                    const float4 v = s_val[i];
+                    // Color4f(value) * wx * wy (block.cpp:121)
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                }
+            }
+        }
+    }
+    if (fx < fcols && fy < frows) {
+        float4 *dst = &fp.film[(size_t) fy * fcols + fx];
+        float4 f = *dst;
+        f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+        *dst = f;
+    }
+}
+
+__global__ void k_resolve(const float4 *film, float *rgb, int W, int H, int b) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 c = film[(size_t) (y + b) * (W + 2 * b) + (x + b)];
+    float *o = &rgb[((size_t) y * W + x) * 3];
+    if (c.w != 0.f) { o[0] = c.x / c.w; o[1] = c.y / c.w; o[2] = c.z / c.w; } else { o[0] = o[1] = o[2] = 0.f; }
+}
+
+// ------------------------------------------------------------------------------ test hooks
+template <bool SHADOW>
+__global__ void __launch_bounds__(128) k_trace(DScene sc, const nori_gpu_ray *rays, unsigned long long n, nori_gpu_hit *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_ray r = rays[i];
+    Hit h; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    bool found = traverse<SHADOW, true>(sc, mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, h, cnt);
+    nori_gpu_hit o;
+    o.t = h.t; o.u = h.u; o.v = h.v; o.shape = NORI_NO_HIT; o.prim = NORI_NO_HIT;
+    o.nodes_visited = cnt.nodes; o.prims_tested = cnt.prims; o.reserved = 0;
+    if (found && !SHADOW) {
+        o.prim = __float_as_uint(sc.prims[3 * h.leafpos].w);
+        o.shape = __float_as_uint(sc.prims[3 * h.leafpos + 1].w);
+    }
+    out[i] = o;
+}
+
+__global__ void k_pcg32(uint64_t initstate, uint64_t initseq, unsigned long long n, float *outf, uint32_t *outu) {
+    if (blockIdx.x || threadIdx.x) return;
+    Pcg32 r; r.seed(initstate, initseq);
+    for (unsigned long long i = 0; i < n; ++i) { if (outf) outf[i] = r.nextFloat(); else outu[i] = r.nextUInt(); }
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_flush(float4 *buf, size_t n) {     // bench helper: evict L2 between timed steps
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}

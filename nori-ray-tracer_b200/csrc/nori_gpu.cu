@@ -1,0 +1,486 @@
+// nori_gpu.cu -- the extern "C" boundary of include/nori_gpu.h over the kernels in kernels.cuh.
+// One context = one CUDA device + one stream.  No torch, no exceptions across the ABI, no CPU
+// fallback: every entry point that computes does so on the device or fails with an error string.
+#include "kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static std::string g_init_error;
+
+struct nori_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool has_scene = false;
+
+    DScene ds{};
+    std::vector<void *> scene_allocs;
+    nori_gpu_filter filter{};
+    int W = 0, H = 0, border = 0;
+    uint32_t bsdf_mask = 0;            // which BSDF types occur in the scene
+
+    float4 *film = nullptr;
+    Pool pool{};
+    std::vector<void *> pool_allocs;
+    float4 *results = nullptr; size_t results_cap = 0;      // in float4 elements
+    Counters *ctr = nullptr; Counters *h_ctr = nullptr;      // device / pinned host
+    float4 *flush_buf = nullptr; size_t flush_n = 0;
+
+    // options
+    int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+
+    nori_gpu_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return 1; } } while (0)
+
+template <typename T> static int devUpload(nori_gpu_ctx *ctx, std::vector<void *> &owner, const T *src, size_t n, const T **out) {
+    *out = nullptr;
+    if (!n) return 0;
+    void *d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(T)));
+    owner.push_back(d);
+    CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const T *) d;
+    return 0;
+}
+
+static void freeAll(std::vector<void *> &v) { for (void *p : v) cudaFree(p); v.clear(); }
+
+extern "C" {
+
+int nori_gpu_init(int device, nori_gpu_ctx **out) {
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_init_error = std::string("nori_gpu_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return 1;
+    }
+    if (device < 0 || device >= n) { g_init_error = "nori_gpu_init: device index out of range"; return 1; }
+    nori_gpu_ctx *ctx = new nori_gpu_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaMalloc((void **) &ctx->ctr, sizeof(Counters)) != cudaSuccess
+        || cudaMallocHost((void **) &ctx->h_ctr, sizeof(Counters)) != cudaSuccess
+        || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        g_init_error = std::string("nori_gpu_init: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx; return 1;
+    }
+    cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return 0;
+}
+
+void nori_gpu_destroy(nori_gpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    freeAll(ctx->scene_allocs); freeAll(ctx->pool_allocs);
+    cudaFree(ctx->film); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
+    cudaFreeHost(ctx->h_ctr);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *nori_gpu_last_error(const nori_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int nori_gpu_abi_sizes(uint32_t *out, int n) {
+    const uint32_t s[] = {sizeof(nori_gpu_bvh_node), sizeof(nori_gpu_shape), sizeof(nori_gpu_bsdf), sizeof(nori_gpu_emitter),
+                          sizeof(nori_gpu_camera), sizeof(nori_gpu_filter), sizeof(nori_gpu_medium), sizeof(nori_gpu_scene),
+                          sizeof(nori_gpu_ray), sizeof(nori_gpu_hit), sizeof(nori_gpu_stats)};
+    int m = (int) (sizeof(s) / sizeof(s[0]));
+    for (int i = 0; i < n && i < m; ++i) out[i] = s[i];
+    return m;
+}
+
+int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
+    REQUIRE(ctx && name, "set_option: null argument");
+    std::string k(name);
+    if (k == "pool") { REQUIRE(value >= 1024 && value <= (1ll << 26), "pool must be in [1024, 2^26]"); ctx->opt_pool = value; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
+    else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
+    else if (k == "stats") ctx->opt_stats = value != 0;
+    else if (k == "megakernel") ctx->opt_megakernel = value != 0;
+    else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
+    else if (k == "flush_l2") {
+        // bench helper: overwrite a buffer larger than L2 (value = MiB)
+        CK(cudaSetDevice(ctx->device));
+        size_t n = (size_t) value * (1 << 20) / sizeof(float4);
+        if (n > ctx->flush_n) { cudaFree(ctx->flush_buf); ctx->flush_buf = nullptr; CK(cudaMalloc((void **) &ctx->flush_buf, n * sizeof(float4))); ctx->flush_n = n; }
+        k_flush<<<148 * 8, 256, 0, ctx->stream>>>(ctx->flush_buf, n);
+        CK(cudaGetLastError());
+    } else { ctx->err = "set_option: unknown option '" + k + "'"; return 1; }
+    return 0;
+}
+
+int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
+    REQUIRE(ctx && s, "upload_scene: null argument");
+    REQUIRE(s->abi_version == NORI_GPU_ABI_VERSION, "upload_scene: ABI version mismatch");
+    REQUIRE(s->integrator >= 0 && s->integrator <= NORI_INTEGRATOR_VOLUMETRIC, "upload_scene: unknown integrator");
+    REQUIRE(s->camera.width > 0 && s->camera.height > 0, "upload_scene: empty film");
+    REQUIRE(s->filter.radius > 0.f && s->filter.radius <= 8.f, "upload_scene: filter radius must be in (0, 8]");
+    REQUIRE(s->n_shapes == 0 || (s->nodes && s->indices && s->shape_offset && s->shapes && s->bsdfs), "upload_scene: null scene arrays");
+    REQUIRE(s->integrator != NORI_INTEGRATOR_VOLUMETRIC || s->medium.present, "upload_scene: volumetric integrator needs a medium");
+    bool needLights = s->integrator == NORI_INTEGRATOR_PATH_MIS || s->integrator == NORI_INTEGRATOR_VOLUMETRIC;
+    REQUIRE(!needLights || s->n_emitters > 0, "upload_scene: this integrator needs at least one emitter (Scene::getRandomEmitter)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    freeAll(ctx->scene_allocs);
+    ctx->has_scene = false;
+    DScene ds{};
+    ds.n_nodes = s->n_nodes; ds.n_prims = s->n_indices; ds.n_shapes = s->n_shapes; ds.n_emitters = s->n_emitters;
+    ds.integrator = s->integrator; ds.av_length = s->av_length; ds.camera = s->camera; ds.medium = s->medium;
+
+    // ---- per-shape arrays + shape table
+    std::vector<DShape> shapes(s->n_shapes);
+    uint32_t mask = 0;
+    for (uint32_t i = 0; i < s->n_shapes; ++i) {
+        const nori_gpu_shape &h = s->shapes[i];
+        DShape &d = shapes[i]; memset(&d, 0, sizeof(d));
+        REQUIRE(h.bsdf >= 0 && (uint32_t) h.bsdf < s->n_bsdfs, "upload_scene: shape references a missing BSDF");
+        REQUIRE(h.emitter < (int32_t) s->n_emitters, "upload_scene: shape references a missing emitter");
+        d.type = h.type; d.bsdf = h.bsdf; d.emitter = h.emitter; d.bsdf_type = s->bsdfs[h.bsdf].type;
+        REQUIRE(d.bsdf_type >= 0 && d.bsdf_type < NORI_BSDF_COUNT, "upload_scene: unknown BSDF type");
+        mask |= 1u << d.bsdf_type;
+        d.n_triangles = h.n_triangles; d.area_normalization = h.area_normalization;
+        d.cx = h.center[0]; d.cy = h.center[1]; d.cz = h.center[2]; d.radius = h.radius;
+        if (h.type == NORI_SHAPE_MESH) {
+            REQUIRE(h.V && h.F, "upload_scene: mesh without vertices/faces");
+            if (devUpload(ctx, ctx->scene_allocs, h.V, 3 * (size_t) h.n_vertices, &d.V)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.N, h.N ? 3 * (size_t) h.n_vertices : 0, &d.N)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.UV, h.UV ? 2 * (size_t) h.n_vertices : 0, &d.UV)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.F, 3 * (size_t) h.n_triangles, &d.F)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.area_cdf, h.area_cdf ? (size_t) h.n_triangles + 1 : 0, &d.cdf)) return 1;
+            d.has_n = h.N != nullptr; d.has_uv = h.UV != nullptr;
+            REQUIRE(h.emitter < 0 || h.area_cdf, "upload_scene: emitter mesh without an area CDF");
+        } else {
+            REQUIRE(h.type == NORI_SHAPE_SPHERE, "upload_scene: unknown shape type");
+            // sphere.cpp:99: std::pow(1.f / r, 2) [double] * 0.25f * INV_PI [float]
+            double ir = (double) (1.f / h.radius);
+            d.sphere_pdf = (float) (ir * ir * (double) (0.25f * NORI_INV_PI));
+        }
+    }
+    // ---- primitive records in leaf order (48 B each): same arithmetic as mesh.cpp:88 for the edges
+    std::vector<float4> prims(3 * (size_t) s->n_indices);
+    for (uint32_t i = 0; i < s->n_indices; ++i) {
+        uint32_t idx = s->indices[i];
+        REQUIRE(idx < s->shape_offset[s->n_shapes], "upload_scene: primitive index out of range");
+        const uint32_t *it = std::lower_bound(s->shape_offset, s->shape_offset + s->n_shapes + 1, idx + 1) - 1;   // bvh.h:105-109
+        uint32_t shape = (uint32_t) (it - s->shape_offset); idx -= *it;
+        const nori_gpu_shape &h = s->shapes[shape];
+        float4 *r = &prims[3 * (size_t) i];
+        uint32_t tag;
+        if (h.type == NORI_SHAPE_MESH) {
+            REQUIRE(idx < h.n_triangles, "upload_scene: triangle index out of range");
+            const uint32_t i0 = h.F[3 * idx], i1 = h.F[3 * idx + 1], i2 = h.F[3 * idx + 2];
+            REQUIRE(i0 < h.n_vertices && i1 < h.n_vertices && i2 < h.n_vertices, "upload_scene: vertex index out of range");
+            const float *p0 = &h.V[3 * i0], *p1 = &h.V[3 * i1], *p2 = &h.V[3 * i2];
+            r[0] = make_float4(p0[0], p0[1], p0[2], 0.f);
+            r[1] = make_float4(p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2], 0.f);
+            r[2] = make_float4(p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2], 0.f);
+            tag = 0u;
+        } else {
+            r[0] = make_float4(h.center[0], h.center[1], h.center[2], 0.f);
+            r[1] = make_float4(h.radius, 0.f, 0.f, 0.f);
+            r[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tag = 1u;
+        }
+        memcpy(&r[0].w, &idx, 4); memcpy(&r[1].w, &shape, 4); memcpy(&r[2].w, &tag, 4);
+    }
+    // ---- emitters
+    std::vector<DEmitter> ems(s->n_emitters);
+    for (uint32_t i = 0; i < s->n_emitters; ++i) {
+        ems[i].pod = s->emitters[i];
+        nori_gpu_emitter &e = ems[i].pod;
+        REQUIRE(e.type >= 0 && e.type <= NORI_EMITTER_ENVMAP, "upload_scene: unknown emitter type");
+        if (e.type == NORI_EMITTER_AREA || e.type == NORI_EMITTER_ENVMAP)
+            REQUIRE(e.shape >= 0 && (uint32_t) e.shape < s->n_shapes, "upload_scene: area/envmap emitter without a shape");
+        if (e.type == NORI_EMITTER_ENVMAP) {
+            const nori_gpu_emitter &h = s->emitters[i];
+            REQUIRE(h.env_rows > 1 && h.env_cols > 1 && h.env_image && h.env_pdf && h.env_cdf && h.env_pmarginal && h.env_cmarginal,
+                    "upload_scene: incomplete environment map tables");
+            size_t R = h.env_rows, C = h.env_cols;
+            if (devUpload(ctx, ctx->scene_allocs, h.env_image, R * C * 3, &e.env_image)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.env_pdf, R * C, &e.env_pdf)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.env_cdf, R * (C + 1), &e.env_cdf)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.env_pmarginal, R, &e.env_pmarginal)) return 1;
+            if (devUpload(ctx, ctx->scene_allocs, h.env_cmarginal, R + 1, &e.env_cmarginal)) return 1;
+        } else { e.env_image = e.env_pdf = e.env_cdf = e.env_pmarginal = e.env_cmarginal = nullptr; }
+    }
+    static_assert(sizeof(nori_gpu_bvh_node) == 2 * sizeof(uint4), "node layout");
+    if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) s->nodes, 2 * (size_t) s->n_nodes, &ds.nodes)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, prims.data(), prims.size(), &ds.prims)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, shapes.data(), shapes.size(), &ds.shapes)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, s->bsdfs, (size_t) s->n_bsdfs, &ds.bsdfs)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, ems.data(), ems.size(), &ds.emitters)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));         // host staging vectors die at return
+
+    ctx->ds = ds; ctx->filter = s->filter; ctx->bsdf_mask = mask;
+    ctx->W = s->camera.width; ctx->H = s->camera.height;
+    ctx->border = (int) std::ceil(s->filter.radius - 0.5f);              // block.cpp:57
+    cudaFree(ctx->film); ctx->film = nullptr;
+    size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+    CK(cudaMalloc((void **) &ctx->film, nf * sizeof(float4)));
+    CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
+    ctx->has_scene = true;
+    return 0;
+}
+
+} // extern "C"
+
+static int ensurePool(nori_gpu_ctx *ctx) {
+    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty()) return 0;
+    freeAll(ctx->pool_allocs);
+    Pool p{}; p.P = (uint32_t) ctx->opt_pool;
+    auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
+    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shO, &p.shD, &p.shC};
+    for (auto pp : f4) { *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
+    p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
+    REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
+    for (int t = 0; t < NORI_BSDF_COUNT; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }
+    k_fill_u32<<<(p.P + 255) / 256, 256, 0, ctx->stream>>>(p.sid, NORI_FREE_SLOT, p.P);
+    CK(cudaMemsetAsync(p.flags, 0, p.P * 4, ctx->stream));
+    CK(cudaGetLastError());
+    ctx->pool = p;
+    return 0;
+}
+
+static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
+    if (n <= ctx->results_cap) return 0;
+    cudaFree(ctx->results); ctx->results = nullptr; ctx->results_cap = 0;
+    CK(cudaMalloc((void **) &ctx->results, n * sizeof(float4)));
+    ctx->results_cap = n;
+    return 0;
+}
+
+template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid) {
+    const uint32_t m = ctx->bsdf_mask;
+    if (m & (1u << NORI_BSDF_DIFFUSE)) k_shade<NORI_BSDF_DIFFUSE, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+    if (m & (1u << NORI_BSDF_MIRROR)) k_shade<NORI_BSDF_MIRROR, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+    if (m & (1u << NORI_BSDF_DIELECTRIC)) k_shade<NORI_BSDF_DIELECTRIC, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+    if (m & (1u << NORI_BSDF_MICROFACET)) k_shade<NORI_BSDF_MICROFACET, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+    if (m & (1u << NORI_BSDF_DISNEY)) k_shade<NORI_BSDF_DISNEY, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+}
+
+// Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
+static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
+    const unsigned long long total = (unsigned long long) nLayers * bt.wh;
+    const bool count = ctx->opt_stats != 0;
+    const int integ = ctx->ds.integrator;
+    const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS) && !ctx->opt_megakernel;
+    if (!wave) {
+        const unsigned grid = (unsigned) ((total + 127) / 128);
+        if (count) k_mega<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total);
+        else k_mega<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total);
+        CK(cudaGetLastError());
+        ctx->stats.iterations += 1;
+        return 0;
+    }
+    if (ensurePool(ctx)) return 1;
+    // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
+    Counters zero{}; zero.total_samples = total;
+    *ctx->h_ctr = zero;
+    CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int occE = 8, occS = 8;
+    if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<true>, 128, 0); }
+    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
+    const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridG = sms * 8, gridSh = sms * 16;
+    const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
+    while (true) {
+        for (int it = 0; it < ctx->opt_poll; ++it) {
+            k_generate<<<gridG, 256, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+            if (count) k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+            else k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+            if (mis) {
+                launchShade<true>(ctx, bt, gridSh);
+                if (count) k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+                else k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+            } else launchShade<false>(ctx, bt, gridSh);
+            ctx->stats.iterations += 1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_ctr->done >= total) break;
+    }
+    return 0;
+}
+
+static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.samples += samples;
+    ctx->stats.rays += ctx->h_ctr->rays; ctx->stats.shadow_rays += ctx->h_ctr->shadow_rays;
+    ctx->stats.nodes_visited += ctx->h_ctr->nodes; ctx->stats.prims_tested += ctx->h_ctr->prims;
+    ctx->stats.invalid_samples += ctx->h_ctr->invalid;
+    CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream));
+    return 0;
+}
+
+static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, float *out_rgba) {
+    REQUIRE(ctx && ctx->has_scene, "render: no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    if (spp_count == 0) return 0;
+    const uint32_t wh = (uint32_t) ctx->W * ctx->H;
+    REQUIRE((unsigned long long) wh * 1 < 0xffffffffull, "render: image too large");
+    size_t maxLayers = std::max<size_t>(1, ((size_t) ctx->opt_results_mb << 20) / ((size_t) wh * sizeof(float4)));
+    maxLayers = std::min<size_t>(maxLayers, 0xfffffff0ull / wh);       // sample ids are 32-bit inside a batch
+    REQUIRE(maxLayers >= 1, "render: image too large for a single-layer batch");
+    if (ensureResults(ctx, std::min<size_t>(maxLayers, spp_count) * wh)) return 1;
+    CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    FilmParams fp{};
+    fp.film = ctx->film; fp.W = ctx->W; fp.H = ctx->H; fp.border = ctx->border; fp.halo = ctx->border;
+    fp.radius = ctx->filter.radius; fp.lookupFactor = NORI_FILTER_RESOLUTION / ctx->filter.radius;      // block.cpp:64
+    memcpy(fp.table, ctx->filter.table, sizeof(fp.table));
+    for (uint32_t done = 0; done < spp_count;) {
+        uint32_t n = (uint32_t) std::min<size_t>(maxLayers, spp_count - done);
+        Batch bt{}; bt.results = ctx->results; bt.seed = seed; bt.spp_first = spp_begin + done; bt.wh = wh;
+        if (traceBatch(ctx, bt, n)) return 1;
+        if (out_rgba) {
+            CK(cudaMemcpyAsync(out_rgba + (size_t) done * wh * 4, ctx->results, (size_t) n * wh * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        } else {
+            const int S = 32 + 2 * fp.halo;
+            size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
+            CK(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            dim3 grid((ctx->W + 2 * ctx->border + 31) / 32, (ctx->H + 2 * ctx->border + 31) / 32);
+            k_film<<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n);
+            CK(cudaGetLastError());
+        }
+        if (foldStats(ctx, (unsigned long long) n * wh)) return 1;
+        done += n;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.render_ms = ms;
+    return 0;
+}
+
+extern "C" {
+
+int nori_gpu_render(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed) {
+    return renderImpl(ctx, spp_begin, spp_count, seed, nullptr);
+}
+
+int nori_gpu_render_samples(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, float *out_rgba) {
+    REQUIRE(ctx && out_rgba, "render_samples: null output");
+    return renderImpl(ctx, spp_begin, spp_count, seed, out_rgba);
+}
+
+int nori_gpu_clear_film(nori_gpu_ctx *ctx) {
+    REQUIRE(ctx && ctx->has_scene, "clear_film: no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+    CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
+    return 0;
+}
+
+int nori_gpu_download_film(nori_gpu_ctx *ctx, float *rgbaw) {
+    REQUIRE(ctx && ctx->has_scene && rgbaw, "download_film: no scene / null buffer");
+    CK(cudaSetDevice(ctx->device));
+    size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+    CK(cudaMemcpyAsync(rgbaw, ctx->film, nf * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int nori_gpu_upload_film(nori_gpu_ctx *ctx, const float *rgbaw) {
+    REQUIRE(ctx && ctx->has_scene && rgbaw, "upload_film: no scene / null buffer");
+    CK(cudaSetDevice(ctx->device));
+    size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+    CK(cudaMemcpyAsync(ctx->film, rgbaw, nf * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int nori_gpu_film_device_ptr(nori_gpu_ctx *ctx, void **dptr, uint64_t *n_floats) {
+    REQUIRE(ctx && ctx->has_scene && dptr && n_floats, "film_device_ptr: no scene / null argument");
+    *dptr = ctx->film;
+    *n_floats = (uint64_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border) * 4;
+    return 0;
+}
+
+int nori_gpu_film_dims(const nori_gpu_ctx *ctx, int32_t *rows, int32_t *cols, int32_t *border) {
+    if (!ctx || !ctx->has_scene) return 1;
+    *rows = ctx->H + 2 * ctx->border; *cols = ctx->W + 2 * ctx->border; *border = ctx->border;
+    return 0;
+}
+
+int nori_gpu_resolve(nori_gpu_ctx *ctx, float *rgb) {
+    REQUIRE(ctx && ctx->has_scene && rgb, "resolve: no scene / null buffer");
+    CK(cudaSetDevice(ctx->device));
+    float *d = nullptr; size_t n = (size_t) ctx->W * ctx->H * 3;
+    CK(cudaMalloc((void **) &d, n * sizeof(float)));
+    dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    k_resolve<<<grid, blk, 0, ctx->stream>>>(ctx->film, d, ctx->W, ctx->H, ctx->border);
+    cudaError_t e = cudaMemcpyAsync(rgb, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = std::string("resolve: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out) {
+    REQUIRE(ctx && ctx->has_scene, "trace: no scene uploaded");
+    if (n == 0) return 0;                                  // empty batch is a no-op
+    REQUIRE(rays && out, "trace: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    nori_gpu_ray *dr = nullptr; nori_gpu_hit *dh = nullptr;
+    CK(cudaMalloc((void **) &dr, n * sizeof(nori_gpu_ray)));
+    if (cudaMalloc((void **) &dh, n * sizeof(nori_gpu_hit)) != cudaSuccess) { cudaFree(dr); ctx->err = "trace: out of device memory"; return 1; }
+    cudaError_t e = cudaMemcpyAsync(dr, rays, n * sizeof(nori_gpu_ray), cudaMemcpyHostToDevice, ctx->stream);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    const unsigned grid = (unsigned) ((n + 127) / 128);
+    if (shadow) k_trace<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
+    else k_trace<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dh, n * sizeof(nori_gpu_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f; if (e == cudaSuccess) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.trace_ms = ms;
+    cudaFree(dr); cudaFree(dh);
+    if (e != cudaSuccess) { ctx->err = std::string("trace: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+} // extern "C"
+
+static int pcgImpl(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *outf, uint32_t *outu) {
+    REQUIRE(ctx, "pcg32: null context");
+    if (n == 0) return 0;
+    REQUIRE(outf || outu, "pcg32: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    CK(cudaMalloc(&d, n * 4));
+    k_pcg32<<<1, 1, 0, ctx->stream>>>(initstate, initseq, n, outf ? (float *) d : nullptr, outf ? nullptr : (uint32_t *) d);
+    cudaError_t e = cudaMemcpyAsync(outf ? (void *) outf : (void *) outu, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = std::string("pcg32: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+extern "C" {
+
+int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out) { return pcgImpl(ctx, initstate, initseq, n, out, nullptr); }
+int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out) { return pcgImpl(ctx, initstate, initseq, n, nullptr, out); }
+
+int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out) { REQUIRE(ctx && out, "get_stats: null argument"); *out = ctx->stats; return 0; }
+int nori_gpu_reset_stats(nori_gpu_ctx *ctx) { REQUIRE(ctx, "reset_stats: null context"); ctx->stats = nori_gpu_stats{}; return 0; }
+int nori_gpu_synchronize(nori_gpu_ctx *ctx) { REQUIRE(ctx, "synchronize: null context"); CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+} // extern "C"

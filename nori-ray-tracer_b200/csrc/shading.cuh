@@ -1,0 +1,471 @@
+// shading.cuh -- device restatement of the per-vertex work of the reference's integrators:
+// hit information, frames, warps, BSDF sample/eval/pdf, emitter sample/eval/pdf, cameras.
+// Each function cites the reference lines whose behaviour it reproduces (quirks included; see
+// SURVEY.md appendix A).  None of this is shared with oracle/ -- the oracle is an independent
+// scalar C++ restatement used only by the tests.
+#pragma once
+#include "device_common.cuh"
+#include "traverse.cuh"
+
+struct Frame { V3 s, t, n; };
+struct Its {                      // shape.h:38-67 (geoFrame is never read by the hot-path integrators)
+    V3 p; P2 uv; Frame sh; int shape;
+};
+
+// common.cpp:274-283 + frame.h:49-51
+__device__ __forceinline__ Frame makeFrame(V3 a) {
+    Frame f; f.n = a;
+    V3 c;
+    if (fabsf(a.x) > fabsf(a.y)) {
+        float invLen = 1.0f / sqrtf(a.x * a.x + a.z * a.z);
+        c = mk(a.z * invLen, 0.0f, -a.x * invLen);
+    } else {
+        float invLen = 1.0f / sqrtf(a.y * a.y + a.z * a.z);
+        c = mk(0.0f, a.z * invLen, -a.y * invLen);
+    }
+    f.s = cross(c, a); f.t = c;
+    return f;
+}
+__device__ __forceinline__ V3 toLocal(const Frame &f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }
+__device__ __forceinline__ V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }
+
+// mesh.cpp:122-170, sphere.cpp:78-93
+__device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit &h, Its &its) {
+    const float4 r0 = __ldg(&sc.prims[3 * h.leafpos]);
+    const float4 r1 = __ldg(&sc.prims[3 * h.leafpos + 1]);
+    const float4 r2 = __ldg(&sc.prims[3 * h.leafpos + 2]);
+    its.shape = (int) __float_as_uint(r1.w);
+    const DShape &m = sc.shapes[its.shape];
+    if (__float_as_uint(r2.w) == 0u) {
+        const uint32_t prim = __float_as_uint(r0.w);
+        const float b1 = h.u, b2 = h.v, b0 = 1 - (b1 + b2);
+        const uint32_t i0 = __ldg(&m.F[3 * prim]), i1 = __ldg(&m.F[3 * prim + 1]), i2 = __ldg(&m.F[3 * prim + 2]);
+        const V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
+        its.p = (b0 * p0 + b1 * p1) + b2 * p2;
+        its.uv.x = b1; its.uv.y = b2;
+        if (m.has_uv) {
+            its.uv.x = (b0 * __ldg(&m.UV[2 * i0]) + b1 * __ldg(&m.UV[2 * i1])) + b2 * __ldg(&m.UV[2 * i2]);
+            its.uv.y = (b0 * __ldg(&m.UV[2 * i0 + 1]) + b1 * __ldg(&m.UV[2 * i1 + 1])) + b2 * __ldg(&m.UV[2 * i2 + 1]);
+        }
+        V3 n;
+        if (m.has_n) n = normalized((b0 * ld3(&m.N[3 * i0]) + b1 * ld3(&m.N[3 * i1])) + b2 * ld3(&m.N[3 * i2]));
+        else n = normalized(cross(p1 - p0, p2 - p0));
+        its.sh = makeFrame(n);
+    } else {
+        const V3 c = mk(r0.x, r0.y, r0.z);
+        its.p = o + h.t * d;
+        const V3 n = normalized(its.p - c);
+        its.sh = makeFrame(n);
+        float th = acosf(n.z), ph = atan2f(n.y, n.x);            // common.cpp:264-272
+        if (ph < 0) ph += 2 * NORI_PI;
+        its.uv.x = (float) (0.5 + th / (2 * NORI_PI));
+        its.uv.y = ph / NORI_PI;
+    }
+}
+
+// ------------------------------------------------------------------------------ warps (warp.cpp)
+__device__ __forceinline__ V3 sphericalDir(float theta, float phi) {
+    float st, ct, sp, cp; sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+    return mk(st * cp, st * sp, ct);
+}
+__device__ __forceinline__ V3 squareToUniformSphere(P2 s) { return sphericalDir(acosf(1 - 2 * (1 - s.x)), 2.f * NORI_PI * s.y); }   // :86-91
+__device__ __forceinline__ V3 squareToCosineHemisphere(P2 s) { return sphericalDir(acosf(sqrtf(1 - (1 - s.x))), 2.f * NORI_PI * s.y); }  // :110-115
+__device__ __forceinline__ V3 squareToBeckmann(P2 s, float alpha) {                                                      // :122-127
+    float theta = (float) atan(sqrt(-((double) alpha * (double) alpha) * (double) logf(1 - s.x)));
+    return sphericalDir(theta, 2 * NORI_PI * s.y);
+}
+__device__ __forceinline__ V3 squareToUniformTriangle(P2 s) {                                                            // :135-140
+    float su1 = sqrtf(s.x); float u = 1.f - su1, v = s.y * su1;
+    return mk(u, v, 1.f - u - v);
+}
+__device__ __forceinline__ P2 squareToConcentricDisk(P2 s) {                                                             // :143-162
+    float ox = 2.f * s.x - 1.f, oy = 2.f * s.y - 1.f; P2 r; r.x = 0.f; r.y = 0.f;
+    if (ox == 0.f && oy == 0.f) return r;
+    float theta, rad;
+    if (fabsf(ox) > fabsf(oy)) { rad = ox; theta = NORI_PI * 0.25f * (oy / ox); }
+    else { rad = oy; theta = NORI_PI * 0.5f - NORI_PI * 0.25f * (ox / oy); }
+    r.x = rad * cosf(theta); r.y = rad * sinf(theta); return r;
+}
+__device__ __forceinline__ V3 squareToGTR2(P2 s, float alpha) {                                                          // :180-185
+    float a2 = (float) ((double) alpha * (double) alpha);
+    return sphericalDir(acosf(sqrtf((1.0f - s.x) / (1.0f + (a2 - 1.0f) * s.x))), 2 * NORI_PI * s.y);
+}
+__device__ __forceinline__ float squareToGTR2Pdf(V3 m, float alpha) {                                                    // :187-193
+    float a2 = (float) ((double) alpha * (double) alpha);
+    float c = m.z;
+    double den = 1 + (double) (a2 - 1.0f) * ((double) c * (double) c);
+    float pdf = (float) ((double) (a2 * c * NORI_INV_PI) / (den * den));
+    return (c >= 0 && fabsf(sqnorm(m) - 1.0f) < 1.0f) ? pdf : 0.0f;
+}
+
+// common.cpp:285-314
+__device__ __forceinline__ float fresnel(float cosThetaI, float extIOR, float intIOR) {
+    float etaI = extIOR, etaT = intIOR;
+    if (extIOR == intIOR) return 0.0f;
+    if (cosThetaI < 0.0f) { float t = etaI; etaI = etaT; etaT = t; cosThetaI = -cosThetaI; }
+    float eta = etaI / etaT, sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
+    if (sinThetaTSqr > 1.0f) return 1.0f;
+    float cosThetaT = sqrtf(1.0f - sinThetaTSqr);
+    float Rs = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    float Rp = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    return (Rs * Rs + Rp * Rp) / 2.0f;
+}
+__device__ __forceinline__ float tanTheta(V3 v) { float t = 1 - v.z * v.z; if (t <= 0.0f) return 0.0f; return sqrtf(t) / v.z; }   // frame.h:81-86
+
+// ------------------------------------------------------------------------------ BSDFs
+enum { M_UNKNOWN = 0, M_SOLID_ANGLE = 1, M_DISCRETE = 2 };
+struct BRec { V3 wi, wo; int measure; P2 uv; };                  // bsdf.h:30-58
+
+__device__ __forceinline__ V3 albedoAt(const nori_gpu_bsdf &b, P2 uv) {
+    if (b.albedo_texture == NORI_TEXTURE_CHECKERBOARD) {          // checkerboard.cpp:31-37
+        int x = (int) fabsf(floorf(uv.x / b.tex_scale[0] - b.tex_delta[0]));
+        int y = (int) fabsf(floorf(uv.y / b.tex_scale[1] - b.tex_delta[1]));
+        return x % 2 == y % 2 ? arr3(b.albedo) : arr3(b.albedo2);
+    }
+    return arr3(b.albedo);                                        // consttexture.cpp:30-32
+}
+__device__ __forceinline__ float evalBeckmann(float alpha, V3 m) {                                    // microfacet.cpp:52-58
+    float temp = tanTheta(m) / alpha, ct = m.z, ct2 = ct * ct;
+    return expf(-temp * temp) / (NORI_PI * alpha * alpha * ct2 * ct2);
+}
+__device__ __forceinline__ float smithBeckmannG1(float alpha, V3 v, V3 m) {                            // microfacet.cpp:61-82
+    float tt = tanTheta(v);
+    if (tt == 0.0f) return 1.0f;
+    if (dot(m, v) * v.z <= 0) return 0.0f;
+    float a = 1.0f / (alpha * tt);
+    if (a >= 1.6f) return 1.0f;
+    float a2 = a * a;
+    return (3.535f * a + 2.181f * a2) / (1.0f + 2.276f * a + 2.577f * a2);
+}
+__device__ __forceinline__ float schlickFresnel(float u) {                                             // disney.cpp:26-30
+    float m = fminf(1.0f, fmaxf(0.0f, 1 - u)); double md = m; return (float) (md * md * md * md * md);
+}
+__device__ __forceinline__ float ggx(float NdotV, float alphaG) { float a = alphaG * alphaG, b = NdotV * NdotV; return 1 / (NdotV + sqrtf(a + b - a * b)); }   // disney.cpp:32-37
+__device__ __forceinline__ V3 lerp3(float t, V3 a, V3 b) { return (1.0f - t) * a + t * b; }                 // disney.cpp:40-43
+__device__ __forceinline__ float luminance(V3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }   // common.cpp:233-235
+
+template <int TYPE>
+__device__ __forceinline__ V3 bsdfEval(const nori_gpu_bsdf &b, const BRec &r) {
+    if (TYPE == NORI_BSDF_DIFFUSE) {                              // diffuse.cpp:72-82
+        if (r.measure != M_SOLID_ANGLE || r.wi.z <= 0 || r.wo.z <= 0) return mk(0.f);
+        return albedoAt(b, r.uv) * NORI_INV_PI;
+    } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:84-94
+        V3 n = normalized(r.wi + r.wo);
+        float D = evalBeckmann(b.alpha, n);
+        float F = fresnel(dot(n, r.wi), b.extIOR, b.intIOR);
+        float G = smithBeckmannG1(b.alpha, r.wi, n) * smithBeckmannG1(b.alpha, r.wo, n);
+        float denom = 4.0f * r.wi.z * r.wo.z;
+        float spec = b.ks * D * F * G / denom;
+        V3 kd = arr3(b.kd) * NORI_INV_PI;
+        return mk(kd.x + spec, kd.y + spec, kd.z + spec);
+    } else if (TYPE == NORI_BSDF_DISNEY) {                        // disney.cpp:63-105
+        float NdotV = r.wi.z, NdotL = r.wo.z;
+        if (NdotV < 0 || NdotL < 0) return mk(0.f);
+        V3 wh = normalized(r.wi + r.wo);
+        float LdotH = dot(r.wo, wh), VdotH = dot(r.wi, wh);
+        V3 base = arr3(b.baseColor), white = mk(1.f);
+        float lum = luminance(base);
+        V3 Ctint = lum > 0.f ? mk(base.x / lum, base.y / lum, base.z / lum) : mk(1.0f);
+        V3 CtintMix = (float) ((double) b.specular * 0.08) * lerp3(b.specularTint, white, Ctint);
+        V3 Cspec = lerp3(b.metallic, CtintMix, base);
+        float fd90 = (float) (0.5 + (double) (2 * b.roughness) * ((double) VdotH * (double) VdotH));
+        float fl = schlickFresnel(NdotL), fv = schlickFresnel(NdotV);
+        V3 diffuse = base * NORI_INV_PI * (1.f + (fd90 - 1.f) * fl) * (1.f + (fd90 - 1.f) * fv);
+        float alpha = fmaxf(0.001f, b.roughness * b.roughness);
+        float Ds = squareToGTR2Pdf(wh, alpha);
+        float FH = schlickFresnel(LdotH);
+        V3 Fs = lerp3(FH, Cspec, white);
+        float Gs = ggx(NdotL, alpha) * ggx(NdotV, alpha);
+        V3 specular = Gs * Fs * Ds;
+        V3 Fsheen = FH * b.sheen * lerp3(b.sheenTint, white, Ctint);
+        return (1 - b.metallic) * (diffuse + Fsheen) + specular;
+    }
+    return mk(0.f);                                               // mirror.cpp:29-32, dielectric.cpp:35-38
+}
+
+template <int TYPE>
+__device__ __forceinline__ float bsdfPdf(const nori_gpu_bsdf &b, const BRec &r) {
+    if (TYPE == NORI_BSDF_DIFFUSE) {                              // diffuse.cpp:85-101
+        if (r.measure != M_SOLID_ANGLE || r.wi.z <= 0 || r.wo.z <= 0) return 0.0f;
+        return NORI_INV_PI * r.wo.z;
+    } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:97-111
+        float c = r.wo.z; if (c <= 0.0f) return 0.0f;
+        V3 n = normalized(r.wi + r.wo);
+        float metallicTerm = evalBeckmann(b.alpha, n) * n.z / (4.0f * fabsf(dot(n, r.wo)));
+        return b.ks * metallicTerm + (1 - b.ks) * (c * NORI_INV_PI);
+    } else if (TYPE == NORI_BSDF_DISNEY) {                        // disney.cpp:108-121
+        float c = r.wo.z; if (c <= 0.0f) return 0.0f;
+        V3 n = normalized(r.wi + r.wo);
+        float metallicTerm = squareToGTR2Pdf(n, b.alpha) * n.z / (4.0f * fabsf(dot(n, r.wo)));
+        return (1 - b.metallic) * (c * NORI_INV_PI) + b.metallic * metallicTerm;
+    }
+    return 0.0f;
+}
+
+// returns the importance weight; on failure wo stays (0,0,0) like the reference's zero-filled
+// TVector (vector.h:49), which makes the next ray miss everything
+template <int TYPE>
+__device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+    r.wo = mk(0.f);
+    if (TYPE == NORI_BSDF_DIFFUSE) {                              // diffuse.cpp:104-120
+        if (r.wi.z <= 0) return mk(0.f);
+        r.measure = M_SOLID_ANGLE; r.wo = squareToCosineHemisphere(s);
+        return albedoAt(b, r.uv);
+    } else if (TYPE == NORI_BSDF_MIRROR) {                        // mirror.cpp:39-55
+        if (r.wi.z <= 0) return mk(0.f);
+        r.wo = mk(-r.wi.x, -r.wi.y, r.wi.z); r.measure = M_DISCRETE;
+        return mk(1.f);
+    } else if (TYPE == NORI_BSDF_DIELECTRIC) {                    // dielectric.cpp:45-73
+        float theta = r.wi.z; V3 nv = mk(0.f, 0.f, 1.0f);
+        if (fresnel(theta, b.extIOR, b.intIOR) > s.x) r.wo = mk(-r.wi.x, -r.wi.y, r.wi.z);
+        else {
+            float factor = b.extIOR / b.intIOR;
+            if (theta < 0.0f) { factor = 1 / factor; nv.z *= -1; }
+            float win = dot(r.wi, nv);
+            V3 part1 = -factor * (r.wi - win * nv);
+            double f2 = (double) factor * (double) factor, w2 = (double) win * (double) win;
+            V3 part2 = -nv * (float) sqrt(1 - f2 * (1 - w2));
+            r.wo = normalized(part1 + part2);
+        }
+        r.measure = M_DISCRETE;
+        return mk(1.f);
+    } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:114-137
+        if (r.wi.z <= 0.0f) return mk(0.f);
+        if (s.x < b.ks) {
+            P2 ns; ns.x = s.x / b.ks; ns.y = s.y;
+            V3 n = squareToBeckmann(ns, b.alpha);
+            r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
+        } else {
+            P2 ns; ns.x = (s.x - b.ks) / (1.f - b.ks); ns.y = s.y;
+            r.wo = squareToCosineHemisphere(ns);
+        }
+        float c = r.wo.z; if (c <= 0.f) return mk(0.f);
+        return bsdfEval<TYPE>(b, r) * c / bsdfPdf<TYPE>(b, r);
+    } else {                                                      // disney.cpp:124-145
+        if (r.wi.z <= 0.0f) return mk(0.f);
+        if (s.x <= b.metallic) {
+            P2 ns; ns.x = s.x / b.metallic; ns.y = s.y;
+            V3 n = squareToGTR2(ns, b.alpha);
+            r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
+        } else {
+            P2 ns; ns.x = (s.x - b.metallic) / (1 - b.metallic); ns.y = s.y;
+            r.wo = squareToCosineHemisphere(ns);
+        }
+        float c = r.wo.z; if (c <= 0.0f) return mk(0.f);
+        return bsdfEval<TYPE>(b, r) * c / bsdfPdf<TYPE>(b, r);
+    }
+}
+
+// runtime-dispatched versions for the single-bounce integrators (megakernel)
+__device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE: return bsdfEval<NORI_BSDF_DIFFUSE>(b, r);
+    case NORI_BSDF_MICROFACET: return bsdfEval<NORI_BSDF_MICROFACET>(b, r);
+    case NORI_BSDF_DISNEY: return bsdfEval<NORI_BSDF_DISNEY>(b, r);
+    default: return mk(0.f);
+    }
+}
+__device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE: return bsdfPdf<NORI_BSDF_DIFFUSE>(b, r);
+    case NORI_BSDF_MICROFACET: return bsdfPdf<NORI_BSDF_MICROFACET>(b, r);
+    case NORI_BSDF_DISNEY: return bsdfPdf<NORI_BSDF_DISNEY>(b, r);
+    default: return 0.f;
+    }
+}
+__device__ __noinline__ V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+    switch (b.type) {
+    case NORI_BSDF_DIFFUSE: return bsdfSample<NORI_BSDF_DIFFUSE>(b, r, s);
+    case NORI_BSDF_MIRROR: return bsdfSample<NORI_BSDF_MIRROR>(b, r, s);
+    case NORI_BSDF_DIELECTRIC: return bsdfSample<NORI_BSDF_DIELECTRIC>(b, r, s);
+    case NORI_BSDF_MICROFACET: return bsdfSample<NORI_BSDF_MICROFACET>(b, r, s);
+    default: return bsdfSample<NORI_BSDF_DISNEY>(b, r, s);
+    }
+}
+
+// ------------------------------------------------------------------------------ emitters
+struct ERec { V3 ref, p, n, wi; float pdf; Ray shadow; };        // emitter.h:31-59
+__device__ __forceinline__ ERec makeERec(V3 ref, V3 p, V3 n) {
+    ERec e; e.ref = ref; e.p = p; e.n = n; e.wi = normalized(p - ref); e.pdf = 0.f; return e;
+}
+__device__ __forceinline__ ERec makeERec(V3 ref) {
+    ERec e; e.ref = ref; e.p = mk(0.f); e.n = mk(0.f); e.wi = mk(0.f); e.pdf = 0.f; return e;
+}
+
+// dpdf.h:119-157 : std::lower_bound over m_cdf, then sample reuse
+__device__ __forceinline__ uint32_t cdfSampleReuse(const float *cdf, uint32_t nEntries /* = F+1 */, float &s) {
+    uint32_t lo = 0, len = nEntries;
+    while (len > 0) {                                             // first element not less than s
+        uint32_t half = len >> 1;
+        if (__ldg(&cdf[lo + half]) < s) { lo += half + 1; len -= half + 1; } else len = half;
+    }
+    int idx = (int) lo - 1; if (idx < 0) idx = 0;
+    if ((uint32_t) idx > nEntries - 2) idx = (int) nEntries - 2;
+    float c0 = __ldg(&cdf[idx]), c1 = __ldg(&cdf[idx + 1]);
+    s = (s - c0) / (c1 - c0);
+    return (uint32_t) idx;
+}
+
+// mesh.cpp:40-61, sphere.cpp:95-105
+__device__ __forceinline__ void sampleSurface(const DShape &m, P2 s, V3 &p, V3 &n, float &pdf) {
+    if (m.type == NORI_SHAPE_MESH) {
+        uint32_t idT = cdfSampleReuse(m.cdf, m.n_triangles + 1, s.x);
+        V3 bc = squareToUniformTriangle(s);
+        uint32_t i0 = __ldg(&m.F[3 * idT]), i1 = __ldg(&m.F[3 * idT + 1]), i2 = __ldg(&m.F[3 * idT + 2]);
+        V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
+        p = (bc.x * p0 + bc.y * p1) + bc.z * p2;
+        if (m.has_n) n = normalized((bc.x * ld3(&m.N[3 * i0]) + bc.y * ld3(&m.N[3 * i1])) + bc.z * ld3(&m.N[3 * i2]));
+        else n = normalized(cross(p1 - p0, p2 - p0));
+        pdf = m.area_normalization;
+    } else {
+        V3 q = squareToUniformSphere(s);
+        p = mk(m.cx, m.cy, m.cz) + m.radius * q; n = q;
+        pdf = m.sphere_pdf;
+    }
+}
+__device__ __forceinline__ float pdfSurface(const DShape &m) { return m.type == NORI_SHAPE_MESH ? m.area_normalization : m.sphere_pdf; }
+
+// envmap.cpp:60-76
+__device__ __forceinline__ P2 envMapIntersect(const nori_gpu_emitter &e, V3 vec) {
+    float th = acosf(vec.z), ph = atan2f(vec.y, vec.x);
+    if (ph < 0) ph += 2 * NORI_PI;
+    P2 r; r.x = th * (e.env_rows - 1) * NORI_INV_PI; r.y = (float) ((double) ph * 0.5 * (e.env_cols - 1) * NORI_INV_PI);
+    if (isnan(r.x) || isnan(r.y)) { r.x = 0.f; r.y = 0.f; }
+    return r;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+__device__ __noinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+    switch (e.type) {
+    case NORI_EMITTER_AREA:                                       // arealight.cpp:39-44
+        return dot(l.n, -l.wi) > 0.0f ? arr3(e.radiance) : mk(0.f);
+    case NORI_EMITTER_POINT:                                      // pointlight.cpp:26-29
+        return arr3(e.radiance) / (4.f * NORI_PI * sqnorm(arr3(e.position) - l.ref));
+    case NORI_EMITTER_SPOT: {                                     // spotlight.cpp:38-42
+        V3 c = arr3(e.radiance) / (4.f * NORI_PI);
+        return c * 2.f * NORI_PI * (float) (1 - 0.5 * (double) (e.cosFalloffStart + e.cosTotalWidth));
+    }
+    default: {                                                    // envmap.cpp:124-156
+        P2 uv = envMapIntersect(e, normalized(l.wi));
+        int W = e.env_rows, H = e.env_cols;
+        int u = clampi((int) uv.x, 0, W - 1), v = clampi((int) uv.y, 0, H - 1);
+        int us = (u + 1) % W, vs = (v + 1) % H;
+        V3 BL = ld3(&e.env_image[((size_t) u * H + v) * 3]), UL = ld3(&e.env_image[((size_t) u * H + vs) * 3]);
+        V3 BR = ld3(&e.env_image[((size_t) us * H + v) * 3]), UR = ld3(&e.env_image[((size_t) us * H + vs) * 3]);
+        int dusu = us - u, dvsv = vs - v;
+        float dusum = us - uv.x, dumu = uv.x - u, dvmv = uv.y - v, dvsvm = vs - uv.y;
+        float k = (float) (1.0 / (double) (dusu * dvsv));
+        return e.weight * (k * ((BL * dusum * dvsvm) + (BR * dumu * dvsvm) + (UL * dusum * dvmv) + (UR * dumu * dvmv)));
+    }
+    }
+}
+
+__device__ __noinline__ float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+    switch (e.type) {
+    case NORI_EMITTER_AREA: return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.shape]) : 0.0f;   // arealight.cpp:64-76
+    case NORI_EMITTER_POINT: return 1.0f;                         // pointlight.cpp:30-33
+    case NORI_EMITTER_SPOT: return l.pdf;                         // spotlight.cpp:44-47
+    default: {                                                    // envmap.cpp:184-192
+        P2 its = envMapIntersect(e, normalized(l.wi));
+        int i = clampi((int) its.x, 0, e.env_rows - 1), j = clampi((int) its.y, 0, e.env_cols - 1);
+        return __ldg(&e.env_pmarginal[i]) * __ldg(&e.env_pdf[(size_t) i * e.env_cols + j]);
+    }
+    }
+}
+
+// envmap.cpp:112-121 (search stops at the last valid interval instead of reading past the table)
+__device__ __forceinline__ void envSample1D(const float *pfRow, const float *PfRow, int nPf, float s, float &x, float &prob) {
+    int i;
+    for (i = 0; i < nPf - 2; i++)
+        if (__ldg(&PfRow[i]) <= s && s < __ldg(&PfRow[i + 1])) break;
+    float P0 = __ldg(&PfRow[i]), P1 = __ldg(&PfRow[i + 1]);
+    float t = (P1 - s) / (P1 - P0);
+    x = (1 - t) * i + t * (i + 1);
+    prob = __ldg(&pfRow[i]);
+}
+
+__device__ __noinline__ V3 emitterSample(const DScene &sc, const nori_gpu_emitter &e, ERec &l, P2 s) {
+    switch (e.type) {
+    case NORI_EMITTER_AREA: {                                     // arealight.cpp:46-62
+        float spdf;
+        sampleSurface(sc.shapes[e.shape], s, l.p, l.n, spdf);
+        l.wi = normalized(l.p - l.ref);
+        l.shadow = mkray(l.ref, l.wi, NORI_EPS, norm(l.p - l.ref) - NORI_EPS);
+        l.pdf = emitterPdf(sc, e, l);
+        float att = dot(l.n, -l.wi) / sqnorm(l.p - l.ref);
+        return l.pdf > 0.0f ? emitterEval(sc, e, l) * att / l.pdf : mk(0.f);
+    }
+    case NORI_EMITTER_POINT: {                                    // pointlight.cpp:15-24
+        V3 pos = arr3(e.position);
+        l.wi = normalized(pos - l.ref); l.p = pos; l.pdf = 1.0f;
+        l.shadow = mkray(l.ref, l.wi, NORI_EPS, norm(pos - l.ref) - NORI_EPS);
+        return arr3(e.radiance) / (4.f * NORI_PI * sqnorm(pos - l.ref));
+    }
+    case NORI_EMITTER_SPOT: {                                     // spotlight.cpp:19-36
+        V3 pos = arr3(e.position), dir = arr3(e.direction);
+        l.wi = normalized(pos - l.ref); l.p = pos; l.pdf = 1.0f; l.n = dir;
+        l.shadow = mkray(l.ref, l.wi, NORI_EPS, norm(pos - l.ref) - NORI_EPS);
+        float cosTheta = dot(dir, normalized(-l.wi)), fall;
+        if (cosTheta < e.cosTotalWidth) fall = 0;
+        else if (cosTheta > e.cosFalloffStart) fall = 1;
+        else fall = (acosf(e.cosTotalWidth) - acosf(cosTheta)) / (acosf(e.cosTotalWidth) - acosf(e.cosFalloffStart));
+        return arr3(e.radiance) * fall / (4.f * NORI_PI * sqnorm(l.ref - l.p));
+    }
+    default: {                                                    // envmap.cpp:158-181
+        int W = e.env_rows, H = e.env_cols;
+        float st2 = 1.0f - l.wi.z * l.wi.z, sinTheta = st2 <= 0.0f ? 0.0f : sqrtf(st2);   // lRec.wi is still (0,0,0) here => 1
+        float jacobian = (float) ((double) ((H - 1) * (W - 1)) / (2 * ((double) NORI_PI * (double) NORI_PI) * (double) sinTheta));
+        float u, v, up, vp;
+        envSample1D(e.env_pmarginal, e.env_cmarginal, W + 1, s.x, u, up);
+        int row = clampi((int) u, 0, W - 1);
+        envSample1D(&e.env_pdf[(size_t) row * H], &e.env_cdf[(size_t) row * (H + 1)], H + 1, s.y, v, vp);
+        float theta = u * NORI_PI / (W - 1), phi = v * 2 * NORI_PI / (H - 1);
+        l.wi = normalized(mk(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta)));
+        l.shadow = mkray(l.ref, l.wi, NORI_EPS, 100000.f);
+        vp = emitterPdf(sc, e, l) * jacobian;
+        return emitterEval(sc, e, l) / vp;
+    }
+    }
+}
+
+// scene.h:68-74
+__device__ __forceinline__ int randomEmitter(const DScene &sc, float rnd) {
+    uint32_t n = sc.n_emitters;
+    uint32_t idx = (uint32_t) floorf((float) n * rnd);
+    return (int) (idx < n - 1 ? idx : n - 1);
+}
+
+// ------------------------------------------------------------------------------ cameras
+__device__ __forceinline__ V3 xfPoint(const float *m, V3 p) {                // transform.h:78-81
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = ((m[4 * i] * p.x + m[4 * i + 1] * p.y) + m[4 * i + 2] * p.z) + m[4 * i + 3] * 1.0f;
+    return mk(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
+}
+__device__ __forceinline__ V3 xfVector(const float *m, V3 v) {               // transform.h:68-70
+    return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+}
+// perspective.cpp:90-112, thinlens.cpp:126-171
+__device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as) {
+    V3 nearP = xfPoint(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
+    V3 d = normalized(nearP);
+    float invZ = 1.0f / d.z;
+    Ray ray;
+    if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
+        P2 disk = squareToConcentricDisk(as);
+        float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
+        float ft = c.focalDistance / d.z;
+        V3 pFocus = mk(0.f) + ft * d;
+        V3 o = mk(lx, ly, 0.0f);
+        V3 dir = normalized(pFocus - o);
+        ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+    } else {
+        ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
+    }
+    ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
+    return ray;
+}
+
+__device__ __forceinline__ bool validColor(V3 c) {                           // common.cpp:224-231
+    return !(c.x < 0 || !isfinite(c.x) || c.y < 0 || !isfinite(c.y) || c.z < 0 || !isfinite(c.z));
+}
