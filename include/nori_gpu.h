@@ -171,9 +171,22 @@ typedef struct {
     uint64_t prims_tested;      /*   "                                                        */
     uint64_t invalid_samples;   /* dropped like block.cpp:94-98                               */
     uint64_t iterations;        /* wavefront iterations executed                              */
+    uint64_t kernel_launches;   /* CUDA kernels launched by render / trace calls              */
     double   render_ms;         /* device time of the last nori_gpu_render (CUDA events)      */
     double   trace_ms;          /* device time of the last nori_gpu_trace kernel              */
 } nori_gpu_stats;
+
+/* per-kernel-class accounting of nori_gpu_render since the last reset (ms only with option
+ * "kernel_timing" = 1: every launch is bracketed by CUDA events on the context's stream) */
+enum { NORI_K_GENERATE = 0, NORI_K_EXTEND = 1, NORI_K_SHADE = 2, NORI_K_SHADOW = 3, NORI_K_FILM = 4,
+       NORI_K_SINGLE = 5, NORI_K_COUNT = 6 };
+typedef struct {
+    double   ms;                /* summed device time of the launches of this class            */
+    uint64_t launches;
+    uint64_t rays;              /* BVH queries issued by this class                            */
+    uint64_t nodes_visited;     /* with option "stats" = 1                                     */
+    uint64_t prims_tested;      /*   "                                                         */
+} nori_gpu_kernel_stats;
 
 /* ---- entry points ---------------------------------------------------------------------------
  * All return 0 on success, non-zero on error (then nori_gpu_last_error() explains).
@@ -190,7 +203,9 @@ const char *nori_gpu_last_error(const nori_gpu_ctx *ctx);   /* ctx may be NULL: 
 int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
 
 /* Tunables: "pool" (resident path slots), "spp_chunk" (samples per pixel per film batch),
- * "stats" (1: count node visits / primitive tests), "flush_l2" (bench only). */
+ * "stats" (1: count node visits / primitive tests), "kernel_timing" (1: CUDA events around every
+ * launch), "megakernel" (1: one thread per sample for every integrator), "poll", "results_mb",
+ * "flush_l2" (bench only: overwrite that many MiB to evict L2). */
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);
 
 /* Render sample indices [spp_begin, spp_begin+spp_count) for every pixel and ACCUMULATE them into
@@ -218,6 +233,13 @@ int nori_gpu_resolve(nori_gpu_ctx *ctx, float *rgb);
  * For shadow rays only `t` (0 = occluded, +inf = free) and the counters are meaningful. */
 int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out);
 
+/* BSDF::eval/pdf/sample (bsdf.h:63-110) and Emitter::sample/pdf/eval (emitter.h:64-105) of one scene
+ * plugin on caller-supplied queries.  Row layouts (floats):
+ *   bsdf:    in  wi.xyz wo.xyz uv.xy sample.xy (10)   out eval.rgb pdf weight.rgb wo'.xyz measure pdf(wo') (12)
+ *   emitter: in  ref.xyz sample.xy (5)                out Li.rgb wi.xyz pdf shadow.mint shadow.maxt p.xyz eval.rgb (15) */
+int nori_gpu_probe_bsdf(nori_gpu_ctx *ctx, uint32_t bsdf, uint64_t n, const float *in, float *out);
+int nori_gpu_probe_emitter(nori_gpu_ctx *ctx, uint32_t emitter, uint64_t n, const float *in, float *out);
+
 /* n floats of pcg32(initstate, initseq).nextFloat() generated on the device (pcg32.h:51-110). */
 int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out);
 /* n raw nextUInt() outputs, for the published pcg32-demo known answers. */
@@ -227,6 +249,7 @@ int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq,
 int nori_gpu_abi_sizes(uint32_t *out, int n);
 
 int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out);
+int nori_gpu_get_kernel_stats(nori_gpu_ctx *ctx, nori_gpu_kernel_stats *out /* [NORI_K_COUNT] */);
 int nori_gpu_reset_stats(nori_gpu_ctx *ctx);
 int nori_gpu_synchronize(nori_gpu_ctx *ctx);
 

@@ -89,9 +89,16 @@ class Hit(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("shadow_rays", u64), ("nodes_visited", u64),
-                ("prims_tested", u64), ("invalid_samples", u64), ("iterations", u64),
+                ("prims_tested", u64), ("invalid_samples", u64), ("iterations", u64), ("kernel_launches", u64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double)]
 
+
+class KernelStats(C.Structure):
+    _fields_ = [("ms", C.c_double), ("launches", u64), ("rays", u64), ("nodes_visited", u64), ("prims_tested", u64)]
+
+
+K_GENERATE, K_EXTEND, K_SHADE, K_SHADOW, K_FILM, K_SINGLE, K_COUNT = range(7)
+K_NAMES = ["generate", "extend", "shade", "shadow", "film", "single"]
 
 import numpy as _np
 
@@ -105,6 +112,6 @@ ENTRY_POINTS = [
     "nori_gpu_init", "nori_gpu_destroy", "nori_gpu_last_error", "nori_gpu_upload_scene",
     "nori_gpu_set_option", "nori_gpu_render", "nori_gpu_render_samples", "nori_gpu_clear_film",
     "nori_gpu_download_film", "nori_gpu_upload_film", "nori_gpu_film_device_ptr",
-    "nori_gpu_film_dims", "nori_gpu_resolve", "nori_gpu_trace", "nori_gpu_pcg32",
-    "nori_gpu_pcg32_uint", "nori_gpu_get_stats", "nori_gpu_reset_stats", "nori_gpu_synchronize",
+    "nori_gpu_film_dims", "nori_gpu_resolve", "nori_gpu_trace", "nori_gpu_probe_bsdf", "nori_gpu_probe_emitter", "nori_gpu_pcg32",
+    "nori_gpu_pcg32_uint", "nori_gpu_abi_sizes", "nori_gpu_get_stats", "nori_gpu_get_kernel_stats", "nori_gpu_reset_stats", "nori_gpu_synchronize",
 ]

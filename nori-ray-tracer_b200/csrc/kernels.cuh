@@ -37,7 +37,7 @@ struct Pool {
 
 struct Counters {
     unsigned long long next_sample, total_samples, done;
-    unsigned long long rays, shadow_rays, nodes, prims, invalid;
+    unsigned long long rays_ext, rays_sh, nodes_ext, prims_ext, nodes_sh, prims_sh, invalid;
     uint32_t qcount[NORI_BSDF_COUNT];
     uint32_t work_extend, work_shadow, pad;
 };
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
             if (type == t) pool.queue[t][qb + __popc(m & ((1u << lane) - 1u))] = slot;
         }
     }
-    warpAdd(&ctr->rays, nRays); warpAdd(&ctr->done, nDone);
-    if (COUNT) { warpAdd(&ctr->nodes, cnt.nodes); warpAdd(&ctr->prims, cnt.prims); }
+    warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
 }
 
 // ------------------------------------------------------------------------------ shade
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(128) k_shadow(DScene sc, Pool pool, Batch bt, 
             pool.flags[slot] = flags & ~PF_SHADOW;
         }
     }
-    warpAdd(&ctr->rays, nRays); warpAdd(&ctr->shadow_rays, nRays); warpAdd(&ctr->done, nDone);
-    if (COUNT) { warpAdd(&ctr->nodes, cnt.nodes); warpAdd(&ctr->prims, cnt.prims); }
+    warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
 
 // ------------------------------------------------------------------------------ short integrators
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(128) k_mega(DScene sc, Batch bt, Counters *ctr
         V3 L = liDispatch<COUNT>(sc, rng, ray, rs);
         finalizePath(bt, ctr, sid, L);
     }
-    warpAdd(&ctr->rays, rs.rays); warpAdd(&ctr->shadow_rays, rs.shadow);
-    if (COUNT) { warpAdd(&ctr->nodes, rs.cnt.nodes); warpAdd(&ctr->prims, rs.cnt.prims); }
+    warpAdd(&ctr->rays_ext, rs.rays - rs.shadow); warpAdd(&ctr->rays_sh, rs.shadow);
+    if (COUNT) { warpAdd(&ctr->nodes_ext, rs.cnt.nodes); warpAdd(&ctr->prims_ext, rs.cnt.prims); }
 }
 
 // ------------------------------------------------------------------------------ film
@@ -346,6 +346,34 @@ __global__ void k_pcg32(uint64_t initstate, uint64_t initseq, unsigned long long
     if (blockIdx.x || threadIdx.x) return;
     Pcg32 r; r.seed(initstate, initseq);
     for (unsigned long long i = 0; i < n; ++i) { if (outf) outf[i] = r.nextFloat(); else outu[i] = r.nextUInt(); }
+}
+
+// per-function probes (rows as in oracle/ref_tools/nori_export.cpp --probe):
+//   bsdf    in (wi.xyz, wo.xyz, uv.xy, sample.xy)   out (eval.rgb, pdf, weight.rgb, wo.xyz, measure, pdf(sampled))
+//   emitter in (ref.xyz, sample.xy)                 out (Li.rgb, wi.xyz, pdf, mint, maxt, p.xyz, eval.rgb)
+__global__ void k_probe_bsdf(DScene sc, uint32_t bsdf, unsigned long long n, const float *in, float *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_bsdf &b = sc.bsdfs[bsdf];
+    const float *q = &in[10 * i]; float *o = &out[12 * i];
+    BRec e; e.wi = mk(q[0], q[1], q[2]); e.wo = mk(q[3], q[4], q[5]); e.measure = M_SOLID_ANGLE; e.uv.x = q[6]; e.uv.y = q[7];
+    V3 ev = bsdfEvalDyn(b, e); float pdf = bsdfPdfDyn(b, e);
+    BRec r; r.wi = e.wi; r.measure = M_UNKNOWN; r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
+    V3 w = bsdfSampleDyn(b, r, s); float pdf2 = bsdfPdfDyn(b, r);
+    o[0] = ev.x; o[1] = ev.y; o[2] = ev.z; o[3] = pdf; o[4] = w.x; o[5] = w.y; o[6] = w.z;
+    o[7] = r.wo.x; o[8] = r.wo.y; o[9] = r.wo.z; o[10] = (float) r.measure; o[11] = pdf2;
+}
+__global__ void k_probe_emitter(DScene sc, uint32_t emitter, unsigned long long n, const float *in, float *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_emitter &em = sc.emitters[emitter].pod;
+    const float *q = &in[5 * i]; float *o = &out[15 * i];
+    ERec e = makeERec(mk(q[0], q[1], q[2])); P2 s; s.x = q[3]; s.y = q[4];
+    e.shadow = mkray(e.ref, mk(0.f));
+    V3 Li = emitterSample(sc, em, e, s); float pdf = emitterPdf(sc, em, e); V3 ev = emitterEval(sc, em, e);
+    o[0] = Li.x; o[1] = Li.y; o[2] = Li.z; o[3] = e.wi.x; o[4] = e.wi.y; o[5] = e.wi.z; o[6] = pdf;
+    o[7] = e.shadow.mint; o[8] = e.shadow.maxt; o[9] = e.p.x; o[10] = e.p.y; o[11] = e.p.z;
+    o[12] = ev.x; o[13] = ev.y; o[14] = ev.z;
 }
 
 __global__ void k_fill_u32(uint32_t *p, uint32_t v, uint32_t n) {

@@ -23,6 +23,7 @@ struct nori_gpu_ctx {
     nori_gpu_filter filter{};
     int W = 0, H = 0, border = 0;
     uint32_t bsdf_mask = 0;            // which BSDF types occur in the scene
+    uint32_t n_bsdfs = 0;
 
     float4 *film = nullptr;
     Pool pool{};
@@ -35,8 +36,28 @@ struct nori_gpu_ctx {
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
 
     nori_gpu_stats stats{};
+    nori_gpu_kernel_stats kstats[NORI_K_COUNT]{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-launch timing (option "kernel_timing")
+    int64_t opt_kernel_timing = 0;
+    std::vector<cudaEvent_t> kev; std::vector<int> kev_kind; size_t kev_used = 0;
+    bool last_wave = false;
 };
+
+// bracket one kernel launch: counts it and, with kernel_timing on, records a CUDA event pair on the stream
+static inline void launchBegin(nori_gpu_ctx *ctx, int kind) {
+    ctx->kstats[kind].launches++; ctx->stats.kernel_launches++;
+    if (!ctx->opt_kernel_timing) return;
+    if (ctx->kev_used + 2 > ctx->kev.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ctx->kev.push_back(a); ctx->kev.push_back(b); }
+    ctx->kev_kind.push_back(kind);
+    cudaEventRecord(ctx->kev[ctx->kev_used], ctx->stream);
+}
+static inline void launchEnd(nori_gpu_ctx *ctx) {
+    if (!ctx->opt_kernel_timing) return;
+    cudaEventRecord(ctx->kev[ctx->kev_used + 1], ctx->stream);
+    ctx->kev_used += 2;
+}
+#define LAUNCH(kind, ...) do { launchBegin(ctx, kind); __VA_ARGS__; launchEnd(ctx); } while (0)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
@@ -89,6 +110,7 @@ void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     cudaFree(ctx->film); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
     cudaFreeHost(ctx->h_ctr);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -111,6 +133,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
     else if (k == "stats") ctx->opt_stats = value != 0;
     else if (k == "megakernel") ctx->opt_megakernel = value != 0;
+    else if (k == "kernel_timing") ctx->opt_kernel_timing = value != 0;
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
         // bench helper: overwrite a buffer larger than L2 (value = MiB)
@@ -225,7 +248,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     if (devUpload(ctx, ctx->scene_allocs, ems.data(), ems.size(), &ds.emitters)) return 1;
     CK(cudaStreamSynchronize(ctx->stream));         // host staging vectors die at return
 
-    ctx->ds = ds; ctx->filter = s->filter; ctx->bsdf_mask = mask;
+    ctx->ds = ds; ctx->filter = s->filter; ctx->bsdf_mask = mask; ctx->n_bsdfs = s->n_bsdfs;
     ctx->W = s->camera.width; ctx->H = s->camera.height;
     ctx->border = (int) std::ceil(s->filter.radius - 0.5f);              // block.cpp:57
     cudaFree(ctx->film); ctx->film = nullptr;
@@ -265,11 +288,11 @@ static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
 
 template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid) {
     const uint32_t m = ctx->bsdf_mask;
-    if (m & (1u << NORI_BSDF_DIFFUSE)) k_shade<NORI_BSDF_DIFFUSE, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-    if (m & (1u << NORI_BSDF_MIRROR)) k_shade<NORI_BSDF_MIRROR, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-    if (m & (1u << NORI_BSDF_DIELECTRIC)) k_shade<NORI_BSDF_DIELECTRIC, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-    if (m & (1u << NORI_BSDF_MICROFACET)) k_shade<NORI_BSDF_MICROFACET, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-    if (m & (1u << NORI_BSDF_DISNEY)) k_shade<NORI_BSDF_DISNEY, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+    if (m & (1u << NORI_BSDF_DIFFUSE)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DIFFUSE, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+    if (m & (1u << NORI_BSDF_MIRROR)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_MIRROR, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+    if (m & (1u << NORI_BSDF_DIELECTRIC)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DIELECTRIC, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+    if (m & (1u << NORI_BSDF_MICROFACET)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_MICROFACET, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+    if (m & (1u << NORI_BSDF_DISNEY)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DISNEY, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
 }
 
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
@@ -280,10 +303,10 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS) && !ctx->opt_megakernel;
     if (!wave) {
         const unsigned grid = (unsigned) ((total + 127) / 128);
-        if (count) k_mega<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total);
-        else k_mega<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total);
+        if (count) LAUNCH(NORI_K_SINGLE, (k_mega<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total)));
+        else LAUNCH(NORI_K_SINGLE, (k_mega<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total)));
         CK(cudaGetLastError());
-        ctx->stats.iterations += 1;
+        ctx->stats.iterations += 1; ctx->last_wave = false;
         return 0;
     }
     if (ensurePool(ctx)) return 1;
@@ -298,15 +321,16 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
     const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridG = sms * 8, gridSh = sms * 16;
     const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
+    ctx->last_wave = true;
     while (true) {
         for (int it = 0; it < ctx->opt_poll; ++it) {
-            k_generate<<<gridG, 256, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-            if (count) k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-            else k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+            LAUNCH(NORI_K_GENERATE, (k_generate<<<gridG, 256, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+            if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+            else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
             if (mis) {
                 launchShade<true>(ctx, bt, gridSh);
-                if (count) k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
-                else k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr);
+                if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+                else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
             } else launchShade<false>(ctx, bt, gridSh);
             ctx->stats.iterations += 1;
         }
@@ -321,10 +345,24 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
 static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const Counters &c = *ctx->h_ctr;
     ctx->stats.samples += samples;
-    ctx->stats.rays += ctx->h_ctr->rays; ctx->stats.shadow_rays += ctx->h_ctr->shadow_rays;
-    ctx->stats.nodes_visited += ctx->h_ctr->nodes; ctx->stats.prims_tested += ctx->h_ctr->prims;
-    ctx->stats.invalid_samples += ctx->h_ctr->invalid;
+    ctx->stats.rays += c.rays_ext + c.rays_sh; ctx->stats.shadow_rays += c.rays_sh;
+    ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
+    ctx->stats.invalid_samples += c.invalid;
+    if (ctx->last_wave) {
+        nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[NORI_K_SHADOW];
+        e.rays += c.rays_ext; e.nodes_visited += c.nodes_ext; e.prims_tested += c.prims_ext;
+        s.rays += c.rays_sh; s.nodes_visited += c.nodes_sh; s.prims_tested += c.prims_sh;
+    } else {
+        nori_gpu_kernel_stats &m = ctx->kstats[NORI_K_SINGLE];
+        m.rays += c.rays_ext + c.rays_sh; m.nodes_visited += c.nodes_ext + c.nodes_sh; m.prims_tested += c.prims_ext + c.prims_sh;
+    }
+    for (size_t i = 0; i < ctx->kev_used; i += 2) {          // the stream is idle here: every event has completed
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->kev[i], ctx->kev[i + 1]) == cudaSuccess) ctx->kstats[ctx->kev_kind[i / 2]].ms += ms;
+    }
+    ctx->kev_used = 0; ctx->kev_kind.clear();
     CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream));
     return 0;
 }
@@ -357,7 +395,7 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
             size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
             CK(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             dim3 grid((ctx->W + 2 * ctx->border + 31) / 32, (ctx->H + 2 * ctx->border + 31) / 32);
-            k_film<<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n);
+            LAUNCH(NORI_K_FILM, (k_film<<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
             CK(cudaGetLastError());
         }
         if (foldStats(ctx, (unsigned long long) n * wh)) return 1;
@@ -447,6 +485,7 @@ int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int 
     const unsigned grid = (unsigned) ((n + 127) / 128);
     if (shadow) k_trace<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
     else k_trace<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
+    ctx->stats.kernel_launches++;
     cudaEventRecord(ctx->ev1, ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dh, n * sizeof(nori_gpu_hit), cudaMemcpyDeviceToHost, ctx->stream);
@@ -459,6 +498,28 @@ int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int 
 }
 
 } // extern "C"
+
+static int probeImpl(nori_gpu_ctx *ctx, bool bsdf, uint32_t index, uint64_t n, const float *in, float *out) {
+    REQUIRE(ctx && ctx->has_scene, "probe: no scene uploaded");
+    if (n == 0) return 0;
+    REQUIRE(in && out, "probe: null buffer");
+    REQUIRE(index < (bsdf ? (uint32_t) ctx->n_bsdfs : ctx->ds.n_emitters), "probe: index out of range");
+    CK(cudaSetDevice(ctx->device));
+    const size_t ni = (bsdf ? 10 : 5) * n, no = (bsdf ? 12 : 15) * n;
+    float *di = nullptr, *dout = nullptr;
+    CK(cudaMalloc((void **) &di, ni * 4));
+    if (cudaMalloc((void **) &dout, no * 4) != cudaSuccess) { cudaFree(di); ctx->err = "probe: out of device memory"; return 1; }
+    cudaError_t e = cudaMemcpyAsync(di, in, ni * 4, cudaMemcpyHostToDevice, ctx->stream);
+    const unsigned grid = (unsigned) ((n + 127) / 128);
+    if (bsdf) k_probe_bsdf<<<grid, 128, 0, ctx->stream>>>(ctx->ds, index, n, di, dout);
+    else k_probe_emitter<<<grid, 128, 0, ctx->stream>>>(ctx->ds, index, n, di, dout);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, no * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(di); cudaFree(dout);
+    if (e != cudaSuccess) { ctx->err = std::string("probe: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
 
 static int pcgImpl(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *outf, uint32_t *outu) {
     REQUIRE(ctx, "pcg32: null context");
@@ -476,11 +537,23 @@ static int pcgImpl(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint
 }
 extern "C" {
 
+int nori_gpu_probe_bsdf(nori_gpu_ctx *ctx, uint32_t bsdf, uint64_t n, const float *in, float *out) { return probeImpl(ctx, true, bsdf, n, in, out); }
+int nori_gpu_probe_emitter(nori_gpu_ctx *ctx, uint32_t emitter, uint64_t n, const float *in, float *out) { return probeImpl(ctx, false, emitter, n, in, out); }
 int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out) { return pcgImpl(ctx, initstate, initseq, n, out, nullptr); }
 int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out) { return pcgImpl(ctx, initstate, initseq, n, nullptr, out); }
 
 int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out) { REQUIRE(ctx && out, "get_stats: null argument"); *out = ctx->stats; return 0; }
-int nori_gpu_reset_stats(nori_gpu_ctx *ctx) { REQUIRE(ctx, "reset_stats: null context"); ctx->stats = nori_gpu_stats{}; return 0; }
+int nori_gpu_get_kernel_stats(nori_gpu_ctx *ctx, nori_gpu_kernel_stats *out) {
+    REQUIRE(ctx && out, "get_kernel_stats: null argument");
+    for (int i = 0; i < NORI_K_COUNT; ++i) out[i] = ctx->kstats[i];
+    return 0;
+}
+int nori_gpu_reset_stats(nori_gpu_ctx *ctx) {
+    REQUIRE(ctx, "reset_stats: null context");
+    ctx->stats = nori_gpu_stats{};
+    for (int i = 0; i < NORI_K_COUNT; ++i) ctx->kstats[i] = nori_gpu_kernel_stats{};
+    return 0;
+}
 int nori_gpu_synchronize(nori_gpu_ctx *ctx) { REQUIRE(ctx, "synchronize: null context"); CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
 
 } // extern "C"

@@ -48,7 +48,7 @@ __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit 
             its.uv.y = (b0 * __ldg(&m.UV[2 * i0 + 1]) + b1 * __ldg(&m.UV[2 * i1 + 1])) + b2 * __ldg(&m.UV[2 * i2 + 1]);
         }
         V3 n;
-        if (m.has_n) n = normalized((b0 * ld3(&m.N[3 * i0]) + b1 * ld3(&m.N[3 * i1])) + b2 * ld3(&m.N[3 * i2]));
+        if (m.has_n) n = normalizedDyn((b0 * ld3(&m.N[3 * i0]) + b1 * ld3(&m.N[3 * i1])) + b2 * ld3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         its.sh = makeFrame(n);
     } else {
@@ -314,7 +314,7 @@ __device__ __forceinline__ void sampleSurface(const DShape &m, P2 s, V3 &p, V3 &
         uint32_t i0 = __ldg(&m.F[3 * idT]), i1 = __ldg(&m.F[3 * idT + 1]), i2 = __ldg(&m.F[3 * idT + 2]);
         V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
         p = (bc.x * p0 + bc.y * p1) + bc.z * p2;
-        if (m.has_n) n = normalized((bc.x * ld3(&m.N[3 * i0]) + bc.y * ld3(&m.N[3 * i1])) + bc.z * ld3(&m.N[3 * i2]));
+        if (m.has_n) n = normalizedDyn((bc.x * ld3(&m.N[3 * i0]) + bc.y * ld3(&m.N[3 * i1])) + bc.z * ld3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         pdf = m.area_normalization;
     } else {

@@ -42,10 +42,13 @@ def load_library():
         "nori_gpu_film_dims": (C.c_int, [vp] + [C.POINTER(C.c_int32)] * 3),
         "nori_gpu_resolve": (C.c_int, [vp, vp]),
         "nori_gpu_trace": (C.c_int, [vp, vp, u64, C.c_int, vp]),
+        "nori_gpu_probe_bsdf": (C.c_int, [vp, u32, u64, vp, vp]),
+        "nori_gpu_probe_emitter": (C.c_int, [vp, u32, u64, vp, vp]),
         "nori_gpu_pcg32": (C.c_int, [vp, u64, u64, u64, vp]),
         "nori_gpu_pcg32_uint": (C.c_int, [vp, u64, u64, u64, vp]),
         "nori_gpu_abi_sizes": (C.c_int, [C.POINTER(u32), C.c_int]),
         "nori_gpu_get_stats": (C.c_int, [vp, C.POINTER(abi.Stats)]),
+        "nori_gpu_get_kernel_stats": (C.c_int, [vp, C.POINTER(abi.KernelStats)]),
         "nori_gpu_reset_stats": (C.c_int, [vp]),
         "nori_gpu_synchronize": (C.c_int, [vp]),
     }
@@ -147,6 +150,18 @@ class NoriGpu:
         self._check(self.lib.nori_gpu_trace(self.ctx, rays.ctypes.data, rays.shape[0], int(shadow), hits.ctypes.data))
         return hits
 
+    def probe_bsdf(self, index, queries):
+        q = np.ascontiguousarray(queries, np.float32)
+        out = np.zeros((len(q), 12), np.float32)
+        self._check(self.lib.nori_gpu_probe_bsdf(self.ctx, index, len(q), q.ctypes.data, out.ctypes.data))
+        return out
+
+    def probe_emitter(self, index, queries):
+        q = np.ascontiguousarray(queries, np.float32)
+        out = np.zeros((len(q), 15), np.float32)
+        self._check(self.lib.nori_gpu_probe_emitter(self.ctx, index, len(q), q.ctypes.data, out.ctypes.data))
+        return out
+
     def pcg32(self, initstate, initseq, n):
         out = np.empty(n, np.float32)
         self._check(self.lib.nori_gpu_pcg32(self.ctx, initstate, initseq, n, out.ctypes.data))
@@ -161,6 +176,12 @@ class NoriGpu:
         s = abi.Stats()
         self._check(self.lib.nori_gpu_get_stats(self.ctx, C.byref(s)))
         return s
+
+    def kernel_stats(self):
+        arr = (abi.KernelStats * abi.K_COUNT)()
+        self._check(self.lib.nori_gpu_get_kernel_stats(self.ctx, arr))
+        return {abi.K_NAMES[i]: dict(ms=arr[i].ms, launches=arr[i].launches, rays=arr[i].rays,
+                                     nodes=arr[i].nodes_visited, prims=arr[i].prims_tested) for i in range(abi.K_COUNT)}
 
     def reset_stats(self):
         self._check(self.lib.nori_gpu_reset_stats(self.ctx))

@@ -79,6 +79,10 @@ inline float norm(V3 a) { return std::sqrt(sqnorm(a)); }
 inline V3 normalized(V3 a) { return a / norm(a); }
 inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 inline V3 load3(const float *p) { return {p[0], p[1], p[2]}; }
+/* Mesh::getInterpolatedNormal / setHitInformation normalise a DYNAMIC-size Eigen expression (sums of
+ * MatrixXf columns, mesh.cpp:63-73,147-160): Eigen's non-unrolled redux adds left to right,
+ * (x*x + y*y) + z*z -- unlike the fixed-size order used everywhere else.  Measured with the probes. */
+inline V3 normalizedDyn(V3 a) { float n = std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); return a / n; }
 
 struct P2 { float x = 0, y = 0; };
 
@@ -226,7 +230,7 @@ void setHitInformation(const Scene &sc, const Ray &ray, Its &its) {
         its.geo = makeFrame(normalized(cross(p1 - p0, p2 - p0)));
         if (!m.N.empty()) {
             V3 n = (b0 * load3(&m.N[3 * i0]) + b1 * load3(&m.N[3 * i1])) + b2 * load3(&m.N[3 * i2]);
-            its.sh = makeFrame(normalized(n));
+            its.sh = makeFrame(normalizedDyn(n));
         } else its.sh = its.geo;
     } else {
         /* by now ray.maxt == its.t (bvh.cpp:444) */
@@ -522,7 +526,7 @@ void sampleSurface(const Shape &m, P2 s, V3 &p, V3 &n, float &pdf) {
         uint32_t i0 = m.F[3 * idT], i1 = m.F[3 * idT + 1], i2 = m.F[3 * idT + 2];
         V3 p0 = load3(&m.V[3 * i0]), p1 = load3(&m.V[3 * i1]), p2 = load3(&m.V[3 * i2]);
         p = (bc.x * p0 + bc.y * p1) + bc.z * p2;
-        if (!m.N.empty()) n = normalized((bc.x * load3(&m.N[3 * i0]) + bc.y * load3(&m.N[3 * i1])) + bc.z * load3(&m.N[3 * i2]));
+        if (!m.N.empty()) n = normalizedDyn((bc.x * load3(&m.N[3 * i0]) + bc.y * load3(&m.N[3 * i1])) + bc.z * load3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         pdf = m.pod.area_normalization;
     } else {
@@ -1098,6 +1102,31 @@ void nori_oracle_block_sequence(void *h, uint64_t n, float *out) {
                 P2 ps; V3 v = cameraSample(*sc, rng, x, y, ps);
                 float *o = &out[5 * done]; o[0] = ps.x; o[1] = ps.y; o[2] = v.x; o[3] = v.y; o[4] = v.z;
             }
+}
+
+/* Per-function probes, same row layout as nori_export --probe (see oracle/ref_tools/nori_export.cpp). */
+void nori_oracle_bsdf_probe(void *h, uint32_t bsdf, uint64_t n, const float *in, float *out) {
+    Scene *sc = (Scene *) h; const nori_gpu_bsdf &b = sc->bsdfs[bsdf];
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *q = &in[10 * i]; float *o = &out[12 * i];
+        BRec e; e.wi = load3(q); e.wo = load3(q + 3); e.measure = ESolidAngle; e.uv.x = q[6]; e.uv.y = q[7];
+        V3 ev = bsdfEval(b, e); float pdf = bsdfPdf(b, e);
+        BRec r; r.wi = load3(q); r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
+        V3 w = bsdfSample(b, r, s); float pdf2 = bsdfPdf(b, r);
+        o[0] = ev.x; o[1] = ev.y; o[2] = ev.z; o[3] = pdf; o[4] = w.x; o[5] = w.y; o[6] = w.z;
+        o[7] = r.wo.x; o[8] = r.wo.y; o[9] = r.wo.z; o[10] = (float) r.measure; o[11] = pdf2;
+    }
+}
+void nori_oracle_emitter_probe(void *h, uint32_t emitter, uint64_t n, const float *in, float *out) {
+    Scene *sc = (Scene *) h; const Emitter &em = sc->emitters[emitter];
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *q = &in[5 * i]; float *o = &out[15 * i];
+        ERec e; e.ref = load3(q); P2 s; s.x = q[3]; s.y = q[4];
+        V3 Li = emitterSample(*sc, em, e, s); float pdf = emitterPdf(*sc, em, e); V3 ev = emitterEval(*sc, em, e);
+        o[0] = Li.x; o[1] = Li.y; o[2] = Li.z; o[3] = e.wi.x; o[4] = e.wi.y; o[5] = e.wi.z; o[6] = pdf;
+        o[7] = e.shadowRay.mint; o[8] = e.shadowRay.maxt; o[9] = e.p.x; o[10] = e.p.y; o[11] = e.p.z;
+        o[12] = ev.x; o[13] = ev.y; o[14] = ev.z;
+    }
 }
 
 /* ImageBlock::toBitmap, block.cpp:76-82 + color.h:84-89 */

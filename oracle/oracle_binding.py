@@ -32,6 +32,8 @@ def _load(abi):
     lib.nori_oracle_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nori_oracle_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
     lib.nori_oracle_reset_stats.argtypes = [C.c_void_p]
+    lib.nori_oracle_bsdf_probe.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.nori_oracle_emitter_probe.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.nori_oracle_block_sequence.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     return lib
 
@@ -93,6 +95,16 @@ class Oracle:
     def block_sequence(self, n):
         out = np.zeros((n, 5), np.float32)
         self.lib.nori_oracle_block_sequence(self.h, n, out.ctypes.data)
+        return out
+
+    def bsdf_probe(self, index, queries):
+        q = np.ascontiguousarray(queries, np.float32); out = np.zeros((len(q), 12), np.float32)
+        self.lib.nori_oracle_bsdf_probe(self.h, index, len(q), q.ctypes.data, out.ctypes.data)
+        return out
+
+    def emitter_probe(self, index, queries):
+        q = np.ascontiguousarray(queries, np.float32); out = np.zeros((len(q), 15), np.float32)
+        self.lib.nori_oracle_emitter_probe(self.h, index, len(q), q.ctypes.data, out.ctypes.data)
         return out
 
     def stats(self):

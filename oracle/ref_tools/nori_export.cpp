@@ -170,13 +170,14 @@ static Replay replay(const BVH *bvh, const Ray3f &_ray, bool shadowRay) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 3) { cerr << "usage: nori_export scene.xml out.nscene [--rays N] [--seed S] [--seq N]" << endl; return 1; }
+    if (argc < 3) { cerr << "usage: nori_export scene.xml out.nscene [--rays N] [--seed S] [--seq N] [--probe N]" << endl; return 1; }
     std::string xml = argv[1], out = argv[2];
-    size_t nRays = 0, nSeq = 0; uint64_t seed = 1;
+    size_t nRays = 0, nSeq = 0, nProbe = 0; uint64_t seed = 1;
     for (int i = 3; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--rays")) nRays = (size_t) atoll(argv[i + 1]);
         if (!strcmp(argv[i], "--seed")) seed = (uint64_t) atoll(argv[i + 1]);
         if (!strcmp(argv[i], "--seq")) nSeq = (size_t) atoll(argv[i + 1]);
+        if (!strcmp(argv[i], "--probe")) nProbe = (size_t) atoll(argv[i + 1]);
     }
     try {
         installFactoryHook();
@@ -435,6 +436,55 @@ int main(int argc, char **argv) {
                         seq.insert(seq.end(), {pixelSample.x(), pixelSample.y(), value[0], value[1], value[2]});
                     }
             w.f32("seq", {nSeq, 5}, seq.data());
+        }
+
+        /* ---- plugin probes: the reference's own BSDF::eval/pdf/sample and Emitter::sample/eval/pdf
+         *      answers on seeded random queries (golden vectors for the per-function parity tests).
+         *      bsdf rows:    in  (wi.xyz, wo.xyz, uv.xy, sample.xy)                        = 10 floats
+         *                    out (eval.rgb, pdf, weight.rgb, sampled wo.xyz, measure, pdf(sampled)) = 12 floats
+         *      emitter rows: in  (ref.xyz, sample.xy)                                      = 5 floats
+         *                    out (Li.rgb, wi.xyz, pdf, shadow.mint, shadow.maxt, p.xyz, eval.rgb) = 15 floats */
+        if (nProbe > 0) {
+            pcg32 rng(seed, 11);
+            auto unit = [&]() { return Warp::squareToUniformSphere(Point2f(rng.nextFloat(), rng.nextFloat())); };
+            std::vector<const BSDF *> order(bsdfs.size());
+            for (auto &kv : bsdfIndex) order[kv.second] = kv.first;
+            for (size_t b = 0; b < order.size(); ++b) {
+                std::vector<float> in, out;
+                for (size_t i = 0; i < nProbe; ++i) {
+                    Vector3f wi = unit(), wo = unit();
+                    if (i % 4 != 3) wi.z() = std::abs(wi.z());
+                    if (i % 8 < 6) wo.z() = std::abs(wo.z());
+                    Point2f uv(rng.nextFloat(), rng.nextFloat()), smp(rng.nextFloat(), rng.nextFloat());
+                    BSDFQueryRecord q(wi, wo, ESolidAngle); q.uv = uv;
+                    Color3f ev = order[b]->eval(q); float pdf = order[b]->pdf(q);
+                    BSDFQueryRecord r(wi); r.uv = uv;
+                    Color3f wgt = order[b]->sample(r, smp);
+                    float pdf2 = order[b]->pdf(r);
+                    in.insert(in.end(), {wi.x(), wi.y(), wi.z(), wo.x(), wo.y(), wo.z(), uv.x(), uv.y(), smp.x(), smp.y()});
+                    out.insert(out.end(), {ev[0], ev[1], ev[2], pdf, wgt[0], wgt[1], wgt[2], r.wo.x(), r.wo.y(), r.wo.z(), (float) r.measure, pdf2});
+                }
+                w.f32("probe.bsdf." + std::to_string(b) + ".in", {nProbe, 10}, in.data());
+                w.f32("probe.bsdf." + std::to_string(b) + ".out", {nProbe, 12}, out.data());
+            }
+            BoundingBox3f bb = scene->getBoundingBox();
+            for (size_t e = 0; e < lights.size(); ++e) {
+                std::vector<float> in, out;
+                for (size_t i = 0; i < nProbe; ++i) {
+                    Point3f ref;
+                    for (int k = 0; k < 3; ++k) ref[k] = bb.min[k] + rng.nextFloat() * (bb.max[k] - bb.min[k]);
+                    Point2f smp(rng.nextFloat(), rng.nextFloat());
+                    EmitterQueryRecord q(ref);
+                    Color3f Li = lights[e]->sample(q, smp);
+                    float pdf = lights[e]->pdf(q);
+                    Color3f ev = lights[e]->eval(q);
+                    in.insert(in.end(), {ref.x(), ref.y(), ref.z(), smp.x(), smp.y()});
+                    out.insert(out.end(), {Li[0], Li[1], Li[2], q.wi.x(), q.wi.y(), q.wi.z(), pdf, q.shadowRay.mint, q.shadowRay.maxt,
+                                           q.p.x(), q.p.y(), q.p.z(), ev[0], ev[1], ev[2]});
+                }
+                w.f32("probe.emitter." + std::to_string(e) + ".in", {nProbe, 5}, in.data());
+                w.f32("probe.emitter." + std::to_string(e) + ".out", {nProbe, 15}, out.data());
+            }
         }
         w.save(out);
         cout << "nori_export: wrote " << out << " (" << w.buf.size() << " bytes, " << bvh->m_nodes.size() << " nodes, "

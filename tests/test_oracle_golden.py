@@ -1,0 +1,103 @@
+"""The oracle (oracle/nori_oracle.cpp) against everything the reference pins for this path:
+pcg32 known answers, ray batches answered by the reference's own BVH::rayIntersect, the reference's
+per-plugin eval/pdf/sample answers, the reference's sample sequence, whole renders of the reference
+binary (pixel by pixel, thanks to the block-sequential RNG mode) and the reference's t-test values."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCENE_NAMES, luminance, students_t_accept
+
+
+def test_pcg32_known_answers(meta, golden_scene, make_oracle):
+    demo = meta["pcg32_demo"]                      # ext/pcg32/pcg32-demo.out:8
+    o = make_oracle(golden_scene("cbox_path_mis"))
+    got = o.pcg32_uint(demo["initstate"], demo["initseq"], len(demo["uint"]))
+    assert got.tolist() == demo["uint"]
+    f = o.pcg32(demo["initstate"], demo["initseq"], 4)
+    expect = ((np.array(demo["uint"][:4], np.uint32) >> 9) | 0x3f800000).view(np.float32) - 1.0
+    assert np.array_equal(f, expect)               # pcg32.h:101-110
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_sample_sequence_bit_exact(name, golden_scene, make_oracle):
+    """First samples of block (0,0) in the reference's own order: pixel sample positions and radiance."""
+    sc = golden_scene(name)
+    ref = sc.entries["seq"]
+    mine = make_oracle(sc).block_sequence(len(ref))
+    assert np.array_equal(ref, mine)
+
+
+@pytest.mark.parametrize("name", [n for n in SCENE_NAMES])
+def test_ray_batches_bit_exact(name, golden_scene, make_oracle):
+    sc = golden_scene(name)
+    rb = sc.ray_batch()
+    if rb is None or len(rb["rays"]) == 0:
+        pytest.skip("fixture carries no ray batch")
+    o = make_oracle(sc)
+    for shadow in (0, 1):
+        m = rb["shadow"] == shadow
+        if not m.any():
+            continue
+        hits, p, uv, n, ng = o.trace(rb["rays"][m], shadow, full=True)
+        ref = rb["hits"][m]
+        for f in ("t", "u", "v", "shape", "prim", "nodes_visited", "prims_tested"):
+            assert np.array_equal(hits[f], ref[f]), (name, shadow, f)
+        if not shadow:
+            hit = ref["shape"] != 0xffffffff
+            assert np.array_equal(p[hit], rb["p"][m][hit])
+            assert np.array_equal(n[hit], rb["n"][m][hit])
+            assert np.array_equal(ng[hit], rb["ng"][m][hit])
+            assert np.allclose(uv[hit], rb["uv"][m][hit], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_plugin_probes_bit_exact(name, golden_scene, make_oracle):
+    """BSDF::eval/pdf/sample and Emitter::sample/pdf/eval of every plugin instance in the scene."""
+    sc = golden_scene(name)
+    o = make_oracle(sc)
+    for b in range(sc.pod.n_bsdfs):
+        ref = sc.entries[f"probe.bsdf.{b}.out"]
+        got = o.bsdf_probe(b, sc.entries[f"probe.bsdf.{b}.in"])
+        assert np.array_equal(ref, got, equal_nan=True), (name, "bsdf", b)
+    for e in range(sc.pod.n_emitters):
+        ref = sc.entries[f"probe.emitter.{e}.out"]
+        got = o.emitter_probe(e, sc.entries[f"probe.emitter.{e}.in"])
+        assert np.array_equal(ref, got, equal_nan=True), (name, "emitter", e)
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_render_matches_reference_binary(name, meta, golden_scene, make_oracle):
+    """Oracle render with the reference's sampler mapping vs the image nori_ref wrote: every pixel."""
+    sc = golden_scene(name)
+    spp = meta["scenes"][name]["ref_spp"][0]
+    o = make_oracle(sc)
+    img = o.resolve(o.render(0, spp, mode=1))
+    ref = np.load(os.path.join(GOLDEN, f"{name}.ref{spp}.npy"))
+    rel = np.abs(img - ref) / (np.abs(ref) + 1e-3)
+    # the only tolerated difference is float summation order in the block merge (block.cpp:124-133)
+    assert rel.max() < 1e-4, (name, float(rel.max()))
+
+
+def _ttest_cases(meta_path=os.path.join(GOLDEN, "meta.json")):
+    import json
+    if not os.path.exists(meta_path):
+        return []
+    m = json.load(open(meta_path))["ttests"]
+    return [(k, i) for k in sorted(m) for i in range(len(m[k]["scenes"]))]
+
+
+@pytest.mark.parametrize("test,idx", _ttest_cases())
+def test_reference_ttests(test, idx, meta, make_oracle):
+    """scenes/pa*/tests/*.xml known answers, accepted at the reference's own significance level."""
+    from nori_ray_tracer_b200 import nscene
+    t = meta["ttests"][test]
+    sc = nscene.load_scene(os.path.join(GOLDEN, t["scenes"][idx]))
+    o = make_oracle(sc)
+    n = t["sampleCount"]
+    assert sc.width == 1 and sc.height == 1
+    vals = o.render_samples(0, n, seed=1234)[:, 0, 0, :3]
+    ok, mean, pval = students_t_accept(luminance(vals.astype(np.float64)), t["references"][idx],
+                                       t["significance"], len(t["references"]))
+    assert ok, (test, idx, mean, t["references"][idx], pval)
