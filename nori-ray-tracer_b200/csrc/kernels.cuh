@@ -1,12 +1,11 @@
 // kernels.cuh -- the __global__ kernels of the wavefront path tracer.
 //
-//   k_generate   raygen + path regeneration: free pool slots claim the next sample index, seed their
-//                pcg32 stream, draw the film/aperture samples and write the camera ray
-//                (render.cpp:98-124, perspective.cpp:90-112, thinlens.cpp:126-171)
-//   k_extend     persistent-thread closest-hit traversal over the pool (bvh.cpp:404-462); misses are
-//                finalised, hits are binned by BSDF type into material queues with warp-aggregated
-//                atomics
-//   k_shade<B>   one launch per material queue: hit info, emission (+MIS weight), NEE sample + BSDF
+//   k_extend     persistent-thread closest-hit traversal over the pool (bvh.cpp:404-462) fused with raygen /
+//                path regeneration: free slots claim the next sample index, seed their pcg32 stream, draw
+//                the film/aperture samples and build the camera ray (render.cpp:98-124,
+//                perspective.cpp:90-112, thinlens.cpp:126-171); misses are finalised and regenerated in
+//                place; hits are binned by BSDF type into material queues with warp-aggregated atomics
+//   k_shade      all material queues in one launch (material-coherent warps): hit info, emission (+MIS weight), NEE sample + BSDF
 //                eval/pdf, Russian roulette, BSDF sample (path_mis.cpp:32-97 / path_mats.cpp:23-55)
 //   k_shadow     persistent-thread any-hit traversal of the NEE rays; adds the contribution and
 //                finalises paths that the roulette ended
@@ -27,7 +26,7 @@ struct Pool {
     float4 *hit;              // (t, u, v, leafpos): the 16-byte hit record
     float4 *thr;              // (throughput rgb, pdf_mat)
     float4 *rad;              // (radiance rgb, -)
-    float4 *shO, *shD, *shC;  // shadow ray + its pending contribution
+    float4 *shD, *shC;        // NEE shadow ray (direction, maxt; origin = rayO, mint = Epsilon) + pending contribution
     uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
     uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
     uint32_t *flags;          // PF_*
@@ -38,8 +37,10 @@ struct Pool {
 struct Counters {
     unsigned long long next_sample, total_samples, done;
     unsigned long long rays_ext, rays_sh, nodes_ext, prims_ext, nodes_sh, prims_sh, invalid;
-    uint32_t qcount[NORI_BSDF_COUNT];
-    uint32_t work_extend, work_shadow, pad;
+    // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
+    // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
+    uint32_t qcount[2][NORI_BSDF_COUNT];
+    uint32_t work_extend[2], work_shadow[2];
 };
 
 struct Batch {
@@ -60,82 +61,101 @@ __device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uin
     if (!ok) atomicAdd(&ctr->invalid, 1ull);
 }
 
-// ------------------------------------------------------------------------------ raygen
-__global__ void __launch_bounds__(256) k_generate(DScene sc, Pool pool, Batch bt, Counters *ctr) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[i] = 0;
-        ctr->work_extend = 0; ctr->work_shadow = 0;
-    }
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t limit = (pool.P + 31u) & ~31u;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < limit; slot += stride) {
-        bool isFree = slot < pool.P && pool.sid[slot] == NORI_FREE_SLOT;
-        uint32_t mask = __ballot_sync(0xffffffffu, isFree);
-        if (!mask) continue;
-        unsigned long long base = 0;
-        int leader = __ffs(mask) - 1;
-        if ((threadIdx.x & 31) == leader) base = atomicAdd(&ctr->next_sample, (unsigned long long) __popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (!isFree) continue;
-        unsigned long long id = base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
-        if (id >= ctr->total_samples) continue;                 // nothing left: the slot stays free
-        const uint32_t sid = (uint32_t) id;
-        const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
-        const int W = sc.camera.width;
-        const int py = pix / W, px = pix - py * W;
-        Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
-        P2 a = rng.next2D();                                    // render.cpp:98-99
-        P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
-        P2 ap = rng.next2D();
-        Ray ray = cameraRay(sc.camera, ps, ap);
-        pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
-        pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
-        pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
-        pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pool.rng[slot] = rng.state;
-        pool.sid[slot] = sid;
-        pool.flags[slot] = PF_ALIVE | PF_FIRST;
-    }
+// ------------------------------------------------------------------------------ raygen (device function)
+// One iteration of renderBlock's loop head (render.cpp:98-124): seed the path's pcg32 stream, draw the
+// film and aperture samples, build the camera ray.
+__device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, uint32_t sid, Ray &ray, uint64_t &rngState) {
+    const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
+    const int W = sc.camera.width;
+    const int py = pix / W, px = pix - py * W;
+    Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+    P2 a = rng.next2D();
+    P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
+    P2 ap = rng.next2D();
+    ray = cameraRay(sc.camera, ps, ap);
+    rngState = rng.state;
 }
 
-// ------------------------------------------------------------------------------ extend
+#define NORI_FETCH 256u      // pool slots claimed per warp per atomic (8 rounds of 32)
+
+// ------------------------------------------------------------------------------ extend (+ regeneration)
+// Persistent warps claim NORI_FETCH consecutive pool slots at a time and run three phases on them:
+//   1. regeneration, compacted: the warp gathers its free slots into a shared-memory list, claims that
+//      many sample indices with ONE atomic, and then every lane generates one camera path per step
+//      (render.cpp:98-124) -- full SIMT width although only ~1/3 of the slots are free per iteration;
+//   2. closest-hit traversal of every live slot (bvh.cpp:404-462), 32 slots per step;
+//   3. binning of the hits by BSDF type into the material queues (one atomic per warp and material).
+// A path that escapes the scene is finalised here and its slot handed to the next iteration.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr) {
-    const uint32_t lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    __shared__ uint32_t s_free[4][NORI_FETCH];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
+    uint32_t *freeList = s_free[warp];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
+    }
+    const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     while (true) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_extend, 32u);
+        if (lane == 0) base = atomicAdd(&ctr->work_extend[par], NORI_FETCH);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= pool.P) break;
-        const uint32_t slot = base + lane;
-        const bool active = slot < pool.P && (pool.flags[slot] & PF_ALIVE);
-        int type = -1;
-        if (active) {
-            const float4 ro = pool.rayO[slot], rd = pool.rayD[slot];
-            Hit h;
-            ++nRays;
-            bool found = traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt);
-            if (found) {
-                pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
-                const uint32_t shape = __float_as_uint(__ldg(&sc.prims[3 * h.leafpos + 1]).w);
-                type = sc.shapes[shape].bsdf_type;
-            } else {                                             // path_mis.cpp:28-29 / :84-85: the path ends here
-                const float4 r = pool.rad[slot];
-                finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
-                pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0;
-                ++nDone;
-            }
+        // ---- phase 1: compacted regeneration
+        uint32_t nFree = 0;
+        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+            const uint32_t slot = base + round * 32u + lane;
+            const bool isFree = slot < pool.P && pool.sid[slot] == NORI_FREE_SLOT;
+            const uint32_t m = __ballot_sync(0xffffffffu, isFree);
+            if (isFree) freeList[nFree + __popc(m & ((1u << lane) - 1u))] = slot;
+            nFree += __popc(m);
         }
-        // bin the hits by material with one atomic per (warp, material)
+        if (nFree) {
+            unsigned long long first = 0;
+            if (lane == 0) first = atomicAdd(&ctr->next_sample, (unsigned long long) nFree);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            __syncwarp();
+            for (uint32_t j = lane; j < nFree; j += 32u) {
+                const unsigned long long id = first + j;
+                if (id >= total) break;                          // batch exhausted: the slot stays free
+                const uint32_t slot = freeList[j];
+                Ray ray; uint64_t rs;
+                generatePath(sc, bt, (uint32_t) id, ray, rs);
+                pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+                pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pool.rng[slot] = rs; pool.sid[slot] = (uint32_t) id;
+                pool.flags[slot] = PF_ALIVE | PF_FIRST;
+            }
+            __syncwarp();
+        }
+        // ---- phase 2 + 3: trace and bin
+        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+            const uint32_t slot = base + round * 32u + lane;
+            int type = -1;
+            if (slot < pool.P && (pool.flags[slot] & PF_ALIVE)) {
+                const float4 ro = pool.rayO[slot], rd = pool.rayD[slot];
+                Hit h; ++nRays;
+                if (traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt)) {
+                    pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
+                    type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * h.leafpos + 1]).w)].bsdf_type;
+                } else {                                         // path_mis.cpp:28-29 / :84-85: the path ends here
+                    const float4 r = pool.rad[slot];
+                    finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+                    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+                }
+            }
 #pragma unroll
-        for (int t = 0; t < NORI_BSDF_COUNT; ++t) {
-            const uint32_t m = __ballot_sync(0xffffffffu, type == t);
-            if (!m) continue;
-            uint32_t qb = 0; const int leader = __ffs(m) - 1;
-            if (lane == leader) qb = atomicAdd(&ctr->qcount[t], (uint32_t) __popc(m));
-            qb = __shfl_sync(0xffffffffu, qb, leader);
-            if (type == t) pool.queue[t][qb + __popc(m & ((1u << lane) - 1u))] = slot;
+            for (int t = 0; t < NORI_BSDF_COUNT; ++t) {
+                const uint32_t m = __ballot_sync(0xffffffffu, type == t);
+                if (!m) continue;
+                uint32_t qb = 0; const int leader = __ffs(m) - 1;
+                if ((int) lane == leader) qb = atomicAdd(&ctr->qcount[par][t], (uint32_t) __popc(m));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (type == t) pool.queue[t][qb + __popc(m & ((1u << lane) - 1u))] = slot;
+            }
         }
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
@@ -143,71 +163,90 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 }
 
 // ------------------------------------------------------------------------------ shade
+// One queue entry.  State layout note: the NEE shadow ray starts at the hit point, which is also the
+// origin of the extension ray, so it is stored once (rayO.xyz); the shadow ray keeps only its
+// direction and far end (shD) -- its mint is always Epsilon (arealight.cpp:56 and friends).
 template <int BSDF, bool MIS>
-__global__ void __launch_bounds__(128) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr) {
-    const uint32_t n = ctr->qcount[BSDF];
+__device__ __forceinline__ uint32_t shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot) {
+    const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
+    const uint32_t sid = pool.sid[slot];
+    PathState st;
+    st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
+    st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
+    st.flags = pool.flags[slot];
+    st.rng.state = pool.rng[slot]; st.rng.inc = ((uint64_t) (sid % bt.wh) << 1u) | 1u;
+    Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
+    VertexOut out;
+    pathVertex<BSDF, MIS>(sc, h, st, out);
+    uint32_t done = 0;
+    if (st.flags & PF_SHADOW) {
+        pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
+        pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
+        if (!(st.flags & PF_ALIVE)) pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
+    }
+    if (st.flags & PF_ALIVE) {
+        pool.rayO[slot] = make_float4(out.next.o.x, out.next.o.y, out.next.o.z, out.next.mint);
+        pool.rayD[slot] = make_float4(out.next.d.x, out.next.d.y, out.next.d.z, out.next.maxt);
+        pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
+        pool.rng[slot] = st.rng.state;
+    }
+    if (!MIS && (st.flags & PF_TERMINATE)) {                 // path_mats has no pending shadow ray
+        finalizePath(bt, ctr, sid, st.rad);
+        pool.sid[slot] = NORI_FREE_SLOT; st.flags = 0; done = 1;
+    } else if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z)
+        pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);      // only emitter hits change it
+    pool.flags[slot] = st.flags;
+    return done;
+}
+
+// All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
+// microfacet | disney) and work item i belongs to the queue whose range contains it, so warps are
+// material-coherent except where a boundary falls inside one.
+template <bool MIS>
+__global__ void __launch_bounds__(128) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    uint32_t off[NORI_BSDF_COUNT + 1]; off[0] = 0;
+#pragma unroll
+    for (int t = 0; t < NORI_BSDF_COUNT; ++t) off[t + 1] = off[t] + ctr->qcount[it & 1u][t];
+    const uint32_t n = off[NORI_BSDF_COUNT];
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nDone = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t slot = pool.queue[BSDF][i];
-        const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
-        const uint32_t sid = pool.sid[slot];
-        PathState st;
-        st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
-        st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
-        st.flags = pool.flags[slot];
-        st.rng.state = pool.rng[slot]; st.rng.inc = ((uint64_t) (sid % bt.wh) << 1u) | 1u;
-        Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
-        VertexOut out;
-        pathVertex<BSDF, MIS>(sc, h, st, out);
-        if (st.flags & PF_SHADOW) {
-            pool.shO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, out.shadow.mint);
-            pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
-            pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
-        }
-        if (st.flags & PF_ALIVE) {
-            pool.rayO[slot] = make_float4(out.next.o.x, out.next.o.y, out.next.o.z, out.next.mint);
-            pool.rayD[slot] = make_float4(out.next.d.x, out.next.d.y, out.next.d.z, out.next.maxt);
-            pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
-            pool.rng[slot] = st.rng.state;
-        }
-        if (!MIS && (st.flags & PF_TERMINATE)) {                 // path_mats has no pending shadow ray
-            finalizePath(bt, ctr, sid, st.rad);
-            pool.sid[slot] = NORI_FREE_SLOT; st.flags = 0; ++nDone;
-        } else pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
-        pool.flags[slot] = st.flags;
+        if (i < off[1]) nDone += shadeSlot<NORI_BSDF_DIFFUSE, MIS>(sc, pool, bt, ctr, pool.queue[0][i]);
+        else if (i < off[2]) nDone += shadeSlot<NORI_BSDF_MIRROR, MIS>(sc, pool, bt, ctr, pool.queue[1][i - off[1]]);
+        else if (i < off[3]) nDone += shadeSlot<NORI_BSDF_DIELECTRIC, MIS>(sc, pool, bt, ctr, pool.queue[2][i - off[2]]);
+        else if (i < off[4]) nDone += shadeSlot<NORI_BSDF_MICROFACET, MIS>(sc, pool, bt, ctr, pool.queue[3][i - off[3]]);
+        else nDone += shadeSlot<NORI_BSDF_DISNEY, MIS>(sc, pool, bt, ctr, pool.queue[4][i - off[4]]);
     }
-    if (!MIS) {
-        // all lanes must reach the shuffle
-        warpAdd(&ctr->done, nDone);
-    }
+    if (!MIS) warpAdd(&ctr->done, nDone);
 }
 
 // ------------------------------------------------------------------------------ shadow
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(DScene sc, Pool pool, Batch bt, Counters *ctr) {
-    const uint32_t lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128) k_shadow(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    const uint32_t lane = threadIdx.x & 31, par = it & 1u;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     while (true) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_shadow, 32u);
+        if (lane == 0) base = atomicAdd(&ctr->work_shadow[par], NORI_FETCH);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= pool.P) break;
-        const uint32_t slot = base + lane;
-        if (slot >= pool.P) continue;
-        const uint32_t flags = pool.flags[slot];
-        if (!(flags & PF_SHADOW)) continue;
-        const float4 so = pool.shO[slot], sd = pool.shD[slot];
-        Hit h; ++nRays;
-        const bool occluded = traverse<true, COUNT>(sc, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), so.w, sd.w, h, cnt);
-        float4 r = pool.rad[slot];
-        if (!occluded) { const float4 c = pool.shC[slot]; r.x = __fadd_rn(r.x, c.x); r.y = __fadd_rn(r.y, c.y); r.z = __fadd_rn(r.z, c.z); }
-        if (flags & PF_TERMINATE) {
-            finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
-            pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0; ++nDone;
-        } else {
-            if (!occluded) pool.rad[slot] = r;
-            pool.flags[slot] = flags & ~PF_SHADOW;
+        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+            const uint32_t slot = base + round * 32u + lane;
+            if (slot >= pool.P) continue;
+            const uint32_t flags = pool.flags[slot];
+            if (!(flags & PF_SHADOW)) continue;
+            const float4 so = pool.rayO[slot], sd = pool.shD[slot];      // same origin as the extension ray
+            Hit h; ++nRays;
+            const bool occluded = traverse<true, COUNT>(sc, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w, h, cnt);
+            float4 r = pool.rad[slot];
+            if (!occluded) { const float4 c = pool.shC[slot]; r.x = __fadd_rn(r.x, c.x); r.y = __fadd_rn(r.y, c.y); r.z = __fadd_rn(r.z, c.z); }
+            if (flags & PF_TERMINATE) {
+                finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+                pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0; ++nDone;
+            } else {
+                if (!occluded) pool.rad[slot] = r;
+                pool.flags[slot] = flags & ~PF_SHADOW;
+            }
         }
     }
     warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);

@@ -266,7 +266,7 @@ static int ensurePool(nori_gpu_ctx *ctx) {
     freeAll(ctx->pool_allocs);
     Pool p{}; p.P = (uint32_t) ctx->opt_pool;
     auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
-    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shO, &p.shD, &p.shC};
+    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shD, &p.shC};
     for (auto pp : f4) { *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
@@ -286,13 +286,8 @@ static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
     return 0;
 }
 
-template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid) {
-    const uint32_t m = ctx->bsdf_mask;
-    if (m & (1u << NORI_BSDF_DIFFUSE)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DIFFUSE, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-    if (m & (1u << NORI_BSDF_MIRROR)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_MIRROR, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-    if (m & (1u << NORI_BSDF_DIELECTRIC)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DIELECTRIC, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-    if (m & (1u << NORI_BSDF_MICROFACET)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_MICROFACET, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-    if (m & (1u << NORI_BSDF_DISNEY)) LAUNCH(NORI_K_SHADE, (k_shade<NORI_BSDF_DISNEY, MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid, uint32_t it) {
+    LAUNCH(NORI_K_SHADE, (k_shade<MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
 }
 
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
@@ -319,19 +314,19 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     int occE = 8, occS = 8;
     if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<true>, 128, 0); }
     else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
-    const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridG = sms * 8, gridSh = sms * 16;
+    const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridSh = sms * 16;
     const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
     ctx->last_wave = true;
+    uint32_t it = 0;
     while (true) {
-        for (int it = 0; it < ctx->opt_poll; ++it) {
-            LAUNCH(NORI_K_GENERATE, (k_generate<<<gridG, 256, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-            if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-            else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
+        for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
+            if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
             if (mis) {
-                launchShade<true>(ctx, bt, gridSh);
-                if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-                else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr)));
-            } else launchShade<false>(ctx, bt, gridSh);
+                launchShade<true>(ctx, bt, gridSh, it);
+                if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            } else launchShade<false>(ctx, bt, gridSh, it);
             ctx->stats.iterations += 1;
         }
         CK(cudaGetLastError());

@@ -335,7 +335,7 @@ __device__ __forceinline__ P2 envMapIntersect(const nori_gpu_emitter &e, V3 vec)
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
-__device__ __noinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+__device__ __forceinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
     switch (e.type) {
     case NORI_EMITTER_AREA:                                       // arealight.cpp:39-44
         return dot(l.n, -l.wi) > 0.0f ? arr3(e.radiance) : mk(0.f);
@@ -360,7 +360,7 @@ __device__ __noinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitter 
     }
 }
 
-__device__ __noinline__ float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+__device__ __forceinline__ float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
     switch (e.type) {
     case NORI_EMITTER_AREA: return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.shape]) : 0.0f;   // arealight.cpp:64-76
     case NORI_EMITTER_POINT: return 1.0f;                         // pointlight.cpp:30-33
@@ -384,7 +384,7 @@ __device__ __forceinline__ void envSample1D(const float *pfRow, const float *PfR
     prob = __ldg(&pfRow[i]);
 }
 
-__device__ __noinline__ V3 emitterSample(const DScene &sc, const nori_gpu_emitter &e, ERec &l, P2 s) {
+__device__ __forceinline__ V3 emitterSample(const DScene &sc, const nori_gpu_emitter &e, ERec &l, P2 s) {
     switch (e.type) {
     case NORI_EMITTER_AREA: {                                     // arealight.cpp:46-62
         float spdf;
