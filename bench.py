@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (headline: 1024)")
-    ap.add_argument("--pool", type=int, default=1 << 21)
+    ap.add_argument("--pool", type=int, default=1 << 22)
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one bounded reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

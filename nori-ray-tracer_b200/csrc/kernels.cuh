@@ -202,8 +202,11 @@ __device__ __forceinline__ uint32_t shadeSlot(const DScene &sc, const Pool &pool
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
 // microfacet | disney) and work item i belongs to the queue whose range contains it, so warps are
 // material-coherent except where a boundary falls inside one.
+#ifndef NORI_SHADE_MINBLOCKS
+#define NORI_SHADE_MINBLOCKS 6
+#endif
 template <bool MIS>
-__global__ void __launch_bounds__(128) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+__global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     uint32_t off[NORI_BSDF_COUNT + 1]; off[0] = 0;
 #pragma unroll
     for (int t = 0; t < NORI_BSDF_COUNT; ++t) off[t + 1] = off[t] + ctr->qcount[it & 1u][t];
