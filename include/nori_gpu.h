@@ -245,6 +245,18 @@ int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint
 /* n raw nextUInt() outputs, for the published pcg32-demo known answers. */
 int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out);
 
+/* ---- host-side helpers (no device needed) -------------------------------------------------------
+ * For scenes that do not come from the reference's loader (synthetic benchmark scenes, host-authored
+ * scenes).  nori_gpu_build_bvh restates the reference's SAH builder (bvh.cpp:54-382: 16 centroid bins
+ * along the largest axis, serial sort-and-sweep below 32 primitives, node compaction) with the chunk
+ * order of a single-threaded run, so the tree is one the reference itself could have produced.
+ * nodes_out: capacity 2 * (total primitives); indices_out: total primitives; shape_offset_out: n_shapes+1. */
+int nori_gpu_build_bvh(const nori_gpu_shape *shapes, uint32_t n_shapes, nori_gpu_bvh_node *nodes_out,
+                       uint32_t *indices_out, uint32_t *shape_offset_out, uint32_t *n_nodes_out, int threads);
+/* Mesh::activate (mesh.cpp:30-38): per-triangle area CDF (n_triangles+1 floats) and 1/total area. */
+int nori_gpu_mesh_area_cdf(const float *V, const uint32_t *F, uint32_t n_triangles, float *cdf_out,
+                           float *normalization_out);
+
 /* sizeof() of every ABI struct as compiled into the library (binding self-check); returns the count. */
 int nori_gpu_abi_sizes(uint32_t *out, int n);
 

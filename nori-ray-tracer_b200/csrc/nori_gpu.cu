@@ -34,6 +34,7 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
 
     nori_gpu_stats stats{};
     nori_gpu_kernel_stats kstats[NORI_K_COUNT]{};
@@ -134,6 +135,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "stats") ctx->opt_stats = value != 0;
     else if (k == "megakernel") ctx->opt_megakernel = value != 0;
     else if (k == "kernel_timing") ctx->opt_kernel_timing = value != 0;
+    else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
         // bench helper: overwrite a buffer larger than L2 (value = MiB)
@@ -311,21 +313,38 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    // plain per-lane loops for tiny scenes, the warp state machine once trees are deep (see kernels.cuh)
+    const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
     int occE = 8, occS = 8;
-    if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<true>, 128, 0); }
-    else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
+    if (sm) {
+        if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow_sm<true>, 128, 0); }
+        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow_sm<false>, 128, 0); }
+    } else {
+        if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<true>, 128, 0); }
+        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
+    }
     const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridSh = sms * 16;
     const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
     ctx->last_wave = true;
     uint32_t it = 0;
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
-            if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            if (sm) {
+                if (count) LAUNCH(NORI_K_EXTEND, (k_extend_sm<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                else LAUNCH(NORI_K_EXTEND, (k_extend_sm<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            } else {
+                if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            }
             if (mis) {
                 launchShade<true>(ctx, bt, gridSh, it);
-                if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                if (sm) {
+                    if (count) LAUNCH(NORI_K_SHADOW, (k_shadow_sm<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                    else LAUNCH(NORI_K_SHADOW, (k_shadow_sm<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                } else {
+                    if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                    else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+                }
             } else launchShade<false>(ctx, bt, gridSh, it);
             ctx->stats.iterations += 1;
         }
