@@ -246,8 +246,8 @@ def main():
         kc = g.kernel_stats()
         g.set_option("stats", 0)
         kernel_ms = {k: v["ms"] for k, v in ks.items()}
-        dom = max(("extend", "shadow", "shade"), key=lambda k: kernel_ms[k])
-        trace_dom = dom if dom in ("extend", "shadow") else "extend"
+        # dominant trace kernel: k_extend (closest-hit + raygen) or k_shade (shading + the any-hit NEE rays)
+        trace_dom = max(("extend", "shade"), key=lambda k: kernel_ms[k])
         c = kc[trace_dom]
         b_ray = 32.0 * c["nodes"] / max(c["rays"], 1) + 48.0 * c["prims"] / max(c["rays"], 1) + 48.0
         k = ks[trace_dom]

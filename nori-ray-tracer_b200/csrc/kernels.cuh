@@ -6,9 +6,8 @@
 //                perspective.cpp:90-112, thinlens.cpp:126-171); misses are finalised and regenerated in
 //                place; hits are binned by BSDF type into material queues with warp-aggregated atomics
 //   k_shade      all material queues in one launch (material-coherent warps): hit info, emission (+MIS weight), NEE sample + BSDF
-//                eval/pdf, Russian roulette, BSDF sample (path_mis.cpp:32-97 / path_mats.cpp:23-55)
-//   k_shadow     persistent-thread any-hit traversal of the NEE rays; adds the contribution and
-//                finalises paths that the roulette ended
+//                eval/pdf, the any-hit query of the NEE shadow ray (bvh.cpp:441-442), Russian roulette,
+//                BSDF sample (path_mis.cpp:32-97 / path_mats.cpp:23-55); finalises paths the roulette ended
 //   k_film       reconstruction-filter accumulation of a batch of finished samples into the film:
 //                one CTA per 32x32 film tile, samples of the tile + halo staged in shared memory,
 //                each film pixel owned by exactly one thread (gather, no atomics), one coalesced
@@ -26,7 +25,6 @@ struct Pool {
     float4 *hit;              // (t, u, v, leafpos): the 16-byte hit record
     float4 *thr;              // (throughput rgb, pdf_mat)
     float4 *rad;              // (radiance rgb, -)
-    float4 *shD, *shC;        // NEE shadow ray (direction, maxt; origin = rayO, mint = Epsilon) + pending contribution
     uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
     uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
     uint32_t *flags;          // PF_*
@@ -40,7 +38,7 @@ struct Counters {
     // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
     // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
     uint32_t qcount[2][NORI_BSDF_COUNT];
-    uint32_t work_extend[2], work_shadow[2];
+    uint32_t work_extend[2], pad[2];
 };
 
 struct Batch {
@@ -93,7 +91,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[par ^ 1u][i] = 0;
-        ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
+        ctr->work_extend[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
@@ -163,11 +161,14 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 }
 
 // ------------------------------------------------------------------------------ shade
-// One queue entry.  State layout note: the NEE shadow ray starts at the hit point, which is also the
-// origin of the extension ray, so it is stored once (rayO.xyz); the shadow ray keeps only its
-// direction and far end (shD) -- its mint is always Epsilon (arealight.cpp:56 and friends).
-template <int BSDF, bool MIS>
-__device__ __forceinline__ uint32_t shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot) {
+// One queue entry: the whole loop body of PathMisIntegrator::Li for one path vertex, INCLUDING the
+// any-hit query of the NEE shadow ray (path_mis.cpp:48).  Tracing the shadow ray here, in the thread
+// that just built it, keeps the ray, its pending contribution and the roulette decision in registers:
+// no shadow-ray record is written to the pool and no separate pass re-reads the path state
+// (measured: shade + shadow went from 266 ms to the fused number in DESIGN.md on the Cornell box).
+template <int BSDF, bool MIS, bool COUNT>
+__device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
+                                          uint32_t &nDone, uint32_t &nShadow, TraceCounters &cnt) {
     const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
     const uint32_t sid = pool.sid[slot];
     PathState st;
@@ -178,25 +179,22 @@ __device__ __forceinline__ uint32_t shadeSlot(const DScene &sc, const Pool &pool
     Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
     VertexOut out;
     pathVertex<BSDF, MIS>(sc, h, st, out);
-    uint32_t done = 0;
-    if (st.flags & PF_SHADOW) {
-        pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
-        pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
-        if (!(st.flags & PF_ALIVE)) pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
+    if (MIS) {                                                  // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
+        Hit sh; ++nShadow;
+        if (!traverse<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
+            st.rad = st.rad + out.contrib;
     }
     if (st.flags & PF_ALIVE) {
         pool.rayO[slot] = make_float4(out.next.o.x, out.next.o.y, out.next.o.z, out.next.mint);
         pool.rayD[slot] = make_float4(out.next.d.x, out.next.d.y, out.next.d.z, out.next.maxt);
         pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
         pool.rng[slot] = st.rng.state;
-    }
-    if (!MIS && (st.flags & PF_TERMINATE)) {                 // path_mats has no pending shadow ray
+        if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
+        pool.flags[slot] = st.flags & (PF_ALIVE | PF_DISCRETE);
+    } else {                                                    // Russian roulette ended the path
         finalizePath(bt, ctr, sid, st.rad);
-        pool.sid[slot] = NORI_FREE_SLOT; st.flags = 0; done = 1;
-    } else if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z)
-        pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);      // only emitter hits change it
-    pool.flags[slot] = st.flags;
-    return done;
+        pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+    }
 }
 
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
@@ -205,54 +203,23 @@ __device__ __forceinline__ uint32_t shadeSlot(const DScene &sc, const Pool &pool
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
-template <bool MIS>
+template <bool MIS, bool COUNT>
 __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     uint32_t off[NORI_BSDF_COUNT + 1]; off[0] = 0;
 #pragma unroll
     for (int t = 0; t < NORI_BSDF_COUNT; ++t) off[t + 1] = off[t] + ctr->qcount[it & 1u][t];
     const uint32_t n = off[NORI_BSDF_COUNT];
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t nDone = 0;
+    uint32_t nDone = 0, nShadow = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (i < off[1]) nDone += shadeSlot<NORI_BSDF_DIFFUSE, MIS>(sc, pool, bt, ctr, pool.queue[0][i]);
-        else if (i < off[2]) nDone += shadeSlot<NORI_BSDF_MIRROR, MIS>(sc, pool, bt, ctr, pool.queue[1][i - off[1]]);
-        else if (i < off[3]) nDone += shadeSlot<NORI_BSDF_DIELECTRIC, MIS>(sc, pool, bt, ctr, pool.queue[2][i - off[2]]);
-        else if (i < off[4]) nDone += shadeSlot<NORI_BSDF_MICROFACET, MIS>(sc, pool, bt, ctr, pool.queue[3][i - off[3]]);
-        else nDone += shadeSlot<NORI_BSDF_DISNEY, MIS>(sc, pool, bt, ctr, pool.queue[4][i - off[4]]);
+        if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MIS, COUNT>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, cnt);
+        else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MIS, COUNT>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, cnt);
+        else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MIS, COUNT>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, cnt);
+        else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MIS, COUNT>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, cnt);
+        else shadeSlot<NORI_BSDF_DISNEY, MIS, COUNT>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, cnt);
     }
-    if (!MIS) warpAdd(&ctr->done, nDone);
-}
-
-// ------------------------------------------------------------------------------ shadow
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
-    const uint32_t lane = threadIdx.x & 31, par = it & 1u;
-    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_shadow[par], NORI_FETCH);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= pool.P) break;
-        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
-            const uint32_t slot = base + round * 32u + lane;
-            if (slot >= pool.P) continue;
-            const uint32_t flags = pool.flags[slot];
-            if (!(flags & PF_SHADOW)) continue;
-            const float4 so = pool.rayO[slot], sd = pool.shD[slot];      // same origin as the extension ray
-            Hit h; ++nRays;
-            const bool occluded = traverse<true, COUNT>(sc, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w, h, cnt);
-            float4 r = pool.rad[slot];
-            if (!occluded) { const float4 c = pool.shC[slot]; r.x = __fadd_rn(r.x, c.x); r.y = __fadd_rn(r.y, c.y); r.z = __fadd_rn(r.z, c.z); }
-            if (flags & PF_TERMINATE) {
-                finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
-                pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0; ++nDone;
-            } else {
-                if (!occluded) pool.rad[slot] = r;
-                pool.flags[slot] = flags & ~PF_SHADOW;
-            }
-        }
-    }
-    warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
+    warpAdd(&ctr->done, nDone);
+    if (MIS) warpAdd(&ctr->rays_sh, nShadow);
     if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
 
@@ -337,7 +304,7 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[par ^ 1u][i] = 0;
-        ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
+        ctr->work_extend[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
@@ -445,74 +412,6 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
-    const uint32_t lane = threadIdx.x & 31, par = it & 1u;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    uint32_t stack[64];
-    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0;
-    uint32_t flags = 0;
-    uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
-    bool moreChunks = true;
-    while (true) {
-        uint32_t idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
-        bool finished = false;
-        if (idle && (moreChunks || chunkNext < NORI_FETCH) && (__popc(idle) >= NORI_REFILL_MIN || idle == 0xffffffffu)) {
-            while (idle) {
-                if (chunkNext >= NORI_FETCH) {
-                    if (!moreChunks) break;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&ctr->work_shadow[par], NORI_FETCH);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= pool.P) { moreChunks = false; break; }
-                    chunkBase = base; chunkNext = 0;
-                }
-                const uint32_t idx = chunkNext + __popc(idle & ltMask);
-                const bool take = L.st == ST_IDLE && idx < NORI_FETCH && !finished;
-                chunkNext = min(chunkNext + (uint32_t) __popc(idle), NORI_FETCH);
-                if (take) {
-                    const uint32_t s = chunkBase + idx;
-                    if (s < pool.P) {
-                        const uint32_t f = pool.flags[s];
-                        if (f & PF_SHADOW) {
-                            const float4 so = pool.rayO[s], sd = pool.shD[s];
-                            L.slot = s; flags = f; ++nRays;
-                            if (travInit(sc, L.r, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w)) L.st = ST_NODE;
-                            else { finished = true; L.st = ST_NODE; }     // unoccluded without a single node visit
-                        }
-                    }
-                }
-                idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
-            }
-        }
-        const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE && !finished);
-        const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
-        if (!(mNode | mLeaf) && !__any_sync(0xffffffffu, finished)) { if (!moreChunks && chunkNext >= NORI_FETCH) break; else continue; }
-        if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
-            if (L.st == ST_LEAF) finished = smPrim<true, COUNT>(sc, L, stack, cnt);
-        } else if (mNode) {
-#pragma unroll 1
-            for (int k = 0; k < NORI_NODE_BURST; ++k)
-                if (L.st == ST_NODE && !finished) finished = smNode<COUNT>(sc, L, stack, cnt);
-        }
-        if (finished) {
-            L.st = ST_IDLE;
-            float4 ra = pool.rad[L.slot];
-            if (!L.r.found) { const float4 c = pool.shC[L.slot]; ra.x = __fadd_rn(ra.x, c.x); ra.y = __fadd_rn(ra.y, c.y); ra.z = __fadd_rn(ra.z, c.z); }
-            if (flags & PF_TERMINATE) {
-                finalizePath(bt, ctr, pool.sid[L.slot], mk(ra.x, ra.y, ra.z));
-                pool.sid[L.slot] = NORI_FREE_SLOT; pool.flags[L.slot] = 0; ++nDone;
-            } else {
-                if (!L.r.found) pool.rad[L.slot] = ra;
-                pool.flags[L.slot] = flags & ~PF_SHADOW;
-            }
-        }
-    }
-    warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
-    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
 
 // ------------------------------------------------------------------------------ short integrators

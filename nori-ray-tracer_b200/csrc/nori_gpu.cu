@@ -268,7 +268,7 @@ static int ensurePool(nori_gpu_ctx *ctx) {
     freeAll(ctx->pool_allocs);
     Pool p{}; p.P = (uint32_t) ctx->opt_pool;
     auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
-    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shD, &p.shC};
+    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad};
     for (auto pp : f4) { *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
@@ -288,8 +288,9 @@ static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
     return 0;
 }
 
-template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid, uint32_t it) {
-    LAUNCH(NORI_K_SHADE, (k_shade<MIS><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid, uint32_t it, bool count) {
+    if (count) LAUNCH(NORI_K_SHADE, (k_shade<MIS, true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+    else LAUNCH(NORI_K_SHADE, (k_shade<MIS, false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
 }
 
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
@@ -315,15 +316,10 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     // plain per-lane loops for tiny scenes, the warp state machine once trees are deep (see kernels.cuh)
     const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
-    int occE = 8, occS = 8;
-    if (sm) {
-        if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow_sm<true>, 128, 0); }
-        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow_sm<false>, 128, 0); }
-    } else {
-        if (count) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<true>, 128, 0); }
-        else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_shadow<false>, 128, 0); }
-    }
-    const int gridE = sms * std::max(1, occE), gridS = sms * std::max(1, occS), gridSh = sms * 16;
+    int occE = 8;
+    if (sm) { if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<false>, 128, 0); }
+    else { if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); }
+    const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
     const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
     ctx->last_wave = true;
     uint32_t it = 0;
@@ -336,16 +332,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
                 if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
                 else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
             }
-            if (mis) {
-                launchShade<true>(ctx, bt, gridSh, it);
-                if (sm) {
-                    if (count) LAUNCH(NORI_K_SHADOW, (k_shadow_sm<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                    else LAUNCH(NORI_K_SHADOW, (k_shadow_sm<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                } else {
-                    if (count) LAUNCH(NORI_K_SHADOW, (k_shadow<true><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                    else LAUNCH(NORI_K_SHADOW, (k_shadow<false><<<gridS, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                }
-            } else launchShade<false>(ctx, bt, gridSh, it);
+            if (mis) launchShade<true>(ctx, bt, gridSh, it, count); else launchShade<false>(ctx, bt, gridSh, it, count);
             ctx->stats.iterations += 1;
         }
         CK(cudaGetLastError());
@@ -365,7 +352,7 @@ static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
     ctx->stats.invalid_samples += c.invalid;
     if (ctx->last_wave) {
-        nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[NORI_K_SHADOW];
+        nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[NORI_K_SHADE];   // shadow rays are traced inside k_shade
         e.rays += c.rays_ext; e.nodes_visited += c.nodes_ext; e.prims_tested += c.prims_ext;
         s.rays += c.rays_sh; s.nodes_visited += c.nodes_sh; s.prims_tested += c.prims_sh;
     } else {
