@@ -229,6 +229,12 @@ int nori_gpu_film_dims(const nori_gpu_ctx *ctx, int32_t *rows, int32_t *cols, in
 /* ImageBlock::toBitmap (block.cpp:76-82): H*W*3 floats = rgb / w (0 where w == 0). */
 int nori_gpu_resolve(nori_gpu_ctx *ctx, float *rgb);
 
+/* The reference's second output, <scene>_variance.exr (render.cpp:190-192,225,238-247,263-278): per
+ * pixel mean_k(m_k^2) - (mean_k m_k)^2 over the running means m_k after each spp pass.
+ * Enable with nori_gpu_set_option(ctx, "variance", 1) after upload_scene and before rendering;
+ * clear_film resets it.  rgb: H*W*3 floats. */
+int nori_gpu_download_variance(nori_gpu_ctx *ctx, float *rgb);
+
 /* BVH::rayIntersect on a caller-supplied ray batch (bvh.cpp:404-462), shadow != 0 => any-hit.
  * For shadow rays only `t` (0 = occluded, +inf = free) and the counters are meaningful. */
 int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out);

@@ -442,9 +442,15 @@ struct FilmParams {
     int W, H, border, halo;   // halo == border: source pixels that can reach a film pixel
     float radius, lookupFactor;
     float table[NORI_FILTER_RESOLUTION + 1];
+    float4 *vsum, *vsum2;     // per-pixel sums of the running mean and of its square (render.cpp:238-247), or NULL
 };
 
 // smem per layer: (32+2*halo)^2 x { float4 value, float2 pos }
+// VARIANCE: also accumulate, after every spp layer (= one pass of the reference's spp-major loop), the
+// running mean m_k = rgb/w of the pixel and its square -- the reference's `*_variance.exr` statistic
+// (render.cpp:225,238-247,263-278).  The accumulation then starts from the film's current
+// value so that m_k covers every pass rendered so far, across batches and render() calls.
+template <bool VARIANCE>
 __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t nLayers) {
     extern __shared__ float4 s_mem[];
     const int T = 32, halo = fp.halo, S = T + 2 * halo, nS = S * S;
@@ -458,6 +464,9 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
     const int sx0 = blockIdx.x * T - b - halo, sy0 = blockIdx.y * T - b - halo;       // image coords of the staged region
     const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 vs = make_float3(0.f, 0.f, 0.f), vs2 = make_float3(0.f, 0.f, 0.f);
+    const bool owner = fx < fcols && fy < frows;
+    if (VARIANCE && owner) acc = fp.film[(size_t) fy * fcols + fx];
     for (uint32_t k = 0; k < nLayers; ++k) {
         __syncthreads();
         for (int i = tid; i < nS; i += T * T) {
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
             s_val[i] = v; s_pos[i] = p;
         }
         __syncthreads();
-        if (fx < fcols && fy < frows) {
+        if (owner) {
             // staged-region coordinates of the source pixels that can reach (fx, fy)
             const int cx = threadIdx.x + halo, cy = threadIdx.y + halo;   // own source pixel (image x = fx - b)
             for (int dy = -halo; dy <= halo; ++dy) {
@@ -506,14 +515,36 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
                     acc.w = __fadd_rn(acc.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
                 }
             }
+            if (VARIANCE) {                                      // Color4f::divideByFilterWeight (color.h:84-89)
+                const float mx = acc.w != 0.f ? acc.x / acc.w : 0.f, my = acc.w != 0.f ? acc.y / acc.w : 0.f, mz = acc.w != 0.f ? acc.z / acc.w : 0.f;
+                vs.x += mx; vs.y += my; vs.z += mz;
+                vs2.x += mx * mx; vs2.y += my * my; vs2.z += mz * mz;
+            }
         }
     }
-    if (fx < fcols && fy < frows) {
+    if (owner) {
         float4 *dst = &fp.film[(size_t) fy * fcols + fx];
-        float4 f = *dst;
-        f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
-        *dst = f;
+        if (VARIANCE) {
+            *dst = acc;
+            float4 a = fp.vsum[(size_t) fy * fcols + fx], b = fp.vsum2[(size_t) fy * fcols + fx];
+            a.x += vs.x; a.y += vs.y; a.z += vs.z; b.x += vs2.x; b.y += vs2.y; b.z += vs2.z;
+            fp.vsum[(size_t) fy * fcols + fx] = a; fp.vsum2[(size_t) fy * fcols + fx] = b;
+        } else {
+            float4 f = *dst;
+            f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+            *dst = f;
+        }
     }
+}
+
+// var = sum2/N - (sum/N)^2 per channel (render.cpp:268-275)
+__global__ void k_variance(const float4 *vsum, const float4 *vsum2, float *rgb, int W, int H, int b, float n) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 s = vsum[(size_t) (y + b) * (W + 2 * b) + (x + b)], s2 = vsum2[(size_t) (y + b) * (W + 2 * b) + (x + b)];
+    float *o = &rgb[((size_t) y * W + x) * 3];
+    const float mx = s.x / n, my = s.y / n, mz = s.z / n;
+    o[0] = s2.x / n - mx * mx; o[1] = s2.y / n - my * my; o[2] = s2.z / n - mz * mz;
 }
 
 __global__ void k_resolve(const float4 *film, float *rgb, int W, int H, int b) {

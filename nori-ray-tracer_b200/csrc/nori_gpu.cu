@@ -26,6 +26,8 @@ struct nori_gpu_ctx {
     uint32_t n_bsdfs = 0;
 
     float4 *film = nullptr;
+    float4 *vsum = nullptr, *vsum2 = nullptr; uint32_t var_passes = 0;   // variance statistic (option "variance")
+    int64_t opt_variance = 0;
     Pool pool{};
     std::vector<void *> pool_allocs;
     float4 *results = nullptr; size_t results_cap = 0;      // in float4 elements
@@ -108,7 +110,7 @@ void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     freeAll(ctx->scene_allocs); freeAll(ctx->pool_allocs);
-    cudaFree(ctx->film); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
+    cudaFree(ctx->film); cudaFree(ctx->vsum); cudaFree(ctx->vsum2); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
     cudaFreeHost(ctx->h_ctr);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -135,6 +137,17 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "stats") ctx->opt_stats = value != 0;
     else if (k == "megakernel") ctx->opt_megakernel = value != 0;
     else if (k == "kernel_timing") ctx->opt_kernel_timing = value != 0;
+    else if (k == "variance") {
+        REQUIRE(ctx->has_scene, "set_option(variance): upload a scene first");
+        CK(cudaSetDevice(ctx->device));
+        ctx->opt_variance = value != 0;
+        size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+        if (ctx->opt_variance && !ctx->vsum) {
+            CK(cudaMalloc((void **) &ctx->vsum, nf * sizeof(float4))); CK(cudaMalloc((void **) &ctx->vsum2, nf * sizeof(float4)));
+            CK(cudaMemsetAsync(ctx->vsum, 0, nf * sizeof(float4), ctx->stream)); CK(cudaMemsetAsync(ctx->vsum2, 0, nf * sizeof(float4), ctx->stream));
+            ctx->var_passes = 0;
+        }
+    }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
@@ -254,6 +267,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     ctx->W = s->camera.width; ctx->H = s->camera.height;
     ctx->border = (int) std::ceil(s->filter.radius - 0.5f);              // block.cpp:57
     cudaFree(ctx->film); ctx->film = nullptr;
+    cudaFree(ctx->vsum); cudaFree(ctx->vsum2); ctx->vsum = ctx->vsum2 = nullptr; ctx->opt_variance = 0; ctx->var_passes = 0;
     size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
     CK(cudaMalloc((void **) &ctx->film, nf * sizeof(float4)));
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
@@ -394,9 +408,14 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
         } else {
             const int S = 32 + 2 * fp.halo;
             size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
-            CK(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            CK(cudaFuncSetAttribute(k_film<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             dim3 grid((ctx->W + 2 * ctx->border + 31) / 32, (ctx->H + 2 * ctx->border + 31) / 32);
-            LAUNCH(NORI_K_FILM, (k_film<<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+            if (ctx->opt_variance) {
+                fp.vsum = ctx->vsum; fp.vsum2 = ctx->vsum2;
+                CK(cudaFuncSetAttribute(k_film<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                LAUNCH(NORI_K_FILM, (k_film<true><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+                ctx->var_passes += n;
+            } else LAUNCH(NORI_K_FILM, (k_film<false><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
             CK(cudaGetLastError());
         }
         if (foldStats(ctx, (unsigned long long) n * wh)) return 1;
@@ -425,6 +444,23 @@ int nori_gpu_clear_film(nori_gpu_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
+    if (ctx->vsum) { CK(cudaMemsetAsync(ctx->vsum, 0, nf * sizeof(float4), ctx->stream)); CK(cudaMemsetAsync(ctx->vsum2, 0, nf * sizeof(float4), ctx->stream)); }
+    ctx->var_passes = 0;
+    return 0;
+}
+
+int nori_gpu_download_variance(nori_gpu_ctx *ctx, float *rgb) {
+    REQUIRE(ctx && ctx->has_scene && rgb, "download_variance: no scene / null buffer");
+    REQUIRE(ctx->vsum && ctx->var_passes > 0, "download_variance: enable option \"variance\" before rendering");
+    CK(cudaSetDevice(ctx->device));
+    float *d = nullptr; size_t n = (size_t) ctx->W * ctx->H * 3;
+    CK(cudaMalloc((void **) &d, n * sizeof(float)));
+    dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    k_variance<<<grid, blk, 0, ctx->stream>>>(ctx->vsum, ctx->vsum2, d, ctx->W, ctx->H, ctx->border, (float) ctx->var_passes);
+    cudaError_t e = cudaMemcpyAsync(rgb, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = std::string("download_variance: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
 

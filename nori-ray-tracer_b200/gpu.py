@@ -41,6 +41,7 @@ def load_library():
         "nori_gpu_film_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "nori_gpu_film_dims": (C.c_int, [vp] + [C.POINTER(C.c_int32)] * 3),
         "nori_gpu_resolve": (C.c_int, [vp, vp]),
+        "nori_gpu_download_variance": (C.c_int, [vp, vp]),
         "nori_gpu_trace": (C.c_int, [vp, vp, u64, C.c_int, vp]),
         "nori_gpu_probe_bsdf": (C.c_int, [vp, u32, u64, vp, vp]),
         "nori_gpu_probe_emitter": (C.c_int, [vp, u32, u64, vp, vp]),
@@ -142,6 +143,12 @@ class NoriGpu:
     def resolve(self):
         rgb = np.empty((self.scene.height, self.scene.width, 3), np.float32)
         self._check(self.lib.nori_gpu_resolve(self.ctx, rgb.ctypes.data))
+        return rgb
+
+    def variance(self):
+        """<scene>_variance.exr of the reference (needs set_option('variance', 1) before rendering)."""
+        rgb = np.empty((self.scene.height, self.scene.width, 3), np.float32)
+        self._check(self.lib.nori_gpu_download_variance(self.ctx, rgb.ctypes.data))
         return rgb
 
     # ---- test hooks -------------------------------------------------------------------------

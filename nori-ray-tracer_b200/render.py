@@ -50,6 +50,7 @@ class RenderThread:
         self._thread = None
         self.result = None
         self.error = None
+        self.variance_image = None
 
     # ---- the reference's polling surface ----------------------------------------------------
     def isBusy(self):
@@ -68,7 +69,7 @@ class RenderThread:
             self._status = 0
 
     # ---- synchronous core -------------------------------------------------------------------
-    def render(self, scene, spp=None, spp_chunk=None, seed=0, distributed=False, progress=None):
+    def render(self, scene, spp=None, spp_chunk=None, seed=0, distributed=False, progress=None, variance=False):
         """Render `scene` (a nscene.SceneData); returns (rgb bitmap, film) on rank 0, (None, film) elsewhere."""
         g = self.gpu
         spp = scene.sample_count if spp is None else spp
@@ -78,6 +79,8 @@ class RenderThread:
             rank, world = dist.get_rank(), dist.get_world_size()
         begin, count = shard_spp(spp, rank, world)
         g.upload_scene(scene)
+        if variance:                                   # the reference's <scene>_variance.exr (render.cpp:263-278)
+            g.set_option("variance", 1)
         g.clear_film()
         chunk = count if not spp_chunk else spp_chunk
         done = 0
@@ -98,6 +101,7 @@ class RenderThread:
             torch.cuda.synchronize(g.device)
         film = g.download_film()
         rgb = g.resolve() if rank == 0 else None
+        self.variance_image = g.variance() if variance else None
         return rgb, film
 
     # ---- the reference's asynchronous entry point ---------------------------------------------
@@ -112,6 +116,8 @@ class RenderThread:
                 self.result = (rgb, film, time.time() - t0)
                 if output and rgb is not None:
                     imageio.write_exr(output, rgb)
+                    if self.variance_image is not None:
+                        imageio.write_exr(output[:-4] + "_variance.exr", self.variance_image)
             except Exception as e:                       # surfaced through .error, like NoriException
                 self.error = e
             finally:

@@ -1050,8 +1050,8 @@ void nori_oracle_render_samples(void *h, uint32_t spp_begin, uint32_t spp_count,
  * mode 0: per-path streams (as above); mode 1: the reference's mapping -- one pcg32 per 32x32 block,
  * seeded (offset.x, offset.y) when spp_begin == 0 and carried across passes through `block_rng`
  * (2 x uint64 per block, caller-owned, may be NULL if a single call renders everything). */
-void nori_oracle_render(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
-                        float *film, uint64_t *block_rng) {
+void nori_oracle_render_var(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
+                            float *film, uint64_t *block_rng, float *vsum, float *vsum2) {
     Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height, b = sc->border;
     const int fcols = W + 2 * b, BS = NORI_BLOCK_SIZE;
     const int nbx = (W + BS - 1) / BS, nby = (H + BS - 1) / BS;
@@ -1084,6 +1084,15 @@ void nori_oracle_render(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_
                 for (int c = 0; c < 4; ++c)
                     film[((size_t) (y + oy) * fcols + (x + ox)) * 4 + c] += blocks[bi][((size_t) y * bc + x) * 4 + c];
         }
+        /* per-pass running mean and its square (render.cpp:238-247); vsum / vsum2 are H*W*3, caller-zeroed */
+        if (vsum && vsum2)
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+                const float *c = &film[((size_t) (y + b) * fcols + (x + b)) * 4];
+                for (int ch = 0; ch < 3; ++ch) {
+                    float m = c[3] != 0 ? c[ch] / c[3] : 0.f;
+                    vsum[((size_t) y * W + x) * 3 + ch] += m; vsum2[((size_t) y * W + x) * 3 + ch] += m * m;
+                }
+            }
     }
     if (block_rng) for (size_t i = 0; i < rngs.size(); ++i) { block_rng[2 * i] = rngs[i].state; block_rng[2 * i + 1] = rngs[i].inc; }
     __atomic_fetch_add(&sc->samples, (uint64_t) spp_count * W * H, __ATOMIC_RELAXED);
@@ -1127,6 +1136,11 @@ void nori_oracle_emitter_probe(void *h, uint32_t emitter, uint64_t n, const floa
         o[7] = e.shadowRay.mint; o[8] = e.shadowRay.maxt; o[9] = e.p.x; o[10] = e.p.y; o[11] = e.p.z;
         o[12] = ev.x; o[13] = ev.y; o[14] = ev.z;
     }
+}
+
+void nori_oracle_render(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
+                        float *film, uint64_t *block_rng) {
+    nori_oracle_render_var(h, spp_begin, spp_count, seed, mode, film, block_rng, nullptr, nullptr);
 }
 
 /* ImageBlock::toBitmap, block.cpp:76-82 + color.h:84-89 */

@@ -29,6 +29,7 @@ def _load(abi):
     lib.nori_oracle_pcg32_uint.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.nori_oracle_render_samples.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     lib.nori_oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.nori_oracle_render_var.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nori_oracle_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nori_oracle_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
     lib.nori_oracle_reset_stats.argtypes = [C.c_void_p]
@@ -86,6 +87,14 @@ class Oracle:
             film = np.zeros(self.scene.film_shape, np.float32)
         self.lib.nori_oracle_render(self.h, spp_begin, spp_count, seed, mode, film.ctypes.data, None)
         return film
+
+    def render_with_variance(self, spp, seed=0, mode=0):
+        """(film, variance image): the reference's two outputs for a render of `spp` passes from scratch."""
+        film = np.zeros(self.scene.film_shape, np.float32)
+        vs = np.zeros((self.scene.height, self.scene.width, 3), np.float32); vs2 = np.zeros_like(vs)
+        self.lib.nori_oracle_render_var(self.h, 0, spp, seed, mode, film.ctypes.data, None, vs.ctypes.data, vs2.ctypes.data)
+        n = np.float32(spp)
+        return film, vs2 / n - (vs / n) ** 2
 
     def resolve(self, film):
         rgb = np.zeros((self.scene.height, self.scene.width, 3), np.float32)

@@ -36,9 +36,9 @@ NORI = os.path.join(ROOT, "oracle", "_ref", "nori_ref")
 
 # name, source xml (under scenes/), overrides, export options, reference renders (spp list)
 FIXTURES = [
-    dict(name="cbox_path_mis", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=12000, seq=2000, ref_spp=[4, 128]),
+    dict(name="cbox_path_mis", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=12000, seq=2000, ref_spp=[4, 128], variance=True),
     dict(name="cbox_path_mats", src="pa4/cbox/cbox_path_mats.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 256]),
-    dict(name="sphere_mesh_normals", src="pa1/sphere-mesh.xml", res=(128, 128), rays=8000, seq=1000, ref_spp=[4]),
+    dict(name="sphere_mesh_normals", src="pa1/sphere-mesh.xml", res=(128, 128), rays=8000, seq=1000, ref_spp=[4], variance=True),
     dict(name="sphere_analytic_normals", src="pa1/sphere-analytic.xml", res=(128, 128), rays=4000, seq=1000, ref_spp=[4]),
     dict(name="sphere_ems", src="pa3/sphere/sphere_ems.xml", res=(128, 128), rays=0, seq=1000, ref_spp=[4]),
     dict(name="sphere2_mats", src="pa3/sphere/sphere2_mats.xml", res=(128, 128), rays=0, seq=1000, ref_spp=[4, 256]),
@@ -153,6 +153,9 @@ def make_scene_fixture(fx, tmp, meta):
         entry.setdefault("ref_time", {})[str(spp)] = m.group(0) if m else None
         img = cv2.imread(os.path.join(work, f"{name}.exr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
         np.save(os.path.join(HERE, f"{name}.ref{spp}.npy"), np.ascontiguousarray(img, dtype=np.float32))
+        if fx.get("variance") and spp == fx["ref_spp"][0]:        # the reference's second output (render.cpp:263-278)
+            var = cv2.imread(os.path.join(work, f"{name}_variance.exr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+            np.save(os.path.join(HERE, f"{name}.refvar{spp}.npy"), np.ascontiguousarray(var, dtype=np.float32))
     meta["scenes"][name] = entry
     print(f"[fixtures] {name}: ok", flush=True)
 

@@ -101,3 +101,14 @@ def test_reference_ttests(test, idx, meta, make_oracle):
     ok, mean, pval = students_t_accept(luminance(vals.astype(np.float64)), t["references"][idx],
                                        t["significance"], len(t["references"]))
     assert ok, (test, idx, mean, t["references"][idx], pval)
+
+
+@pytest.mark.parametrize("name", ["cbox_path_mis", "sphere_mesh_normals"])
+def test_variance_output_matches_reference_binary(name, golden_scene, make_oracle):
+    """<scene>_variance.exr of nori_ref (render.cpp:263-278) vs the oracle, pixel by pixel."""
+    sc = golden_scene(name)
+    film, var = make_oracle(sc).render_with_variance(4, mode=1)
+    ref = np.load(os.path.join(GOLDEN, f"{name}.refvar4.npy"))
+    # var = E[m^2] - E[m]^2 cancels catastrophically in fp32: tolerance relative to the largest m^2
+    scale = max(np.abs(ref).max(), 1e-6)
+    assert np.abs(var - ref).max() < 2e-5 * scale + 1e-6
