@@ -60,6 +60,17 @@ FIXTURES = [
                '<vector name="direction" value="0.2,-1,-0.1"/><float name="falloffStart" value="15"/><float name="totalWidth" value="35"/></emitter>'
                '<emitter type="point"><point name="position" value="-0.5,0.8,0.6"/><color name="power" value="4,8,12"/></emitter>'),
     dict(name="cbox_envmap", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 64], envmap=True),
+    # BASELINE config 3: Disney + microfacet BSDFs, envmap emitter, thin-lens camera, path_mis
+    dict(name="c3_project", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=4000, seq=1000, ref_spp=[4, 64], envmap=True,
+         camera=("thinlens", '<float name="lensRadius" value="0.03"/><float name="focalDist" value="4.9"/>'),
+         swap=[('<bsdf type="mirror"/>', '<bsdf type="disney"><color name="baseColor" value="0.9,0.6,0.2"/><float name="metallic" value="0.6"/>'
+                '<float name="specular" value="0.8"/><float name="specularTint" value="0.2"/><float name="roughness" value="0.3"/>'
+                '<float name="sheen" value="0.3"/><float name="sheenTint" value="0.5"/></bsdf>'),
+               ('<bsdf type="dielectric"/>', '<bsdf type="microfacet"><float name="alpha" value="0.15"/><color name="kd" value="0.2,0.25,0.6"/></bsdf>')]),
+    # BASELINE config 5: homogeneous medium, volumetric integrator, spot light + envmap
+    dict(name="c5_volumetric", src="project/volumetric/volumetric.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 512], envmap=True,
+         extra='<emitter type="spotlight"><point name="position" value="0,1.5,0.5"/><color name="color" value="30,20,10"/>'
+               '<vector name="direction" value="0.2,-1,-0.1"/><float name="falloffStart" value="15"/><float name="totalWidth" value="35"/></emitter>'),
 ]
 TTESTS = [
     dict(name="ttest_pa4_direct", src="pa4/tests/test-direct.xml"),
@@ -124,6 +135,9 @@ def rewrite(xml, fx, spp):
     if "camera" in fx:
         typ, body = fx["camera"]
         xml = re.sub(r'<camera type="[^"]*">', f'<camera type="{typ}">{body}', xml)
+    for a, b in fx.get("swap", []):
+        assert a in xml, a
+        xml = xml.replace(a, b)
     if "extra" in fx:
         xml = xml.replace("</scene>", fx["extra"] + "</scene>")
     if fx.get("envmap"):
