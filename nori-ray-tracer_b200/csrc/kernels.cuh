@@ -19,6 +19,8 @@
 #include "integrators.cuh"
 
 #define NORI_FREE_SLOT 0xffffffffu
+#define NORI_Q_MISS NORI_BSDF_COUNT          // volumetric only: rays that left the scene may still scatter in the medium
+#define NORI_NQ (NORI_BSDF_COUNT + 1)
 
 struct Pool {
     float4 *rayO, *rayD;      // (o.xyz, mint) (d.xyz, maxt): the 32-byte ray record
@@ -28,16 +30,17 @@ struct Pool {
     uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
     uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
     uint32_t *flags;          // PF_*
-    uint32_t *queue[NORI_BSDF_COUNT];
+    uint32_t *queue[NORI_NQ];
     uint32_t P;
 };
 
 struct Counters {
     unsigned long long next_sample, total_samples, done;
     unsigned long long rays_ext, rays_sh, nodes_ext, prims_ext, nodes_sh, prims_sh, invalid;
+    unsigned long long rays_sh_closest;      // volumetric.cpp:63: the medium vertex's NEE query is a closest-hit one
     // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
     // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
-    uint32_t qcount[2][NORI_BSDF_COUNT];
+    uint32_t qcount[2][NORI_NQ];
     uint32_t work_extend[2], pad[2];
 };
 
@@ -84,13 +87,32 @@ __device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, 
 //   2. closest-hit traversal of every live slot (bvh.cpp:404-462), 32 slots per step;
 //   3. binning of the hits by BSDF type into the material queues (one atomic per warp and material).
 // A path that escapes the scene is finalised here and its slot handed to the next iteration.
-template <bool COUNT>
+// The miss rule (shared by both extend kernels).  path_mis.cpp:28-29 / :84-85: a ray that leaves the scene ends
+// the path.  volumetric.cpp:34-38,147-151: it ends only if it also misses the medium's box
+// (medium.cpp:62-66 returns hitObject without drawing a number); otherwise the free-flight sample may
+// still scatter it, so the slot goes to the miss queue with t = inf (the reference's its.t after a miss).
+template <bool VOL>
+__device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot, V3 o, V3 d, uint32_t &nDone) {
+    if (VOL) {
+        float nearT, farT;
+        if (boundsHit(sc.medium, o, d, nearT, farT)) {
+            pool.hit[slot] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __uint_as_float(NORI_NO_HIT));
+            return NORI_Q_MISS;
+        }
+    }
+    const float4 r = pool.rad[slot];
+    finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+    return -1;
+}
+
+template <bool COUNT, bool VOL>
 __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
         ctr->work_extend[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
@@ -139,14 +161,10 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
                 if (traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt)) {
                     pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
                     type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * h.leafpos + 1]).w)].bsdf_type;
-                } else {                                         // path_mis.cpp:28-29 / :84-85: the path ends here
-                    const float4 r = pool.rad[slot];
-                    finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
-                    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
-                }
+                } else type = missRule<VOL>(sc, pool, bt, ctr, slot, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), nDone);
             }
 #pragma unroll
-            for (int t = 0; t < NORI_BSDF_COUNT; ++t) {
+            for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
                 const uint32_t m = __ballot_sync(0xffffffffu, type == t);
                 if (!m) continue;
                 uint32_t qb = 0; const int leader = __ffs(m) - 1;
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 #ifndef NORI_NODE_BURST
 #define NORI_NODE_BURST 1
 #endif
-enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2 };
+enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
 struct LaneTrav {
     RayTrav r;
@@ -296,14 +314,14 @@ __device__ __forceinline__ bool smPrim(const DScene &sc, LaneTrav &L, uint32_t *
     return false;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool VOL>
 __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int i = 0; i < NORI_BSDF_COUNT; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
         ctr->work_extend[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
@@ -362,11 +380,7 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
                         const float4 ro = pool.rayO[s], rd = pool.rayD[s];
                         L.slot = s; ++nRays;
                         if (travInit(sc, L.r, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w)) L.st = ST_NODE;
-                        else {                                   // decided before the first node: the path escapes
-                            const float4 ra = pool.rad[s];
-                            finalizePath(bt, ctr, pool.sid[s], mk(ra.x, ra.y, ra.z));
-                            pool.sid[s] = NORI_FREE_SLOT; pool.flags[s] = 0u; ++nDone;
-                        }
+                        else { L.r.found = false; L.st = ST_DONE; }  // decided before the first node: a miss
                     }
                 }
                 idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
@@ -386,6 +400,7 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
                 if (L.st == ST_NODE && !finished) finished = smNode<COUNT>(sc, L, stack, cnt);
         }
         // ---- publish finished rays, bin hits by material (one atomic per warp and material)
+        finished = finished || L.st == ST_DONE;
         if (__any_sync(0xffffffffu, finished)) {
             int type = -1;
             if (finished) {
@@ -393,14 +408,10 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
                 if (L.r.found) {
                     pool.hit[L.slot] = make_float4(L.r.hit.t, L.r.hit.u, L.r.hit.v, __uint_as_float(L.r.hit.leafpos));
                     type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * L.r.hit.leafpos + 1]).w)].bsdf_type;
-                } else {
-                    const float4 ra = pool.rad[L.slot];
-                    finalizePath(bt, ctr, pool.sid[L.slot], mk(ra.x, ra.y, ra.z));
-                    pool.sid[L.slot] = NORI_FREE_SLOT; pool.flags[L.slot] = 0u; ++nDone;
-                }
+                } else type = missRule<VOL>(sc, pool, bt, ctr, L.slot, L.r.o, L.r.d, nDone);
             }
 #pragma unroll
-            for (int t = 0; t < NORI_BSDF_COUNT; ++t) {
+            for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
                 const uint32_t m = __ballot_sync(0xffffffffu, type == t);
                 if (!m) continue;
                 uint32_t qb = 0; const int leader = __ffs(m) - 1;

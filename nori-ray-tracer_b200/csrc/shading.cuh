@@ -373,13 +373,22 @@ __device__ __forceinline__ float emitterPdf(const DScene &sc, const nori_gpu_emi
     }
 }
 
-// envmap.cpp:112-121 (search stops at the last valid interval instead of reading past the table)
+// envmap.cpp:112-121.  The reference scans i = 0,1,.. for the first interval with Pf[i] <= s < Pf[i+1];
+// Pf is non-decreasing (a running sum of non-negative terms, last entry 1), so that interval is
+// upper_bound(s) - 1 and a binary search returns the same index in O(log n) instead of O(n) -- it
+// matters because the reference's table puts almost every sample in the LAST interval.
+// When no interval matches (s >= 1) the reference reads past the table; here the last interval is used.
 __device__ __forceinline__ void envSample1D(const float *pfRow, const float *PfRow, int nPf, float s, float &x, float &prob) {
-    int i;
-    for (i = 0; i < nPf - 2; i++)
-        if (__ldg(&PfRow[i]) <= s && s < __ldg(&PfRow[i + 1])) break;
-    float P0 = __ldg(&PfRow[i]), P1 = __ldg(&PfRow[i + 1]);
-    float t = (P1 - s) / (P1 - P0);
+    int lo = 0, hi = nPf - 1;                                   // first index in [0, nPf-1] with Pf > s (or nPf-1)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&PfRow[mid]) > s) hi = mid; else lo = mid + 1;
+    }
+    int i = lo - 1;
+    if (i < 0) i = 0;
+    if (i > nPf - 2) i = nPf - 2;
+    const float P0 = __ldg(&PfRow[i]), P1 = __ldg(&PfRow[i + 1]);
+    const float t = (P1 - s) / (P1 - P0);
     x = (1 - t) * i + t * (i + 1);
     prob = __ldg(&pfRow[i]);
 }
