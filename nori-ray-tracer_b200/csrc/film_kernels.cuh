@@ -1,0 +1,184 @@
+// film_kernels.cuh -- film accumulation / resolve kernels and the ABI's test-hook kernels (included by nori_gpu.cu only)
+#pragma once
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------ film
+struct FilmParams {
+    float4 *film;             // (H+2b) x (W+2b) row-major (r,g,b,w): the memory image of ImageBlock m_block
+    int W, H, border, halo;   // halo == border: source pixels that can reach a film pixel
+    float radius, lookupFactor;
+    float table[NORI_FILTER_RESOLUTION + 1];
+    float4 *vsum, *vsum2;     // per-pixel sums of the running mean and of its square (render.cpp:238-247), or NULL
+};
+
+// smem per layer: (32+2*halo)^2 x { float4 value, float2 pos }
+// VARIANCE: also accumulate, after every spp layer (= one pass of the reference's spp-major loop), the
+// running mean m_k = rgb/w of the pixel and its square -- the reference's `*_variance.exr` statistic
+// (render.cpp:225,238-247,263-278).  The accumulation then starts from the film's current
+// value so that m_k covers every pass rendered so far, across batches and render() calls.
+template <bool VARIANCE>
+__global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t nLayers) {
+    extern __shared__ float4 s_mem[];
+    const int T = 32, halo = fp.halo, S = T + 2 * halo, nS = S * S;
+    float4 *s_val = s_mem;
+    float2 *s_pos = (float2 *) (s_mem + nS);
+    __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
+    const int tid = threadIdx.y * T + threadIdx.x;
+    if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
+    const int b = fp.border;
+    const int fx = blockIdx.x * T + threadIdx.x, fy = blockIdx.y * T + threadIdx.y;   // film pixel owned by this thread
+    const int sx0 = blockIdx.x * T - b - halo, sy0 = blockIdx.y * T - b - halo;       // image coords of the staged region
+    const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 vs = make_float3(0.f, 0.f, 0.f), vs2 = make_float3(0.f, 0.f, 0.f);
+    const bool owner = fx < fcols && fy < frows;
+    if (VARIANCE && owner) acc = fp.film[(size_t) fy * fcols + fx];
+    for (uint32_t k = 0; k < nLayers; ++k) {
+        __syncthreads();
+        for (int i = tid; i < nS; i += T * T) {
+            const int ly = i / S, lx = i - ly * S;
+            const int sx = sx0 + lx, sy = sy0 + ly;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f); float2 p = make_float2(0.f, 0.f);
+            if (sx >= 0 && sx < fp.W && sy >= 0 && sy < fp.H) {
+                const uint32_t pix = (uint32_t) sy * fp.W + sx;
+                v = bt.results[(size_t) k * bt.wh + pix];
+                Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+                P2 a = rng.next2D();
+                const float psx = (float) sx + a.x, psy = (float) sy + a.y;
+                // block.cpp:101-104 with the offset of the 32x32 block that rendered the sample
+                const int ox = sx & ~(NORI_BLOCK_SIZE - 1), oy = sy & ~(NORI_BLOCK_SIZE - 1);
+                p.x = __fsub_rn(__fsub_rn(psx, 0.5f), (float) (ox - b));
+                p.y = __fsub_rn(__fsub_rn(psy, 0.5f), (float) (oy - b));
+            }
+            s_val[i] = v; s_pos[i] = p;
+        }
+        __syncthreads();
+        if (owner) {
+            // staged-region coordinates of the source pixels that can reach (fx, fy)
+            const int cx = threadIdx.x + halo, cy = threadIdx.y + halo;   // own source pixel (image x = fx - b)
+            for (int dy = -halo; dy <= halo; ++dy) {
+                const int sy = sy0 + cy + dy;
+                if (sy < 0 || sy >= fp.H) continue;
+                const int oy = sy & ~(NORI_BLOCK_SIZE - 1);
+                const float yb = (float) (fy - oy);                        // pixel row in that block's coordinates
+                for (int dx = -halo; dx <= halo; ++dx) {
+                    const int sx = sx0 + cx + dx;
+                    if (sx < 0 || sx >= fp.W) continue;
+                    const int ox = sx & ~(NORI_BLOCK_SIZE - 1);
+                    const float xb = (float) (fx - ox);
+                    const int i = (cy + dy) * S + (cx + dx);
+                    const float2 p = s_pos[i];
+                    // window [ceil(p-r), floor(p+r)] of block.cpp:107-110
+                    if (xb < __fsub_rn(p.x, fp.radius) || xb > __fadd_rn(p.x, fp.radius)) continue;
+                    if (yb < __fsub_rn(p.y, fp.radius) || yb > __fadd_rn(p.y, fp.radius)) continue;
+                    const float wx = s_table[(int) __fmul_rn(fabsf(__fsub_rn(xb, p.x)), fp.lookupFactor)];
+                    const float wy = s_table[(int) __fmul_rn(fabsf(__fsub_rn(yb, p.y)), fp.lookupFactor)];
+                    const float4 v = s_val[i];
+                    // Color4f(value) * wx * wy (block.cpp:121)
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                }
+            }
+            if (VARIANCE) {                                      // Color4f::divideByFilterWeight (color.h:84-89)
+                const float mx = acc.w != 0.f ? acc.x / acc.w : 0.f, my = acc.w != 0.f ? acc.y / acc.w : 0.f, mz = acc.w != 0.f ? acc.z / acc.w : 0.f;
+                vs.x += mx; vs.y += my; vs.z += mz;
+                vs2.x += mx * mx; vs2.y += my * my; vs2.z += mz * mz;
+            }
+        }
+    }
+    if (owner) {
+        float4 *dst = &fp.film[(size_t) fy * fcols + fx];
+        if (VARIANCE) {
+            *dst = acc;
+            float4 a = fp.vsum[(size_t) fy * fcols + fx], b = fp.vsum2[(size_t) fy * fcols + fx];
+            a.x += vs.x; a.y += vs.y; a.z += vs.z; b.x += vs2.x; b.y += vs2.y; b.z += vs2.z;
+            fp.vsum[(size_t) fy * fcols + fx] = a; fp.vsum2[(size_t) fy * fcols + fx] = b;
+        } else {
+            float4 f = *dst;
+            f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+            *dst = f;
+        }
+    }
+}
+
+// var = sum2/N - (sum/N)^2 per channel (render.cpp:268-275)
+__global__ void k_variance(const float4 *vsum, const float4 *vsum2, float *rgb, int W, int H, int b, float n) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 s = vsum[(size_t) (y + b) * (W + 2 * b) + (x + b)], s2 = vsum2[(size_t) (y + b) * (W + 2 * b) + (x + b)];
+    float *o = &rgb[((size_t) y * W + x) * 3];
+    const float mx = s.x / n, my = s.y / n, mz = s.z / n;
+    o[0] = s2.x / n - mx * mx; o[1] = s2.y / n - my * my; o[2] = s2.z / n - mz * mz;
+}
+
+__global__ void k_resolve(const float4 *film, float *rgb, int W, int H, int b) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 c = film[(size_t) (y + b) * (W + 2 * b) + (x + b)];
+    float *o = &rgb[((size_t) y * W + x) * 3];
+    if (c.w != 0.f) { o[0] = c.x / c.w; o[1] = c.y / c.w; o[2] = c.z / c.w; } else { o[0] = o[1] = o[2] = 0.f; }
+}
+
+// ------------------------------------------------------------------------------ test hooks
+template <bool SHADOW>
+__global__ void __launch_bounds__(128) k_trace(DScene sc, const nori_gpu_ray *rays, unsigned long long n, nori_gpu_hit *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_ray r = rays[i];
+    Hit h; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    bool found = traverse<SHADOW, true>(sc, mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, h, cnt);
+    nori_gpu_hit o;
+    o.t = h.t; o.u = h.u; o.v = h.v; o.shape = NORI_NO_HIT; o.prim = NORI_NO_HIT;
+    o.nodes_visited = cnt.nodes; o.prims_tested = cnt.prims; o.reserved = 0;
+    if (found && !SHADOW) {
+        o.prim = __float_as_uint(sc.prims[3 * h.leafpos].w);
+        o.shape = __float_as_uint(sc.prims[3 * h.leafpos + 1].w);
+    }
+    out[i] = o;
+}
+
+__global__ void k_pcg32(uint64_t initstate, uint64_t initseq, unsigned long long n, float *outf, uint32_t *outu) {
+    if (blockIdx.x || threadIdx.x) return;
+    Pcg32 r; r.seed(initstate, initseq);
+    for (unsigned long long i = 0; i < n; ++i) { if (outf) outf[i] = r.nextFloat(); else outu[i] = r.nextUInt(); }
+}
+
+// per-function probes (rows as in oracle/ref_tools/nori_export.cpp --probe):
+//   bsdf    in (wi.xyz, wo.xyz, uv.xy, sample.xy)   out (eval.rgb, pdf, weight.rgb, wo.xyz, measure, pdf(sampled))
+//   emitter in (ref.xyz, sample.xy)                 out (Li.rgb, wi.xyz, pdf, mint, maxt, p.xyz, eval.rgb)
+__global__ void k_probe_bsdf(DScene sc, uint32_t bsdf, unsigned long long n, const float *in, float *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_bsdf &b = sc.bsdfs[bsdf];
+    const float *q = &in[10 * i]; float *o = &out[12 * i];
+    BRec e; e.wi = mk(q[0], q[1], q[2]); e.wo = mk(q[3], q[4], q[5]); e.measure = M_SOLID_ANGLE; e.uv.x = q[6]; e.uv.y = q[7];
+    V3 ev = bsdfEvalDyn(b, e); float pdf = bsdfPdfDyn(b, e);
+    BRec r; r.wi = e.wi; r.measure = M_UNKNOWN; r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
+    V3 w = bsdfSampleDyn(b, r, s); float pdf2 = bsdfPdfDyn(b, r);
+    o[0] = ev.x; o[1] = ev.y; o[2] = ev.z; o[3] = pdf; o[4] = w.x; o[5] = w.y; o[6] = w.z;
+    o[7] = r.wo.x; o[8] = r.wo.y; o[9] = r.wo.z; o[10] = (float) r.measure; o[11] = pdf2;
+}
+__global__ void k_probe_emitter(DScene sc, uint32_t emitter, unsigned long long n, const float *in, float *out) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const nori_gpu_emitter &em = sc.emitters[emitter].pod;
+    const float *q = &in[5 * i]; float *o = &out[15 * i];
+    ERec e = makeERec(mk(q[0], q[1], q[2])); P2 s; s.x = q[3]; s.y = q[4];
+    e.shadow = mkray(e.ref, mk(0.f));
+    V3 Li = emitterSample(sc, em, e, s); float pdf = emitterPdf(sc, em, e); V3 ev = emitterEval(sc, em, e);
+    o[0] = Li.x; o[1] = Li.y; o[2] = Li.z; o[3] = e.wi.x; o[4] = e.wi.y; o[5] = e.wi.z; o[6] = pdf;
+    o[7] = e.shadow.mint; o[8] = e.shadow.maxt; o[9] = e.p.x; o[10] = e.p.y; o[11] = e.p.z;
+    o[12] = ev.x; o[13] = ev.y; o[14] = ev.z;
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_flush(float4 *buf, size_t n) {     // bench helper: evict L2 between timed steps
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}

@@ -4,6 +4,9 @@
 #pragma once
 #include "shading.cuh"
 
+#define NORI_Q_MISS NORI_BSDF_COUNT          // volumetric only: rays that left the scene may still scatter in the medium
+#define NORI_NQ (NORI_BSDF_COUNT + 1)
+
 enum { PF_ALIVE = 1u, PF_SHADOW = 2u, PF_TERMINATE = 4u, PF_FIRST = 8u, PF_DISCRETE = 16u };
 
 struct PathState {
@@ -215,7 +218,7 @@ __device__ __forceinline__ bool boundsContain(const nori_gpu_medium &m, V3 p) { 
     return p.x >= m.bounds_min[0] && p.x <= m.bounds_max[0] && p.y >= m.bounds_min[1] && p.y <= m.bounds_max[1]
         && p.z >= m.bounds_min[2] && p.z <= m.bounds_max[2];
 }
-__device__ V3 mediumTr(const nori_gpu_medium &m, V3 src, V3 dst) {                       // medium.cpp:22-57
+static __device__ V3 mediumTr(const nori_gpu_medium &m, V3 src, V3 dst) {                       // medium.cpp:22-57
     float nearT, farT;
     V3 d = normalized(dst - src);
     if (!boundsHit(m, src, d, nearT, farT)) return mk(1.0f);
@@ -225,7 +228,7 @@ __device__ V3 mediumTr(const nori_gpu_medium &m, V3 src, V3 dst) {              
     V3 ext = arr3(m.sigma_a) + arr3(m.sigma_s);
     return mk(expf(-ext.x * len), expf(-ext.y * len), expf(-ext.z * len));
 }
-__device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg32 &rng, float tMax, bool &hitObject, V3 &p) {   // medium.cpp:59-90
+static __device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg32 &rng, float tMax, bool &hitObject, V3 &p) {   // medium.cpp:59-90
     float nearT, farT;
     if (!boundsHit(m, ray.o, ray.d, nearT, farT)) { hitObject = true; return mk(1.0f); }
     V3 sp = boundsContain(m, ray.o) ? ray.o : ray.o + normalized(ray.d) * nearT;
@@ -235,6 +238,82 @@ __device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg32 &rng,
     V3 albedo = mk(m.sigma_s[0] / ext.x, m.sigma_s[1] / ext.y, m.sigma_s[2] / ext.z);
     if (distance >= tMax) hitObject = true; else { p = ray.o + distance * ray.d; hitObject = false; }
     return albedo;
+}
+
+
+// One iteration of the while(true) body of VolumetricIntegrator::Li (volumetric.cpp:31-151) for the
+// wavefront: the closest-hit query of the current ray has been answered by k_extend (`hit`; BSDF ==
+// NORI_Q_MISS when it left the scene).  Free-flight sampling decides between a medium vertex
+// (volumetric.cpp:47-87) and a surface vertex (:89-145); both NEE queries are traced here.  `w_mats`
+// of the reference (:76-82, :133-142) is a function of the pdf of the direction that produced the
+// current ray, of whether it came from a discrete BSDF, and of the emitter that was hit -- it is
+// recomputed here from st.pdf_mat / PF_DISCRETE / PF_FIRST with the same expression.
+template <int BSDF, bool COUNT>
+__device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, PathState &st, Ray &next,
+                                          uint32_t &nClosest, uint32_t &nShadow, TraceCounters &cnt) {
+    const nori_gpu_medium &med = sc.medium;
+    constexpr bool intersection = BSDF != NORI_Q_MISS;
+    const uint32_t inFlags = st.flags;
+    Its its;
+    float tmax = hit.t;
+    if constexpr (intersection) { hitInfo(sc, st.o, st.d, hit, its); tmax = norm(its.p - st.o); }
+    bool hitObject; V3 mp = mk(0.f);
+    const Ray cur = mkray(st.o, st.d);
+    const V3 sampled = mediumSample(med, cur, st.rng, tmax, hitObject, mp);
+    if (!hitObject) {
+        V3 wo = squareToUniformSphere(st.rng.next2D()); const float pdf_mat = NORI_INV_FOURPI;   // phasefunction.cpp:13-16
+        const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
+        ERec e = makeERec(mp);
+        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
+        st.thr = st.thr * sampled;
+        // a closest-hit query in the reference (volumetric.cpp:63); only its boolean is used, which an
+        // any-hit query answers identically -- the closest-hit form is kept when the counters are on
+        Hit tmp; ++nClosest;
+        if (!traverse<!COUNT, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt))
+            st.rad = st.rad + st.thr * mediumTr(med, mp, e.p) * Li * pdf_mat;
+        float p = fminf(st.thr.x, 0.80f);
+        if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
+        st.thr = st.thr / p;
+        next = mkray(mp, normalized(wo));
+        st.pdf_mat = pdf_mat; st.flags = PF_ALIVE;
+    } else if constexpr (intersection) {
+        const DShape &shp = sc.shapes[its.shape];
+        const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+        if (shp.emitter >= 0) {
+            const nori_gpu_emitter &em = sc.emitters[shp.emitter].pod;
+            ERec e = makeERec(st.o, its.p, its.sh.n);
+            float w_mats = 1.0f;
+            if (!(inFlags & (PF_FIRST | PF_DISCRETE))) {
+                float pdf_em = emitterPdf(sc, em, e);
+                w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
+            }
+            st.rad = st.rad + st.thr * w_mats * emitterEval(sc, em, e) * mediumTr(med, its.p, e.p);
+        }
+        const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
+        ERec e = makeERec(its.p);
+        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
+        const V3 wiLocal = toLocal(its.sh, -st.d);
+        Hit tmp; ++nShadow;
+        if (!traverse<true, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt)) {
+            float pdf_em = emitterPdf(sc, light, e);
+            V3 woLocal = toLocal(its.sh, e.wi);
+            float theta = fmaxf(0.0f, woLocal.z);
+            BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv.x = 0.f; b.uv.y = 0.f;   // uv not set, :103
+            V3 f = evalT<BSDF>(bsdf, b);
+            float pdf_mat = pdfT<BSDF>(bsdf, b);
+            float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+            st.rad = st.rad + st.thr * w_ems * f * theta * Li * mediumTr(med, its.p, e.p);
+        }
+        float p = fminf(st.thr.x, 0.80f);
+        if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
+        st.thr = st.thr / p;
+        BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv.x = 0.f; b.uv.y = 0.f;
+        V3 w = sampleT<BSDF>(bsdf, b, st.rng.next2D());
+        st.thr = st.thr * w;
+        st.pdf_mat = pdfT<BSDF>(bsdf, b);
+        next = mkray(its.p, toWorld(its.sh, b.wo));
+        st.flags = PF_ALIVE | (b.measure == M_DISCRETE ? PF_DISCRETE : 0u);
+    } else st.flags = PF_TERMINATE;                                 // volumetric.cpp:147-151
 }
 
 // volumetric.cpp:18-156

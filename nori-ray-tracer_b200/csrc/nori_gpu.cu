@@ -1,7 +1,7 @@
 // nori_gpu.cu -- the extern "C" boundary of include/nori_gpu.h over the kernels in kernels.cuh.
 // One context = one CUDA device + one stream.  No torch, no exceptions across the ABI, no CPU
 // fallback: every entry point that computes does so on the device or fails with an error string.
-#include "kernels.cuh"
+#include "film_kernels.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -286,7 +286,7 @@ static int ensurePool(nori_gpu_ctx *ctx) {
     for (auto pp : f4) { *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
-    for (int t = 0; t < NORI_BSDF_COUNT; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }
+    for (int t = 0; t < NORI_NQ; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }
     k_fill_u32<<<(p.P + 255) / 256, 256, 0, ctx->stream>>>(p.sid, NORI_FREE_SLOT, p.P);
     CK(cudaMemsetAsync(p.flags, 0, p.P * 4, ctx->stream));
     CK(cudaGetLastError());
@@ -302,21 +302,16 @@ static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
     return 0;
 }
 
-template <bool MIS> static void launchShade(nori_gpu_ctx *ctx, const Batch &bt, int grid, uint32_t it, bool count) {
-    if (count) LAUNCH(NORI_K_SHADE, (k_shade<MIS, true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-    else LAUNCH(NORI_K_SHADE, (k_shade<MIS, false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-}
-
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
 static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const unsigned long long total = (unsigned long long) nLayers * bt.wh;
     const bool count = ctx->opt_stats != 0;
     const int integ = ctx->ds.integrator;
-    const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS) && !ctx->opt_megakernel;
+    const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
+                      && !ctx->opt_megakernel;
     if (!wave) {
         const unsigned grid = (unsigned) ((total + 127) / 128);
-        if (count) LAUNCH(NORI_K_SINGLE, (k_mega<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total)));
-        else LAUNCH(NORI_K_SINGLE, (k_mega<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, bt, ctx->ctr, total)));
+        LAUNCH(NORI_K_SINGLE, noriLaunchMega(count, grid, ctx->stream, ctx->ds, bt, ctx->ctr, total));
         CK(cudaGetLastError());
         ctx->stats.iterations += 1; ctx->last_wave = false;
         return 0;
@@ -330,23 +325,19 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     // plain per-lane loops for tiny scenes, the warp state machine once trees are deep (see kernels.cuh)
     const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
+    const int mode = integ == NORI_INTEGRATOR_PATH_MIS ? MODE_MIS : integ == NORI_INTEGRATOR_PATH_MATS ? MODE_MATS : MODE_VOL;
+    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL);
     int occE = 8;
-    if (sm) { if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend_sm<false>, 128, 0); }
-    else { if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, k_extend<false>, 128, 0); }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
-    const bool mis = integ == NORI_INTEGRATOR_PATH_MIS;
     ctx->last_wave = true;
     uint32_t it = 0;
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
-            if (sm) {
-                if (count) LAUNCH(NORI_K_EXTEND, (k_extend_sm<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                else LAUNCH(NORI_K_EXTEND, (k_extend_sm<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            } else {
-                if (count) LAUNCH(NORI_K_EXTEND, (k_extend<true><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-                else LAUNCH(NORI_K_EXTEND, (k_extend<false><<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            }
-            if (mis) launchShade<true>(ctx, bt, gridSh, it, count); else launchShade<false>(ctx, bt, gridSh, it, count);
+            LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMats(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            else LAUNCH(NORI_K_SHADE, noriLaunchShadeVol(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             ctx->stats.iterations += 1;
         }
         CK(cudaGetLastError());
@@ -362,13 +353,13 @@ static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     CK(cudaStreamSynchronize(ctx->stream));
     const Counters &c = *ctx->h_ctr;
     ctx->stats.samples += samples;
-    ctx->stats.rays += c.rays_ext + c.rays_sh; ctx->stats.shadow_rays += c.rays_sh;
+    ctx->stats.rays += c.rays_ext + c.rays_sh + c.rays_sh_closest; ctx->stats.shadow_rays += c.rays_sh;
     ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
     ctx->stats.invalid_samples += c.invalid;
     if (ctx->last_wave) {
         nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[NORI_K_SHADE];   // shadow rays are traced inside k_shade
         e.rays += c.rays_ext; e.nodes_visited += c.nodes_ext; e.prims_tested += c.prims_ext;
-        s.rays += c.rays_sh; s.nodes_visited += c.nodes_sh; s.prims_tested += c.prims_sh;
+        s.rays += c.rays_sh + c.rays_sh_closest; s.nodes_visited += c.nodes_sh; s.prims_tested += c.prims_sh;
     } else {
         nori_gpu_kernel_stats &m = ctx->kstats[NORI_K_SINGLE];
         m.rays += c.rays_ext + c.rays_sh; m.nodes_visited += c.nodes_ext + c.nodes_sh; m.prims_tested += c.prims_ext + c.prims_sh;

@@ -257,7 +257,7 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
 }
 
 // runtime-dispatched versions for the single-bounce integrators (megakernel)
-__device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
+static __device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfEval<NORI_BSDF_DIFFUSE>(b, r);
     case NORI_BSDF_MICROFACET: return bsdfEval<NORI_BSDF_MICROFACET>(b, r);
@@ -265,7 +265,7 @@ __device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
     default: return mk(0.f);
     }
 }
-__device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) {
+static __device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfPdf<NORI_BSDF_DIFFUSE>(b, r);
     case NORI_BSDF_MICROFACET: return bsdfPdf<NORI_BSDF_MICROFACET>(b, r);
@@ -273,7 +273,7 @@ __device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) 
     default: return 0.f;
     }
 }
-__device__ __noinline__ V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+static __device__ __noinline__ V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 s) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfSample<NORI_BSDF_DIFFUSE>(b, r, s);
     case NORI_BSDF_MIRROR: return bsdfSample<NORI_BSDF_MIRROR>(b, r, s);

@@ -1,0 +1,293 @@
+// wave_extend.cu -- k_extend / k_extend_sm: closest-hit traversal of the path pool fused with camera-path
+// regeneration and material binning (see kernels.cuh for the overview).
+#include "kernels.cuh"
+
+#define NORI_FETCH 256u      // pool slots claimed per warp per atomic (8 rounds of 32)
+
+// ------------------------------------------------------------------------------ extend (+ regeneration)
+// Persistent warps claim NORI_FETCH consecutive pool slots at a time and run three phases on them:
+//   1. regeneration, compacted: the warp gathers its free slots into a shared-memory list, claims that
+//      many sample indices with ONE atomic, and then every lane generates one camera path per step
+//      (render.cpp:98-124) -- full SIMT width although only ~1/3 of the slots are free per iteration;
+//   2. closest-hit traversal of every live slot (bvh.cpp:404-462), 32 slots per step;
+//   3. binning of the hits by BSDF type into the material queues (one atomic per warp and material).
+// A path that escapes the scene is finalised here and its slot handed to the next iteration.
+// The miss rule (shared by both extend kernels).  path_mis.cpp:28-29 / :84-85: a ray that leaves the scene ends
+// the path.  volumetric.cpp:34-38,147-151: it ends only if it also misses the medium's box
+// (medium.cpp:62-66 returns hitObject without drawing a number); otherwise the free-flight sample may
+// still scatter it, so the slot goes to the miss queue with t = inf (the reference's its.t after a miss).
+template <bool VOL>
+__device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot, V3 o, V3 d, uint32_t &nDone) {
+    if (VOL) {
+        float nearT, farT;
+        if (boundsHit(sc.medium, o, d, nearT, farT)) {
+            pool.hit[slot] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __uint_as_float(NORI_NO_HIT));
+            return NORI_Q_MISS;
+        }
+    }
+    const float4 r = pool.rad[slot];
+    finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
+    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+    return -1;
+}
+
+template <bool COUNT, bool VOL>
+__global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    __shared__ uint32_t s_free[4][NORI_FETCH];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
+    uint32_t *freeList = s_free[warp];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        ctr->work_extend[par ^ 1u] = 0;
+    }
+    const unsigned long long total = ctr->total_samples;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_extend[par], NORI_FETCH);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= pool.P) break;
+        // ---- phase 1: compacted regeneration
+        uint32_t nFree = 0;
+        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+            const uint32_t slot = base + round * 32u + lane;
+            const bool isFree = slot < pool.P && pool.sid[slot] == NORI_FREE_SLOT;
+            const uint32_t m = __ballot_sync(0xffffffffu, isFree);
+            if (isFree) freeList[nFree + __popc(m & ((1u << lane) - 1u))] = slot;
+            nFree += __popc(m);
+        }
+        if (nFree) {
+            unsigned long long first = 0;
+            if (lane == 0) first = atomicAdd(&ctr->next_sample, (unsigned long long) nFree);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            __syncwarp();
+            for (uint32_t j = lane; j < nFree; j += 32u) {
+                const unsigned long long id = first + j;
+                if (id >= total) break;                          // batch exhausted: the slot stays free
+                const uint32_t slot = freeList[j];
+                Ray ray; uint64_t rs;
+                generatePath(sc, bt, (uint32_t) id, ray, rs);
+                pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+                pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+                pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pool.rng[slot] = rs; pool.sid[slot] = (uint32_t) id;
+                pool.flags[slot] = PF_ALIVE | PF_FIRST;
+            }
+            __syncwarp();
+        }
+        // ---- phase 2 + 3: trace and bin
+        for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+            const uint32_t slot = base + round * 32u + lane;
+            int type = -1;
+            if (slot < pool.P && (pool.flags[slot] & PF_ALIVE)) {
+                const float4 ro = pool.rayO[slot], rd = pool.rayD[slot];
+                Hit h; ++nRays;
+                if (traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt)) {
+                    pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
+                    type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * h.leafpos + 1]).w)].bsdf_type;
+                } else type = missRule<VOL>(sc, pool, bt, ctr, slot, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), nDone);
+            }
+#pragma unroll
+            for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
+                const uint32_t m = __ballot_sync(0xffffffffu, type == t);
+                if (!m) continue;
+                uint32_t qb = 0; const int leader = __ffs(m) - 1;
+                if ((int) lane == leader) qb = atomicAdd(&ctr->qcount[par][t], (uint32_t) __popc(m));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (type == t) pool.queue[t][qb + __popc(m & ((1u << lane) - 1u))] = slot;
+            }
+        }
+    }
+    warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
+}
+
+// ------------------------------------------------------------------------------ large-scene trace kernels
+// On scenes with deep trees the rays of one warp need very different numbers of node visits (10 M
+// triangles: 158 on average, long-tailed), and a leaf costs several times an inner node.  Run as plain
+// per-lane loops that leaves a warp at ~5 of 32 active lanes (ncu, profiles/).  These variants keep the
+// SAME per-ray visiting order (so results and counters stay the reference's) but schedule the warp as a
+// small state machine:
+//   * every lane is IDLE, at a NODE (one box test pending) or in a LEAF (one primitive test pending);
+//   * each warp step runs EITHER the node code for all NODE lanes OR the primitive code for all LEAF
+//     lanes -- the primitive phase is entered once NORI_LEAF_MIN lanes wait in a leaf (or nothing else
+//     is runnable), so both code paths execute with many lanes active;
+//   * IDLE lanes are refilled from the warp's slot chunk as soon as NORI_REFILL_MIN lanes are idle, so
+//     short rays do not wait for the longest ray of the warp.
+#define NORI_LEAF_MIN 16
+#define NORI_REFILL_MIN 8
+#ifndef NORI_NODE_BURST
+#define NORI_NODE_BURST 1
+#endif
+enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
+
+struct LaneTrav {
+    RayTrav r;
+    uint32_t st, leafI, leafEnd, slot;
+};
+
+// node phase for one lane: returns true when the ray is finished
+template <bool COUNT>
+__device__ __forceinline__ bool smNode(const DScene &sc, LaneTrav &L, uint32_t *stack, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    const uint4 n0 = __ldg(&sc.nodes[2 * r.node]);
+    const uint4 n1 = __ldg(&sc.nodes[2 * r.node + 1]);
+    if (COUNT) ++cnt.nodes;
+    float nearT = __int_as_float(0xff800000), farT = __int_as_float(0x7f800000);
+    const bool in = slab(r.o.x, r.d.x, r.rcp.x, __uint_as_float(n0.z), __uint_as_float(n1.y), nearT, farT)
+                 && slab(r.o.y, r.d.y, r.rcp.y, __uint_as_float(n0.w), __uint_as_float(n1.z), nearT, farT)
+                 && slab(r.o.z, r.d.z, r.rcp.z, __uint_as_float(n1.x), __uint_as_float(n1.w), nearT, farT)
+                 && (r.mint <= farT && nearT <= r.maxt);
+    if (in) {
+        if (!(n0.x & 1u)) { stack[r.sp++] = n0.y; ++r.node; return false; }
+        const uint32_t size = n0.x >> 1;
+        if (size) { L.st = ST_LEAF; L.leafI = n0.y; L.leafEnd = n0.y + size; return false; }
+    }
+    if (r.sp == 0) return true;
+    r.node = stack[--r.sp];
+    return false;
+}
+
+// primitive phase for one lane: one primitive test; returns true when the ray is finished
+template <bool SHADOW, bool COUNT>
+__device__ __forceinline__ bool smPrim(const DScene &sc, LaneTrav &L, uint32_t *stack, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    const uint32_t i = L.leafI;
+    const float4 r0 = __ldg(&sc.prims[3 * i]);
+    const float4 r1 = __ldg(&sc.prims[3 * i + 1]);
+    const float4 r2 = __ldg(&sc.prims[3 * i + 2]);
+    if (COUNT) ++cnt.prims;
+    float u = 0.f, v = 0.f, t;
+    bool h;
+    if (__float_as_uint(r2.w) == 0u)
+        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
+    else
+        h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
+    if (h) {
+        r.found = true;
+        if (SHADOW) { r.hit.t = 0.f; return true; }
+        r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
+    }
+    if (++L.leafI < L.leafEnd) return false;
+    L.st = ST_NODE;
+    if (r.sp == 0) return true;
+    r.node = stack[--r.sp];
+    return false;
+}
+
+template <bool COUNT, bool VOL>
+__global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    __shared__ uint32_t s_free[4][NORI_FETCH];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    uint32_t *freeList = s_free[warp];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        ctr->work_extend[par ^ 1u] = 0;
+    }
+    const unsigned long long total = ctr->total_samples;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t stack[64];
+    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0;
+    uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
+    bool moreChunks = true;
+    while (true) {
+        // ---- refill
+        uint32_t idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+        if (idle && (moreChunks || chunkNext < NORI_FETCH) && (__popc(idle) >= NORI_REFILL_MIN || idle == 0xffffffffu)) {
+            while (idle) {
+                if (chunkNext >= NORI_FETCH) {
+                    if (!moreChunks) break;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&ctr->work_extend[par], NORI_FETCH);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= pool.P) { moreChunks = false; break; }
+                    chunkBase = base; chunkNext = 0;
+                    uint32_t nFree = 0;                          // compacted regeneration (render.cpp:98-124)
+                    for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+                        const uint32_t s = base + round * 32u + lane;
+                        const bool isFree = s < pool.P && pool.sid[s] == NORI_FREE_SLOT;
+                        const uint32_t m = __ballot_sync(0xffffffffu, isFree);
+                        if (isFree) freeList[nFree + __popc(m & ltMask)] = s;
+                        nFree += __popc(m);
+                    }
+                    if (nFree) {
+                        unsigned long long first = 0;
+                        if (lane == 0) first = atomicAdd(&ctr->next_sample, (unsigned long long) nFree);
+                        first = __shfl_sync(0xffffffffu, first, 0);
+                        __syncwarp();
+                        for (uint32_t j = lane; j < nFree; j += 32u) {
+                            const unsigned long long id = first + j;
+                            if (id >= total) break;
+                            const uint32_t s = freeList[j];
+                            Ray ray; uint64_t rs;
+                            generatePath(sc, bt, (uint32_t) id, ray, rs);
+                            pool.rayO[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                            pool.rayD[s] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+                            pool.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+                            pool.rad[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            pool.rng[s] = rs; pool.sid[s] = (uint32_t) id;
+                            pool.flags[s] = PF_ALIVE | PF_FIRST;
+                        }
+                        __syncwarp();
+                    }
+                }
+                const uint32_t idx = chunkNext + __popc(idle & ltMask);
+                const bool take = L.st == ST_IDLE && idx < NORI_FETCH;
+                chunkNext = min(chunkNext + (uint32_t) __popc(idle), NORI_FETCH);
+                if (take) {
+                    const uint32_t s = chunkBase + idx;
+                    if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
+                        const float4 ro = pool.rayO[s], rd = pool.rayD[s];
+                        L.slot = s; ++nRays;
+                        if (travInit(sc, L.r, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w)) L.st = ST_NODE;
+                        else { L.r.found = false; L.st = ST_DONE; }  // decided before the first node: a miss
+                    }
+                }
+                idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+            }
+        }
+        // ---- pick the phase
+        const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
+        const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
+        if (!(mNode | mLeaf)) { if (!moreChunks && chunkNext >= NORI_FETCH) break; else continue; }
+        bool finished = false;
+        if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
+            if (L.st == ST_LEAF) finished = smPrim<false, COUNT>(sc, L, stack, cnt);
+        } else {
+            // several node visits per scheduling decision: lanes that reach a leaf or finish sit out the rest
+#pragma unroll 1
+            for (int k = 0; k < NORI_NODE_BURST; ++k)
+                if (L.st == ST_NODE && !finished) finished = smNode<COUNT>(sc, L, stack, cnt);
+        }
+        // ---- publish finished rays, bin hits by material (one atomic per warp and material)
+        finished = finished || L.st == ST_DONE;
+        if (__any_sync(0xffffffffu, finished)) {
+            int type = -1;
+            if (finished) {
+                L.st = ST_IDLE;
+                if (L.r.found) {
+                    pool.hit[L.slot] = make_float4(L.r.hit.t, L.r.hit.u, L.r.hit.v, __uint_as_float(L.r.hit.leafpos));
+                    type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * L.r.hit.leafpos + 1]).w)].bsdf_type;
+                } else type = missRule<VOL>(sc, pool, bt, ctr, L.slot, L.r.o, L.r.d, nDone);
+            }
+#pragma unroll
+            for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
+                const uint32_t m = __ballot_sync(0xffffffffu, type == t);
+                if (!m) continue;
+                uint32_t qb = 0; const int leader = __ffs(m) - 1;
+                if ((int) lane == leader) qb = atomicAdd(&ctr->qcount[par][t], (uint32_t) __popc(m));
+                qb = __shfl_sync(0xffffffffu, qb, leader);
+                if (type == t) pool.queue[t][qb + __popc(m & ltMask)] = L.slot;
+            }
+        }
+    }
+    warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
+}
+
+ExtendKernel noriPickExtend(bool sm, bool count, bool vol) {
+    if (sm) return count ? (vol ? k_extend_sm<true, true> : k_extend_sm<true, false>) : (vol ? k_extend_sm<false, true> : k_extend_sm<false, false>);
+    return count ? (vol ? k_extend<true, true> : k_extend<true, false>) : (vol ? k_extend<false, true> : k_extend<false, false>);
+}

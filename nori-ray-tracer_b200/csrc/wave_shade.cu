@@ -1,0 +1,87 @@
+// wave_shade.cu -- k_shade, compiled once per integrator mode (-DNORI_SHADE_MODE=0|1|2: path_mats,
+// path_mis, volumetric) so the three variants build in parallel.
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------ shade
+// One queue entry: the whole loop body of PathMisIntegrator::Li for one path vertex, INCLUDING the
+// any-hit query of the NEE shadow ray (path_mis.cpp:48).  Tracing the shadow ray here, in the thread
+// that just built it, keeps the ray, its pending contribution and the roulette decision in registers:
+// no shadow-ray record is written to the pool and no separate pass re-reads the path state
+// (measured: shade + shadow went from 266 ms to the fused number in DESIGN.md on the Cornell box).
+
+template <int BSDF, int MODE, bool COUNT>
+__device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
+                                          uint32_t &nDone, uint32_t &nShadow, uint32_t &nClosest, TraceCounters &cnt) {
+    const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
+    const uint32_t sid = pool.sid[slot];
+    PathState st;
+    st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
+    st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
+    st.flags = pool.flags[slot];
+    st.rng.state = pool.rng[slot]; st.rng.inc = ((uint64_t) (sid % bt.wh) << 1u) | 1u;
+    Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
+    Ray next;
+    if constexpr (MODE == MODE_VOL) {
+        volVertex<BSDF, COUNT>(sc, h, st, next, nClosest, nShadow, cnt);
+    } else {
+        VertexOut out;
+        pathVertex<BSDF, MODE == MODE_MIS>(sc, h, st, out);
+        if (MODE == MODE_MIS) {                                     // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
+            Hit sh; ++nShadow;
+            if (!traverse<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
+                st.rad = st.rad + out.contrib;
+        }
+        next = out.next;
+    }
+    if (st.flags & PF_ALIVE) {
+        pool.rayO[slot] = make_float4(next.o.x, next.o.y, next.o.z, next.mint);
+        pool.rayD[slot] = make_float4(next.d.x, next.d.y, next.d.z, next.maxt);
+        pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
+        pool.rng[slot] = st.rng.state;
+        if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
+        pool.flags[slot] = st.flags & (PF_ALIVE | PF_DISCRETE);
+    } else {                                                    // Russian roulette ended the path
+        finalizePath(bt, ctr, sid, st.rad);
+        pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+    }
+}
+
+// All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
+// microfacet | disney | [volumetric: misses]) and work item i belongs to the queue whose range contains
+// it, so warps are material-coherent except where a boundary falls inside one.
+#ifndef NORI_SHADE_MINBLOCKS
+#define NORI_SHADE_MINBLOCKS 6
+#endif
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    uint32_t off[NORI_NQ + 1]; off[0] = 0;
+#pragma unroll
+    for (int t = 0; t < NORI_NQ; ++t) off[t + 1] = off[t] + ctr->qcount[it & 1u][t];
+    const uint32_t n = off[NORI_NQ];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
+        else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
+        else if constexpr (MODE == MODE_VOL) shadeSlot<NORI_Q_MISS, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[NORI_Q_MISS][i - off[5]], nDone, nShadow, nClosest, cnt);
+    }
+    warpAdd(&ctr->done, nDone);
+    if (MODE != MODE_MATS) warpAdd(&ctr->rays_sh, nShadow);
+    if (MODE == MODE_VOL) warpAdd(&ctr->rays_sh_closest, nClosest);
+    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
+}
+
+#if NORI_SHADE_MODE == 0
+#define LAUNCHER noriLaunchShadeMats
+#elif NORI_SHADE_MODE == 1
+#define LAUNCHER noriLaunchShadeMis
+#else
+#define LAUNCHER noriLaunchShadeVol
+#endif
+void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    if (count) k_shade<NORI_SHADE_MODE, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<NORI_SHADE_MODE, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+}
