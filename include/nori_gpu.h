@@ -205,7 +205,10 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
 /* Tunables: "pool" (resident path slots), "spp_chunk" (samples per pixel per film batch),
  * "stats" (1: count node visits / primitive tests), "kernel_timing" (1: CUDA events around every
  * launch), "megakernel" (1: one thread per sample for every integrator), "poll", "results_mb",
- * "flush_l2" (bench only: overwrite that many MiB to evict L2). */
+ * "flush_l2" (bench only: overwrite that many MiB to evict L2), "order" (0: the reference's child
+ * order, left child first, bvh.cpp:430-433 -- node-visit / primitive-test counters equal the
+ * reference's; 1: the child on the ray's side of the node's split axis first -- same hits, same
+ * primitive ids incl. the reference's tie rule, fewer node visits). */
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);
 
 /* Render sample indices [spp_begin, spp_begin+spp_count) for every pixel and ACCUMULATE them into

@@ -36,6 +36,7 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_order = 0;             // 0 reference child order (counters equal the reference's), 1 near child first
     int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
 
     nori_gpu_stats stats{};
@@ -149,6 +150,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         }
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
+    else if (k == "order") { REQUIRE(value >= 0 && value <= 1, "order must be 0 (reference child order) or 1 (near child first)"); ctx->opt_order = value; ctx->ds.ordered = (int32_t) value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
         // bench helper: overwrite a buffer larger than L2 (value = MiB)
@@ -177,6 +179,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     ctx->has_scene = false;
     DScene ds{};
     ds.n_nodes = s->n_nodes; ds.n_prims = s->n_indices; ds.n_shapes = s->n_shapes; ds.n_emitters = s->n_emitters;
+    ds.ordered = (int32_t) ctx->opt_order;
     ds.integrator = s->integrator; ds.av_length = s->av_length; ds.camera = s->camera; ds.medium = s->medium;
 
     // ---- per-shape arrays + shape table

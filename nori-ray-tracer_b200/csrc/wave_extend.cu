@@ -140,7 +140,7 @@ __device__ __forceinline__ bool smNode(const DScene &sc, LaneTrav &L, uint32_t *
                  && slab(r.o.z, r.d.z, r.rcp.z, __uint_as_float(n1.x), __uint_as_float(n1.w), nearT, farT)
                  && (r.mint <= farT && nearT <= r.maxt);
     if (in) {
-        if (!(n0.x & 1u)) { stack[r.sp++] = n0.y; ++r.node; return false; }
+        if (!(n0.x & 1u)) { descend(sc, n0, r.d, r.node, stack, r.sp); return false; }
         const uint32_t size = n0.x >> 1;
         if (size) { L.st = ST_LEAF; L.leafI = n0.y; L.leafEnd = n0.y + size; return false; }
     }
@@ -164,7 +164,7 @@ __device__ __forceinline__ bool smPrim(const DScene &sc, LaneTrav &L, uint32_t *
         h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
     else
         h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
-    if (h) {
+    if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
         r.found = true;
         if (SHADOW) { r.hit.t = 0.f; return true; }
         r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;

@@ -49,6 +49,9 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
 // microfacet | disney | [volumetric: misses]) and work item i belongs to the queue whose range contains
 // it, so warps are material-coherent except where a boundary falls inside one.
+#ifndef NORI_SHADE_TEMPLATED
+#define NORI_SHADE_TEMPLATED 0
+#endif
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
@@ -61,12 +64,24 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#if NORI_SHADE_TEMPLATED
         if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
         else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
         else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
         else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
         else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
         else if constexpr (MODE == MODE_VOL) shadeSlot<NORI_Q_MISS, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[NORI_Q_MISS][i - off[5]], nDone, nShadow, nClosest, cnt);
+#else
+        // ONE copy of the vertex code for every material: the BSDF's eval / pdf / sample are reached through
+        // a switch on the BSDF type, which is warp-uniform because the queues are sorted by type.  (A copy
+        // of the whole vertex per BSDF type made the kernel 0.5 MB of SASS and instruction-fetch bound.)
+        int q = 0;
+#pragma unroll
+        for (int t = 1; t < NORI_NQ; ++t) q += i >= off[t];
+        const uint32_t slot = pool.queue[q][i - off[q]];
+        if (MODE == MODE_VOL && q == NORI_Q_MISS) shadeSlot<NORI_Q_MISS, MODE, COUNT>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        else shadeSlot<-1, MODE, COUNT>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+#endif
     }
     warpAdd(&ctr->done, nDone);
     if (MODE != MODE_MATS) warpAdd(&ctr->rays_sh, nShadow);

@@ -9,7 +9,7 @@ spp = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 pool = int(sys.argv[2]) if len(sys.argv) > 2 else (1 << 21)
 scene = sys.argv[3] if len(sys.argv) > 3 else 'cbox_path_mis'
 sc = nscene.load_scene(f'tests/golden/{scene}.nscene')
-if scene.startswith('cbox') or scene.startswith('table') or scene.startswith('disney'):
+if scene.startswith(('cbox', 'table', 'disney', 'c3', 'c5', 'volumetric')):
     sc.set_resolution(800, 600)
 g = NoriGpu(0); g.upload_scene(sc); g.set_option('pool', pool)
 g.render(0, spp, seed=0)
