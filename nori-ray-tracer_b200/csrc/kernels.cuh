@@ -25,6 +25,8 @@ struct Pool {
     float4 *hit;              // (t, u, v, leafpos): the 16-byte hit record
     float4 *thr;              // (throughput rgb, pdf_mat)
     float4 *rad;              // (radiance rgb, -)
+    float4 *shD, *shC;        // deferred NEE shadow ray (large scenes only): (direction, maxt) -- origin = rayO, mint = Epsilon --
+                              // and its pending contribution; NULL when shadow rays are traced inside k_shade
     uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
     uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
     uint32_t *flags;          // PF_*
@@ -39,7 +41,7 @@ struct Counters {
     // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
     // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
     uint32_t qcount[2][NORI_NQ];
-    uint32_t work_extend[2], pad[2];
+    uint32_t work_extend[2], work_shadow[2];
 };
 
 struct Batch {
@@ -82,6 +84,9 @@ enum { MODE_MATS = 0, MODE_MIS = 1, MODE_VOL = 2 };
 typedef void (*ExtendKernel)(DScene, Pool, Batch, Counters *, uint32_t);
 ExtendKernel noriPickExtend(bool stateMachine, bool count, bool vol);
 void noriLaunchShadeMats(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+int noriShadowSmOccupancy(bool count);
 void noriLaunchShadeMis(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchMega(bool count, unsigned grid, cudaStream_t st, const DScene &sc, const Batch &bt, Counters *ctr, unsigned long long total);

@@ -36,7 +36,10 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
-    int64_t opt_order = 0;             // 0 reference child order (counters equal the reference's), 1 near child first
+    int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
+    // 0 reference child order (counters equal the reference's), 1 near child first, 2 auto: near child first when
+    // rendering scenes with deep trees, reference order for small scenes and for the nori_gpu_trace test hook
+    int64_t opt_order = 2;
     int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
 
     nori_gpu_stats stats{};
@@ -45,7 +48,7 @@ struct nori_gpu_ctx {
     // optional per-launch timing (option "kernel_timing")
     int64_t opt_kernel_timing = 0;
     std::vector<cudaEvent_t> kev; std::vector<int> kev_kind; size_t kev_used = 0;
-    bool last_wave = false;
+    bool last_wave = false, last_defer = false;
 };
 
 // bracket one kernel launch: counts it and, with kernel_timing on, records a CUDA event pair on the stream
@@ -150,7 +153,8 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         }
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
-    else if (k == "order") { REQUIRE(value >= 0 && value <= 1, "order must be 0 (reference child order) or 1 (near child first)"); ctx->opt_order = value; ctx->ds.ordered = (int32_t) value; }
+    else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
+    else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
         // bench helper: overwrite a buffer larger than L2 (value = MiB)
@@ -179,7 +183,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     ctx->has_scene = false;
     DScene ds{};
     ds.n_nodes = s->n_nodes; ds.n_prims = s->n_indices; ds.n_shapes = s->n_shapes; ds.n_emitters = s->n_emitters;
-    ds.ordered = (int32_t) ctx->opt_order;
+    ds.ordered = 0;
     ds.integrator = s->integrator; ds.av_length = s->av_length; ds.camera = s->camera; ds.medium = s->medium;
 
     // ---- per-shape arrays + shape table
@@ -280,13 +284,14 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
 
 } // extern "C"
 
-static int ensurePool(nori_gpu_ctx *ctx) {
-    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty()) return 0;
+static int ensurePool(nori_gpu_ctx *ctx, bool deferShadow) {
+    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty() && (!deferShadow || ctx->pool.shD)) return 0;
     freeAll(ctx->pool_allocs);
     Pool p{}; p.P = (uint32_t) ctx->opt_pool;
     auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
-    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad};
-    for (auto pp : f4) { *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
+    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shD, &p.shC};
+    for (auto pp : f4) {
+        if (!deferShadow && (pp == &p.shD || pp == &p.shC)) continue; *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
     for (int t = 0; t < NORI_NQ; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }
@@ -310,6 +315,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const unsigned long long total = (unsigned long long) nLayers * bt.wh;
     const bool count = ctx->opt_stats != 0;
     const int integ = ctx->ds.integrator;
+    ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
                       && !ctx->opt_megakernel;
     if (!wave) {
@@ -319,26 +325,32 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
         ctx->stats.iterations += 1; ctx->last_wave = false;
         return 0;
     }
-    if (ensurePool(ctx)) return 1;
+    // plain per-lane loops for tiny scenes, the warp state machine once trees are deep (see wave_extend.cu)
+    const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
+    const int mode = integ == NORI_INTEGRATOR_PATH_MIS ? MODE_MIS : integ == NORI_INTEGRATOR_PATH_MATS ? MODE_MATS : MODE_VOL;
+    // NEE shadow rays: traced inside k_shade on small scenes, by their own state-machine pass on deep trees
+    const bool defer = mode == MODE_MIS && (ctx->opt_shadow_pass == 1 || (ctx->opt_shadow_pass == 0 && sm && ctx->ds.n_prims > (1u << 18)));
+    if (ensurePool(ctx, defer)) return 1;
     // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
     Counters zero{}; zero.total_samples = total;
     *ctx->h_ctr = zero;
     CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    // plain per-lane loops for tiny scenes, the warp state machine once trees are deep (see kernels.cuh)
-    const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
-    const int mode = integ == NORI_INTEGRATOR_PATH_MIS ? MODE_MIS : integ == NORI_INTEGRATOR_PATH_MATS ? MODE_MATS : MODE_VOL;
     const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL);
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
-    ctx->last_wave = true;
+    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count)) : 0;
+    ctx->last_wave = true; ctx->last_defer = defer;
     uint32_t it = 0;
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
             LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            if (defer) {
+                LAUNCH(NORI_K_SHADE, noriLaunchShadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+                LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            } else if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMats(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             else LAUNCH(NORI_K_SHADE, noriLaunchShadeVol(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             ctx->stats.iterations += 1;
@@ -360,7 +372,8 @@ static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
     ctx->stats.invalid_samples += c.invalid;
     if (ctx->last_wave) {
-        nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[NORI_K_SHADE];   // shadow rays are traced inside k_shade
+        // shadow rays are traced inside k_shade unless the deferred pass ran
+        nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[ctx->last_defer ? NORI_K_SHADOW : NORI_K_SHADE];
         e.rays += c.rays_ext; e.nodes_visited += c.nodes_ext; e.prims_tested += c.prims_ext;
         s.rays += c.rays_sh + c.rays_sh_closest; s.nodes_visited += c.nodes_sh; s.prims_tested += c.prims_sh;
     } else {
@@ -514,6 +527,7 @@ int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int 
     cudaError_t e = cudaMemcpyAsync(dr, rays, n * sizeof(nori_gpu_ray), cudaMemcpyHostToDevice, ctx->stream);
     cudaEventRecord(ctx->ev0, ctx->stream);
     const unsigned grid = (unsigned) ((n + 127) / 128);
+    ctx->ds.ordered = ctx->opt_order == 1;
     if (shadow) k_trace<true><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
     else k_trace<false><<<grid, 128, 0, ctx->stream>>>(ctx->ds, dr, n, dh);
     ctx->stats.kernel_launches++;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
-        ctr->work_extend[par ^ 1u] = 0;
+        ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
@@ -105,31 +105,52 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 
 // ------------------------------------------------------------------------------ large-scene trace kernels
 // On scenes with deep trees the rays of one warp need very different numbers of node visits (10 M
-// triangles: 158 on average, long-tailed), and a leaf costs several times an inner node.  Run as plain
+// triangles: ~100 on average, long-tailed), and a leaf costs several times an inner node.  Run as plain
 // per-lane loops that leaves a warp at ~5 of 32 active lanes (ncu, profiles/).  These variants keep the
-// SAME per-ray visiting order (so results and counters stay the reference's) but schedule the warp as a
-// small state machine:
-//   * every lane is IDLE, at a NODE (one box test pending) or in a LEAF (one primitive test pending);
+// SAME per-ray visiting order (results, and in reference order the counters, are unchanged) but schedule
+// the warp as a small state machine:
+//   * every lane is IDLE, at a NODE (one box test pending), in a LEAF (one primitive test pending) or
+//     DONE (its answer waits in registers to be published);
 //   * each warp step runs EITHER the node code for all NODE lanes OR the primitive code for all LEAF
 //     lanes -- the primitive phase is entered once NORI_LEAF_MIN lanes wait in a leaf (or nothing else
 //     is runnable), so both code paths execute with many lanes active;
-//   * IDLE lanes are refilled from the warp's slot chunk as soon as NORI_REFILL_MIN lanes are idle, so
-//     short rays do not wait for the longest ray of the warp.
+//   * the stepping loop (smRun) costs two ballots per step; publishing answers and refilling lanes from
+//     the warp's slot chunk happens only once NORI_REFILL_MIN lanes are out of work, so short rays do
+//     not wait for the longest ray of the warp and long rays do not pay for the bookkeeping.
+#ifndef NORI_PREFETCH
+#define NORI_PREFETCH 1
+#endif
 #define NORI_LEAF_MIN 16
 #define NORI_REFILL_MIN 8
-#ifndef NORI_NODE_BURST
-#define NORI_NODE_BURST 1
-#endif
 enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
 struct LaneTrav {
     RayTrav r;
     uint32_t st, leafI, leafEnd, slot;
+    uint32_t neg;          // bit a set: the ray runs towards -a and the near-child-first order is on (descend(), traverse.cuh)
 };
 
-// node phase for one lane: returns true when the ray is finished
+// Traversal stack of one lane: the first NORI_SM_STACK entries live in shared memory (column `tid` of a
+// [entry][thread] array: conflict-free), deeper ones spill to a local array.  With the whole stack in local
+// memory (ncu, 10M-triangle scene) every pop was an L1 lookup with a 47 % miss rate -- an L2 round trip in
+// front of the node fetch that depends on it -- and the stack lines evicted node data from L1.
+#define NORI_SM_STACK 32
+struct LaneStack {
+    uint32_t *sh;                       // &s_stack[0][tid]; entry e at sh[e * 128]
+    uint32_t ovf[64 - NORI_SM_STACK];
+    __device__ __forceinline__ void push(uint32_t sp, uint32_t v) { if (sp < NORI_SM_STACK) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK] = v; }
+    __device__ __forceinline__ uint32_t pop(uint32_t sp) const { return sp < NORI_SM_STACK ? sh[sp * 128u] : ovf[sp - NORI_SM_STACK]; }
+};
+
+__device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 d, float mint, float maxt) {
+    L.neg = sc.ordered ? ((d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u)) : 0u;
+    if (travInit(sc, L.r, o, d, mint, maxt)) L.st = ST_NODE;
+    else { L.r.found = false; L.st = ST_DONE; }                  // decided before the first node: a miss
+}
+
+// node phase for one lane
 template <bool COUNT>
-__device__ __forceinline__ bool smNode(const DScene &sc, LaneTrav &L, uint32_t *stack, TraceCounters &cnt) {
+__device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint4 n0 = __ldg(&sc.nodes[2 * r.node]);
     const uint4 n1 = __ldg(&sc.nodes[2 * r.node + 1]);
@@ -140,18 +161,36 @@ __device__ __forceinline__ bool smNode(const DScene &sc, LaneTrav &L, uint32_t *
                  && slab(r.o.z, r.d.z, r.rcp.z, __uint_as_float(n1.x), __uint_as_float(n1.w), nearT, farT)
                  && (r.mint <= farT && nearT <= r.maxt);
     if (in) {
-        if (!(n0.x & 1u)) { descend(sc, n0, r.d, r.node, stack, r.sp); return false; }
+        if (!(n0.x & 1u)) {                                      // inner: descend() of traverse.cuh with the sign mask
+            const bool swap = (L.neg >> (n0.x >> 1)) & 1u;
+            const uint32_t farC = swap ? r.node + 1 : n0.y;
+            stack.push(r.sp++, farC);
+            r.node = swap ? n0.y : r.node + 1;
+#if NORI_PREFETCH
+            // the far child is fetched many steps from now (after the near subtree): start pulling its line
+            // towards L2 so that the pop finds it there instead of paying a DRAM round trip in lockstep
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes[2 * farC]));
+#endif
+            return;
+        }
         const uint32_t size = n0.x >> 1;
-        if (size) { L.st = ST_LEAF; L.leafI = n0.y; L.leafEnd = n0.y + size; return false; }
+        if (size) {
+            L.st = ST_LEAF; L.leafI = n0.y; L.leafEnd = n0.y + size;
+#if NORI_PREFETCH
+            // the lane now waits for NORI_LEAF_MIN lanes to reach a leaf: pull its primitive records meanwhile
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.prims[3 * n0.y]));
+            if (size > 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.prims[3 * n0.y + 8]));
+#endif
+            return;
+        }
     }
-    if (r.sp == 0) return true;
-    r.node = stack[--r.sp];
-    return false;
+    if (r.sp == 0) { L.st = ST_DONE; return; }
+    r.node = stack.pop(--r.sp);
 }
 
-// primitive phase for one lane: one primitive test; returns true when the ray is finished
+// primitive phase for one lane: one primitive test
 template <bool SHADOW, bool COUNT>
-__device__ __forceinline__ bool smPrim(const DScene &sc, LaneTrav &L, uint32_t *stack, TraceCounters &cnt) {
+__device__ __forceinline__ void smPrim(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint32_t i = L.leafI;
     const float4 r0 = __ldg(&sc.prims[3 * i]);
@@ -166,106 +205,63 @@ __device__ __forceinline__ bool smPrim(const DScene &sc, LaneTrav &L, uint32_t *
         h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
     if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
         r.found = true;
-        if (SHADOW) { r.hit.t = 0.f; return true; }
+        if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }
         r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
     }
-    if (++L.leafI < L.leafEnd) return false;
+    if (++L.leafI < L.leafEnd) return;
+    if (r.sp == 0) { L.st = ST_DONE; return; }
     L.st = ST_NODE;
-    if (r.sp == 0) return true;
-    r.node = stack[--r.sp];
-    return false;
+    r.node = stack.pop(--r.sp);
+}
+
+// Step the warp until NORI_REFILL_MIN lanes are out of work (and `canRefill` says new rays exist) or no
+// lane has work left.
+template <bool SHADOW, bool COUNT>
+__device__ __forceinline__ void smRun(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt, bool canRefill) {
+    while (true) {
+        const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
+        const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
+        const uint32_t mWork = mNode | mLeaf;
+        if (!mWork || (canRefill && __popc(mWork) <= 32 - NORI_REFILL_MIN)) return;
+        if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
+            if (L.st == ST_LEAF) smPrim<SHADOW, COUNT>(sc, L, stack, cnt);
+        } else {
+            if (L.st == ST_NODE) smNode<COUNT>(sc, L, stack, cnt);
+        }
+    }
+}
+
+// Claim the warp's next NORI_FETCH pool slots; returns false when the pool is exhausted.
+__device__ __forceinline__ bool smNextChunk(uint32_t *work, uint32_t P, uint32_t lane, uint32_t &chunkBase) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work, NORI_FETCH);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    chunkBase = base;
+    return base < P;
 }
 
 template <bool COUNT, bool VOL>
-__global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+__global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
-        ctr->work_extend[par ^ 1u] = 0;
+        ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    uint32_t stack[64];
-    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0;
+    __shared__ uint32_t s_stack[NORI_SM_STACK][128];
+    LaneStack stack; stack.sh = &s_stack[0][threadIdx.x];
+    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0;
     uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
     bool moreChunks = true;
     while (true) {
-        // ---- refill
-        uint32_t idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
-        if (idle && (moreChunks || chunkNext < NORI_FETCH) && (__popc(idle) >= NORI_REFILL_MIN || idle == 0xffffffffu)) {
-            while (idle) {
-                if (chunkNext >= NORI_FETCH) {
-                    if (!moreChunks) break;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&ctr->work_extend[par], NORI_FETCH);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= pool.P) { moreChunks = false; break; }
-                    chunkBase = base; chunkNext = 0;
-                    uint32_t nFree = 0;                          // compacted regeneration (render.cpp:98-124)
-                    for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
-                        const uint32_t s = base + round * 32u + lane;
-                        const bool isFree = s < pool.P && pool.sid[s] == NORI_FREE_SLOT;
-                        const uint32_t m = __ballot_sync(0xffffffffu, isFree);
-                        if (isFree) freeList[nFree + __popc(m & ltMask)] = s;
-                        nFree += __popc(m);
-                    }
-                    if (nFree) {
-                        unsigned long long first = 0;
-                        if (lane == 0) first = atomicAdd(&ctr->next_sample, (unsigned long long) nFree);
-                        first = __shfl_sync(0xffffffffu, first, 0);
-                        __syncwarp();
-                        for (uint32_t j = lane; j < nFree; j += 32u) {
-                            const unsigned long long id = first + j;
-                            if (id >= total) break;
-                            const uint32_t s = freeList[j];
-                            Ray ray; uint64_t rs;
-                            generatePath(sc, bt, (uint32_t) id, ray, rs);
-                            pool.rayO[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
-                            pool.rayD[s] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
-                            pool.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
-                            pool.rad[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            pool.rng[s] = rs; pool.sid[s] = (uint32_t) id;
-                            pool.flags[s] = PF_ALIVE | PF_FIRST;
-                        }
-                        __syncwarp();
-                    }
-                }
-                const uint32_t idx = chunkNext + __popc(idle & ltMask);
-                const bool take = L.st == ST_IDLE && idx < NORI_FETCH;
-                chunkNext = min(chunkNext + (uint32_t) __popc(idle), NORI_FETCH);
-                if (take) {
-                    const uint32_t s = chunkBase + idx;
-                    if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
-                        const float4 ro = pool.rayO[s], rd = pool.rayD[s];
-                        L.slot = s; ++nRays;
-                        if (travInit(sc, L.r, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w)) L.st = ST_NODE;
-                        else { L.r.found = false; L.st = ST_DONE; }  // decided before the first node: a miss
-                    }
-                }
-                idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
-            }
-        }
-        // ---- pick the phase
-        const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
-        const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
-        if (!(mNode | mLeaf)) { if (!moreChunks && chunkNext >= NORI_FETCH) break; else continue; }
-        bool finished = false;
-        if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
-            if (L.st == ST_LEAF) finished = smPrim<false, COUNT>(sc, L, stack, cnt);
-        } else {
-            // several node visits per scheduling decision: lanes that reach a leaf or finish sit out the rest
-#pragma unroll 1
-            for (int k = 0; k < NORI_NODE_BURST; ++k)
-                if (L.st == ST_NODE && !finished) finished = smNode<COUNT>(sc, L, stack, cnt);
-        }
         // ---- publish finished rays, bin hits by material (one atomic per warp and material)
-        finished = finished || L.st == ST_DONE;
-        if (__any_sync(0xffffffffu, finished)) {
+        if (__any_sync(0xffffffffu, L.st == ST_DONE)) {
             int type = -1;
-            if (finished) {
+            if (L.st == ST_DONE) {
                 L.st = ST_IDLE;
                 if (L.r.found) {
                     pool.hit[L.slot] = make_float4(L.r.hit.t, L.r.hit.u, L.r.hit.v, __uint_as_float(L.r.hit.leafpos));
@@ -282,9 +278,131 @@ __global__ void __launch_bounds__(128) k_extend_sm(DScene sc, Pool pool, Batch b
                 if (type == t) pool.queue[t][qb + __popc(m & ltMask)] = L.slot;
             }
         }
+        // ---- refill idle lanes from the warp's chunk of pool slots
+        uint32_t idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+        while (idle) {
+            if (chunkNext >= NORI_FETCH) {
+                if (!moreChunks) break;
+                if (!smNextChunk(&ctr->work_extend[par], pool.P, lane, chunkBase)) { moreChunks = false; break; }
+                chunkNext = 0;
+                uint32_t nFree = 0;                              // compacted regeneration (render.cpp:98-124)
+                for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
+                    const uint32_t s = chunkBase + round * 32u + lane;
+                    const bool isFree = s < pool.P && pool.sid[s] == NORI_FREE_SLOT;
+                    const uint32_t m = __ballot_sync(0xffffffffu, isFree);
+                    if (isFree) freeList[nFree + __popc(m & ltMask)] = s;
+                    nFree += __popc(m);
+                }
+                if (nFree) {
+                    unsigned long long first = 0;
+                    if (lane == 0) first = atomicAdd(&ctr->next_sample, (unsigned long long) nFree);
+                    first = __shfl_sync(0xffffffffu, first, 0);
+                    __syncwarp();
+                    for (uint32_t j = lane; j < nFree; j += 32u) {
+                        const unsigned long long id = first + j;
+                        if (id >= total) break;
+                        const uint32_t s = freeList[j];
+                        Ray ray; uint64_t rs;
+                        generatePath(sc, bt, (uint32_t) id, ray, rs);
+                        pool.rayO[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                        pool.rayD[s] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+                        pool.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+                        pool.rad[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        pool.rng[s] = rs; pool.sid[s] = (uint32_t) id;
+                        pool.flags[s] = PF_ALIVE | PF_FIRST;
+                    }
+                    __syncwarp();
+                }
+            }
+            const uint32_t idx = chunkNext + __popc(idle & ltMask);
+            const bool take = L.st == ST_IDLE && idx < NORI_FETCH;
+            chunkNext = min(chunkNext + (uint32_t) __popc(idle), NORI_FETCH);
+            if (take) {
+                const uint32_t s = chunkBase + idx;
+                if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
+                    const float4 ro = pool.rayO[s], rd = pool.rayD[s];
+                    L.slot = s; ++nRays;
+                    smStart(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
+                }
+            }
+            idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+        }
+        const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
+        if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
+        smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
+}
+
+// ------------------------------------------------------------------------------ deferred shadow rays
+// Any-hit traversal (bvh.cpp:441-442) of the NEE rays k_shade<.., DEFER> left in the pool, same warp
+// state machine as k_extend_sm.  Adds the pending contribution when the ray is unoccluded
+// (path_mis.cpp:48-61) and finalises the paths the roulette ended.
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    const uint32_t lane = threadIdx.x & 31, par = it & 1u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    __shared__ uint32_t s_stack[NORI_SM_STACK][128];
+    LaneStack stack; stack.sh = &s_stack[0][threadIdx.x];
+    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0;
+    uint32_t flags = 0;
+    uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
+    bool moreChunks = true;
+    while (true) {
+        if (L.st == ST_DONE) {                                   // publish
+            L.st = ST_IDLE;
+            float4 ra = pool.rad[L.slot];
+            if (!L.r.found) { const float4 c = pool.shC[L.slot]; ra.x = __fadd_rn(ra.x, c.x); ra.y = __fadd_rn(ra.y, c.y); ra.z = __fadd_rn(ra.z, c.z); }
+            if (flags & PF_TERMINATE) {
+                finalizePath(bt, ctr, pool.sid[L.slot], mk(ra.x, ra.y, ra.z));
+                pool.sid[L.slot] = NORI_FREE_SLOT; pool.flags[L.slot] = 0; ++nDone;
+            } else {
+                if (!L.r.found) pool.rad[L.slot] = ra;
+                pool.flags[L.slot] = flags & ~PF_SHADOW;
+            }
+        }
+        uint32_t idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+        while (idle) {
+            if (chunkNext >= NORI_FETCH) {
+                if (!moreChunks) break;
+                if (!smNextChunk(&ctr->work_shadow[par], pool.P, lane, chunkBase)) { moreChunks = false; break; }
+                chunkNext = 0;
+            }
+            const uint32_t idx = chunkNext + __popc(idle & ltMask);
+            const bool take = L.st == ST_IDLE && idx < NORI_FETCH;
+            chunkNext = min(chunkNext + (uint32_t) __popc(idle), NORI_FETCH);
+            if (take) {
+                const uint32_t s = chunkBase + idx;
+                if (s < pool.P) {
+                    const uint32_t f = pool.flags[s];
+                    if (f & PF_SHADOW) {
+                        const float4 so = pool.rayO[s], sd = pool.shD[s];
+                        L.slot = s; flags = f; ++nRays;
+                        smStart(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
+                    }
+                }
+            }
+            idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
+        }
+        const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
+        if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
+        smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
+    }
+    warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
+    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
+}
+
+void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    if (count) k_shadow_sm<true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shadow_sm<false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+}
+int noriShadowSmOccupancy(bool count) {
+    int occ = 8;
+    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false>, 128, 0);
+    return occ;
 }
 
 ExtendKernel noriPickExtend(bool sm, bool count, bool vol) {

@@ -9,7 +9,11 @@
 // no shadow-ray record is written to the pool and no separate pass re-reads the path state
 // (measured: shade + shadow went from 266 ms to the fused number in DESIGN.md on the Cornell box).
 
-template <int BSDF, int MODE, bool COUNT>
+// DEFER (path_mis on large scenes): the shadow ray is not traced here but written to the pool (direction
+// + far end; it starts at the next ray's origin with mint = Epsilon, arealight.cpp:56) together with its
+// pending contribution, and k_shadow_sm traces it with the warp state machine -- on deep trees a
+// plain per-lane loop inside this kernel leaves most lanes idle.
+template <int BSDF, int MODE, bool COUNT, bool DEFER>
 __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
                                           uint32_t &nDone, uint32_t &nShadow, uint32_t &nClosest, TraceCounters &cnt) {
     const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
@@ -26,7 +30,16 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
     } else {
         VertexOut out;
         pathVertex<BSDF, MODE == MODE_MIS>(sc, h, st, out);
-        if (MODE == MODE_MIS) {                                     // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
+        if (DEFER) {
+            pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
+            pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
+            if (!(st.flags & PF_ALIVE)) {                           // the roulette ended the path: k_shadow_sm finalises it
+                pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
+                if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
+                pool.flags[slot] = PF_SHADOW | PF_TERMINATE;
+                return;
+            }
+        } else if (MODE == MODE_MIS) {                              // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
             Hit sh; ++nShadow;
             if (!traverse<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
                 st.rad = st.rad + out.contrib;
@@ -39,7 +52,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
         pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
         pool.rng[slot] = st.rng.state;
         if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
-        pool.flags[slot] = st.flags & (PF_ALIVE | PF_DISCRETE);
+        pool.flags[slot] = st.flags & (PF_ALIVE | PF_DISCRETE | (DEFER ? PF_SHADOW : 0u));
     } else {                                                    // Russian roulette ended the path
         finalizePath(bt, ctr, sid, st.rad);
         pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
@@ -55,7 +68,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool DEFER>
 __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     uint32_t off[NORI_NQ + 1]; off[0] = 0;
 #pragma unroll
@@ -65,12 +78,12 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
     uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 #if NORI_SHADE_TEMPLATED
-        if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
-        else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
-        else if constexpr (MODE == MODE_VOL) shadeSlot<NORI_Q_MISS, MODE, COUNT>(sc, pool, bt, ctr, pool.queue[NORI_Q_MISS][i - off[5]], nDone, nShadow, nClosest, cnt);
+        if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
+        else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
+        else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
+        else if constexpr (MODE == MODE_VOL) shadeSlot<NORI_Q_MISS, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[NORI_Q_MISS][i - off[5]], nDone, nShadow, nClosest, cnt);
 #else
         // ONE copy of the vertex code for every material: the BSDF's eval / pdf / sample are reached through
         // a switch on the BSDF type, which is warp-uniform because the queues are sorted by type.  (A copy
@@ -79,12 +92,12 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 #pragma unroll
         for (int t = 1; t < NORI_NQ; ++t) q += i >= off[t];
         const uint32_t slot = pool.queue[q][i - off[q]];
-        if (MODE == MODE_VOL && q == NORI_Q_MISS) shadeSlot<NORI_Q_MISS, MODE, COUNT>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-        else shadeSlot<-1, MODE, COUNT>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        if (MODE == MODE_VOL && q == NORI_Q_MISS) shadeSlot<NORI_Q_MISS, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        else shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
 #endif
     }
     warpAdd(&ctr->done, nDone);
-    if (MODE != MODE_MATS) warpAdd(&ctr->rays_sh, nShadow);
+    if (MODE != MODE_MATS && !DEFER) warpAdd(&ctr->rays_sh, nShadow);
     if (MODE == MODE_VOL) warpAdd(&ctr->rays_sh_closest, nClosest);
     if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
@@ -97,6 +110,12 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 #define LAUNCHER noriLaunchShadeVol
 #endif
 void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    if (count) k_shade<NORI_SHADE_MODE, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<NORI_SHADE_MODE, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    if (count) k_shade<NORI_SHADE_MODE, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<NORI_SHADE_MODE, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
 }
+#if NORI_SHADE_MODE == 1
+void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    if (count) k_shade<MODE_MIS, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<MODE_MIS, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+}
+#endif

@@ -9,7 +9,7 @@ spp = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 integ = sys.argv[3] if len(sys.argv) > 3 else 'path_mis'
 t = time.time(); sc = host_scene.heightfield_scene(n=n, integrator=integ); print('build s', round(time.time() - t, 1), 'prims', sc.pod.n_indices, 'nodes', sc.pod.n_nodes, flush=True)
 g = NoriGpu(0); t = time.time(); g.upload_scene(sc); print('upload s', round(time.time() - t, 2))
-g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '0')))
+g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '2')))
 g.render(0, 2, seed=1)
 g.set_option('stats', 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); s = g.stats(); kc = g.kernel_stats(); g.set_option('stats', 0)
 print('rays/sample', s.rays / s.samples, 'shadow/sample', s.shadow_rays / s.samples, 'nodes/ray', s.nodes_visited / s.rays, 'prims/ray', s.prims_tested / s.rays)
