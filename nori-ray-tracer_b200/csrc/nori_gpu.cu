@@ -262,6 +262,42 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             if (devUpload(ctx, ctx->scene_allocs, h.env_cmarginal, R + 1, &e.env_cmarginal)) return 1;
         } else { e.env_image = e.env_pdf = e.env_cdf = e.env_pmarginal = e.env_cmarginal = nullptr; }
     }
+    // ---- child-box layout for the large-scene kernels (wave_extend.cu): one 64-byte record per inner node
+    // with both children's boxes and references.  Built only when every leaf fits the reference encoding.
+    std::vector<uint4> nodes2;
+    {
+        const uint32_t *w = (const uint32_t *) s->nodes;         // 8 words per node: flag|size-or-axis, start-or-right, bmin[3], bmax[3]
+        auto isLeaf = [&](uint32_t i) { return (w[8 * (size_t) i] & 1u) != 0; };
+        bool ok = s->n_nodes > 0 && !isLeaf(0) && s->n_indices < (1u << 25) && s->n_nodes < (1u << 29);
+        std::vector<uint32_t> innerIdx;
+        if (ok) {
+            innerIdx.assign(s->n_nodes, 0);
+            uint32_t n = 0;
+            for (uint32_t i = 0; i < s->n_nodes && ok; ++i) {
+                if (isLeaf(i)) { if ((w[8 * (size_t) i] >> 1) > 63u) ok = false; }
+                else innerIdx[i] = n++;
+            }
+            if (ok) {
+                nodes2.resize(4 * (size_t) n);
+                auto ref = [&](uint32_t c) -> uint32_t {
+                    const uint32_t w0 = w[8 * (size_t) c], w1 = w[8 * (size_t) c + 1];
+                    return isLeaf(c) ? (0x80000000u | ((w0 >> 1) << 25) | w1) : ((innerIdx[c] << 2) | ((w0 >> 1) & 3u));
+                };
+                for (uint32_t i = 0; i < s->n_nodes; ++i) {
+                    if (isLeaf(i)) continue;
+                    const uint32_t l = i + 1, r = w[8 * (size_t) i + 1];
+                    REQUIRE(r < s->n_nodes && l < s->n_nodes, "upload_scene: BVH child index out of range");
+                    const uint32_t *a = &w[8 * (size_t) l], *b = &w[8 * (size_t) r];
+                    uint4 *o = &nodes2[4 * (size_t) innerIdx[i]];
+                    o[0] = make_uint4(a[2], a[3], a[4], ref(l)); o[1] = make_uint4(a[5], a[6], a[7], ref(r));
+                    o[2] = make_uint4(b[2], b[3], b[4], 0u);     o[3] = make_uint4(b[5], b[6], b[7], 0u);
+                }
+                ds.root_ref = (w[0] >> 1) & 3u;
+                memcpy(ds.root_min, &w[2], 12); memcpy(ds.root_max, &w[5], 12);
+            }
+        }
+    }
+    if (devUpload(ctx, ctx->scene_allocs, nodes2.data(), nodes2.size(), &ds.nodes2)) return 1;
     static_assert(sizeof(nori_gpu_bvh_node) == 2 * sizeof(uint4), "node layout");
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) s->nodes, 2 * (size_t) s->n_nodes, &ds.nodes)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, prims.data(), prims.size(), &ds.prims)) return 1;
@@ -337,11 +373,11 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL);
+    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL, sm && ctx->ds.ordered && ctx->ds.nodes2);
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
-    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count)) : 0;
+    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count, ctx->ds.ordered && ctx->ds.nodes2)) : 0;
     ctx->last_wave = true; ctx->last_defer = defer;
     uint32_t it = 0;
     while (true) {

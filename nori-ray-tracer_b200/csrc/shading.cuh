@@ -256,8 +256,17 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
     }
 }
 
-// runtime-dispatched versions for the single-bounce integrators (megakernel)
-static __device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
+// runtime-dispatched versions: a switch on the BSDF type (warp-uniform in k_shade, whose queues are sorted by
+// type).  Out of line in the one-thread-per-sample kernel (many call sites), inline in k_shade.
+#ifndef NORI_DYN_INLINE
+#define NORI_DYN_INLINE 0
+#endif
+#if NORI_DYN_INLINE
+#define NORI_DYN __forceinline__
+#else
+#define NORI_DYN __noinline__
+#endif
+static __device__ NORI_DYN V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec &r) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfEval<NORI_BSDF_DIFFUSE>(b, r);
     case NORI_BSDF_MICROFACET: return bsdfEval<NORI_BSDF_MICROFACET>(b, r);
@@ -265,7 +274,7 @@ static __device__ __noinline__ V3 bsdfEvalDyn(const nori_gpu_bsdf &b, const BRec
     default: return mk(0.f);
     }
 }
-static __device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) {
+static __device__ NORI_DYN float bsdfPdfDyn(const nori_gpu_bsdf &b, const BRec &r) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfPdf<NORI_BSDF_DIFFUSE>(b, r);
     case NORI_BSDF_MICROFACET: return bsdfPdf<NORI_BSDF_MICROFACET>(b, r);
@@ -273,7 +282,7 @@ static __device__ __noinline__ float bsdfPdfDyn(const nori_gpu_bsdf &b, const BR
     default: return 0.f;
     }
 }
-static __device__ __noinline__ V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 s) {
+static __device__ NORI_DYN V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 s) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE: return bsdfSample<NORI_BSDF_DIFFUSE>(b, r, s);
     case NORI_BSDF_MIRROR: return bsdfSample<NORI_BSDF_MIRROR>(b, r, s);

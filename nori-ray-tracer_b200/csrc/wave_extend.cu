@@ -114,19 +114,22 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 //   * each warp step runs EITHER the node code for all NODE lanes OR the primitive code for all LEAF
 //     lanes -- the primitive phase is entered once NORI_LEAF_MIN lanes wait in a leaf (or nothing else
 //     is runnable), so both code paths execute with many lanes active;
+//     (measured on the 10M-triangle scene: thresholds 4..8 are best, 16 costs 20 %, 24 costs 80 %);
 //   * the stepping loop (smRun) costs two ballots per step; publishing answers and refilling lanes from
 //     the warp's slot chunk happens only once NORI_REFILL_MIN lanes are out of work, so short rays do
 //     not wait for the longest ray of the warp and long rays do not pay for the bookkeeping.
-#ifndef NORI_PREFETCH
-#define NORI_PREFETCH 1
+#ifndef NORI_LEAF_MIN
+#define NORI_LEAF_MIN 8
 #endif
-#define NORI_LEAF_MIN 16
-#define NORI_REFILL_MIN 8
+#ifndef NORI_REFILL_MIN
+#define NORI_REFILL_MIN 4
+#endif
 enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
 struct LaneTrav {
     RayTrav r;
     uint32_t st, leafI, leafEnd, slot;
+    uint32_t cur;          // child-box layout only: reference of the current inner node (index << 2 | split axis)
     uint32_t neg;          // bit a set: the ray runs towards -a and the near-child-first order is on (descend(), traverse.cuh)
 };
 
@@ -134,7 +137,9 @@ struct LaneTrav {
 // [entry][thread] array: conflict-free), deeper ones spill to a local array.  With the whole stack in local
 // memory (ncu, 10M-triangle scene) every pop was an L1 lookup with a 47 % miss rate -- an L2 round trip in
 // front of the node fetch that depends on it -- and the stack lines evicted node data from L1.
+#ifndef NORI_SM_STACK
 #define NORI_SM_STACK 32
+#endif
 struct LaneStack {
     uint32_t *sh;                       // &s_stack[0][tid]; entry e at sh[e * 128]
     uint32_t ovf[64 - NORI_SM_STACK];
@@ -142,10 +147,126 @@ struct LaneStack {
     __device__ __forceinline__ uint32_t pop(uint32_t sp) const { return sp < NORI_SM_STACK ? sh[sp * 128u] : ovf[sp - NORI_SM_STACK]; }
 };
 
+// Child-box layout (DScene::nodes2; built at upload from the reference's nodes, see nori_gpu.cu): one
+// 64-byte record per INNER node holding the boxes and references of both children, so that
+//   * one step answers two box tests from one record (4 x LDG.128) -- half the dependent fetches;
+//   * leaf nodes are never fetched: a leaf child's reference carries its primitive range;
+//   * the far child is pushed together with its entry distance and culled at pop time, without a fetch,
+//     when a closer hit has been found meanwhile.
+// The box arithmetic is the reference's slab test on the reference's boxes, so the set of primitives a
+// ray can reach is unchanged; used with the near-child-first order only (the node counters then count
+// boxes tested and no longer equal the reference's).
+//   child reference: bit 31 = leaf; leaf: size in bits 30..25, first primitive in bits 24..0;
+//                    inner: record index in bits 30..2, split axis in bits 1..0
+#ifndef NORI_SM_STACK2
+#define NORI_SM_STACK2 16
+#endif
+struct LaneStack2 {
+    uint2 *sh;                          // &s_stack2[0][tid]; entry e at sh[e * 128]
+    uint2 ovf[64 - NORI_SM_STACK2];
+    __device__ __forceinline__ void push(uint32_t sp, uint32_t ref, float nearT) {
+        const uint2 v = make_uint2(ref, __float_as_uint(nearT));
+        if (sp < NORI_SM_STACK2) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK2] = v;
+    }
+    __device__ __forceinline__ uint2 pop(uint32_t sp) const { return sp < NORI_SM_STACK2 ? sh[sp * 128u] : ovf[sp - NORI_SM_STACK2]; }
+};
+
+// bbox.h:336-363 on one child box, plus the interval test of bvh.cpp:423
+__device__ __forceinline__ bool boxTest(const RayTrav &r, float3 mn, float3 mx, float &nearT) {
+    nearT = __int_as_float(0xff800000); float farT = __int_as_float(0x7f800000);
+    return slab(r.o.x, r.d.x, r.rcp.x, mn.x, mx.x, nearT, farT) && slab(r.o.y, r.d.y, r.rcp.y, mn.y, mx.y, nearT, farT)
+        && slab(r.o.z, r.d.z, r.rcp.z, mn.z, mx.z, nearT, farT) && (r.mint <= farT && nearT <= r.maxt);
+}
+
+// continue with child `ref`: an inner child becomes the current node, a leaf child the current primitive range
+__device__ __forceinline__ bool smEnter(LaneTrav &L, uint32_t ref) {
+    if (ref & 0x80000000u) {
+        const uint32_t size = (ref >> 25) & 63u, start = ref & 0x1ffffffu;
+        if (!size) return false;                                 // empty leaf (bvh.cpp:437): nothing to do
+        L.st = ST_LEAF; L.leafI = start; L.leafEnd = start + size;
+    } else { L.st = ST_NODE; L.cur = ref; }
+    return true;
+}
+// pop until an entry survives the distance cull; ST_DONE when the stack runs dry
+__device__ __forceinline__ void smPop2(LaneTrav &L, const LaneStack2 &stack) {
+    RayTrav &r = L.r;
+    while (r.sp) {
+        const uint2 e = stack.pop(--r.sp);
+        if (__uint_as_float(e.y) <= r.maxt && smEnter(L, e.x)) return;
+    }
+    L.st = ST_DONE;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    const uint4 *rec = &sc.nodes2[4 * (size_t) (L.cur >> 2)];
+    const uint4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2), d = __ldg(rec + 3);
+    if (COUNT) cnt.nodes += 2;
+    float nearL, nearR;
+    const bool hitL = boxTest(r, make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)),
+                              make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), nearL);
+    const bool hitR = boxTest(r, make_float3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)),
+                              make_float3(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z)), nearR);
+    const bool swap = (L.neg >> (L.cur & 3u)) & 1u;                  // the right child is the near one
+    const uint32_t refN = swap ? b.w : a.w, refF = swap ? a.w : b.w;
+    const bool hitN = swap ? hitR : hitL, hitF = swap ? hitL : hitR;
+    const float nearF = swap ? nearL : nearR;
+    if (hitN) {
+        if (hitF) stack.push(r.sp++, refF, nearF);
+        if (smEnter(L, refN)) return;
+    } else if (hitF && smEnter(L, refF)) return;
+    smPop2(L, stack);
+}
+
+template <bool SHADOW, bool COUNT>
+__device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    const uint32_t i = L.leafI;
+    const float4 r0 = __ldg(&sc.prims[3 * i]);
+    const float4 r1 = __ldg(&sc.prims[3 * i + 1]);
+    const float4 r2 = __ldg(&sc.prims[3 * i + 2]);
+    if (COUNT) ++cnt.prims;
+    float u = 0.f, v = 0.f, t;
+    bool h;
+    if (__float_as_uint(r2.w) == 0u)
+        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
+    else
+        h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
+    if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
+        r.found = true;
+        if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }
+        r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
+    }
+    if (++L.leafI < L.leafEnd) return;
+    smPop2(L, stack);
+}
+
+template <bool SHADOW, bool COUNT>
+__device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt, bool canRefill) {
+    while (true) {
+        const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
+        const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
+        const uint32_t mWork = mNode | mLeaf;
+        if (!mWork || (canRefill && __popc(mWork) <= 32 - NORI_REFILL_MIN)) return;
+        if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
+            if (L.st == ST_LEAF) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+        } else {
+            if (L.st == ST_NODE) smNode2<COUNT>(sc, L, stack, cnt);
+        }
+    }
+}
+
+template <bool L2>
 __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 d, float mint, float maxt) {
     L.neg = sc.ordered ? ((d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u)) : 0u;
-    if (travInit(sc, L.r, o, d, mint, maxt)) L.st = ST_NODE;
-    else { L.r.found = false; L.st = ST_DONE; }                  // decided before the first node: a miss
+    if (!travInit(sc, L.r, o, d, mint, maxt)) { L.r.found = false; L.st = ST_DONE; return; }   // decided before the first node: a miss
+    L.st = ST_NODE;
+    if (L2) {                                                    // the root's own box (bvh.cpp:421-423 on node 0)
+        L.cur = sc.root_ref;
+        float nearT;
+        if (!boxTest(L.r, make_float3(sc.root_min[0], sc.root_min[1], sc.root_min[2]), make_float3(sc.root_max[0], sc.root_max[1], sc.root_max[2]), nearT)) L.st = ST_DONE;
+    }
 }
 
 // node phase for one lane
@@ -166,21 +287,11 @@ __device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack 
             const uint32_t farC = swap ? r.node + 1 : n0.y;
             stack.push(r.sp++, farC);
             r.node = swap ? n0.y : r.node + 1;
-#if NORI_PREFETCH
-            // the far child is fetched many steps from now (after the near subtree): start pulling its line
-            // towards L2 so that the pop finds it there instead of paying a DRAM round trip in lockstep
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes[2 * farC]));
-#endif
             return;
         }
         const uint32_t size = n0.x >> 1;
         if (size) {
             L.st = ST_LEAF; L.leafI = n0.y; L.leafEnd = n0.y + size;
-#if NORI_PREFETCH
-            // the lane now waits for NORI_LEAF_MIN lanes to reach a leaf: pull its primitive records meanwhile
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.prims[3 * n0.y]));
-            if (size > 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.prims[3 * n0.y + 8]));
-#endif
             return;
         }
     }
@@ -240,7 +351,7 @@ __device__ __forceinline__ bool smNextChunk(uint32_t *work, uint32_t P, uint32_t
     return base < P;
 }
 
-template <bool COUNT, bool VOL>
+template <bool COUNT, bool VOL, bool L2>
 __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
@@ -252,9 +363,10 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    __shared__ uint32_t s_stack[NORI_SM_STACK][128];
-    LaneStack stack; stack.sh = &s_stack[0][threadIdx.x];
-    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0;
+    __shared__ uint2 s_stack_mem[(L2 ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
+    LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
+    LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
+    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0; L.cur = 0;
     uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
     bool moreChunks = true;
     while (true) {
@@ -322,14 +434,14 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
                 if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
                     const float4 ro = pool.rayO[s], rd = pool.rayD[s];
                     L.slot = s; ++nRays;
-                    smStart(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
+                    smStart<L2>(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
                 }
             }
             idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
+        if (L2) smRun2<false, COUNT>(sc, L, stack2, cnt, canRefill); else smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
@@ -339,14 +451,15 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
 // Any-hit traversal (bvh.cpp:441-442) of the NEE rays k_shade<.., DEFER> left in the pool, same warp
 // state machine as k_extend_sm.  Adds the pending contribution when the ray is unoccluded
 // (path_mis.cpp:48-61) and finalises the paths the roulette ended.
-template <bool COUNT>
+template <bool COUNT, bool L2>
 __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     const uint32_t lane = threadIdx.x & 31, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    __shared__ uint32_t s_stack[NORI_SM_STACK][128];
-    LaneStack stack; stack.sh = &s_stack[0][threadIdx.x];
-    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0;
+    __shared__ uint2 s_stack_mem[(L2 ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
+    LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
+    LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
+    LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0; L.cur = 0;
     uint32_t flags = 0;
     uint32_t chunkBase = 0, chunkNext = NORI_FETCH;
     bool moreChunks = true;
@@ -380,7 +493,7 @@ __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Bat
                     if (f & PF_SHADOW) {
                         const float4 so = pool.rayO[s], sd = pool.shD[s];
                         L.slot = s; flags = f; ++nRays;
-                        smStart(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
+                        smStart<L2>(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
                     }
                 }
             }
@@ -388,24 +501,29 @@ __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Bat
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
+        if (L2) smRun2<true, COUNT>(sc, L, stack2, cnt, canRefill); else smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
 
-void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    if (count) k_shadow_sm<true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shadow_sm<false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+template <bool COUNT, bool L2> static void launchShadowSm(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    k_shadow_sm<COUNT, L2><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
 }
-int noriShadowSmOccupancy(bool count) {
+void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    const bool l2 = sc.ordered && sc.nodes2;
+    if (count) { if (l2) launchShadowSm<true, true>(grid, st, sc, pool, bt, ctr, it); else launchShadowSm<true, false>(grid, st, sc, pool, bt, ctr, it); }
+    else { if (l2) launchShadowSm<false, true>(grid, st, sc, pool, bt, ctr, it); else launchShadowSm<false, false>(grid, st, sc, pool, bt, ctr, it); }
+}
+int noriShadowSmOccupancy(bool count, bool l2) {
     int occ = 8;
-    if (count) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false>, 128, 0);
+    if (count) { if (l2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true, true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true, false>, 128, 0); }
+    else { if (l2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false, true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false, false>, 128, 0); }
     return occ;
 }
 
-ExtendKernel noriPickExtend(bool sm, bool count, bool vol) {
-    if (sm) return count ? (vol ? k_extend_sm<true, true> : k_extend_sm<true, false>) : (vol ? k_extend_sm<false, true> : k_extend_sm<false, false>);
+ExtendKernel noriPickExtend(bool sm, bool count, bool vol, bool l2) {
+    if (sm && l2) return count ? (vol ? k_extend_sm<true, true, true> : k_extend_sm<true, false, true>) : (vol ? k_extend_sm<false, true, true> : k_extend_sm<false, false, true>);
+    if (sm) return count ? (vol ? k_extend_sm<true, true, false> : k_extend_sm<true, false, false>) : (vol ? k_extend_sm<false, true, false> : k_extend_sm<false, false, false>);
     return count ? (vol ? k_extend<true, true> : k_extend<true, false>) : (vol ? k_extend<false, true> : k_extend<false, false>);
 }

@@ -62,6 +62,9 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
 // microfacet | disney | [volumetric: misses]) and work item i belongs to the queue whose range contains
 // it, so warps are material-coherent except where a boundary falls inside one.
+#ifndef NORI_SHADE_DIFFUSE_COPY
+#define NORI_SHADE_DIFFUSE_COPY 0
+#endif
 #ifndef NORI_SHADE_TEMPLATED
 #define NORI_SHADE_TEMPLATED 0
 #endif
@@ -93,6 +96,9 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
         for (int t = 1; t < NORI_NQ; ++t) q += i >= off[t];
         const uint32_t slot = pool.queue[q][i - off[q]];
         if (MODE == MODE_VOL && q == NORI_Q_MISS) shadeSlot<NORI_Q_MISS, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+#if NORI_SHADE_DIFFUSE_COPY
+        else if (q == NORI_BSDF_DIFFUSE) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+#endif
         else shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
 #endif
     }
