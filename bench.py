@@ -36,6 +36,46 @@ WIDTH, HEIGHT, SPP = 800, 600, 1024
 WORKLOAD = "cornell-box(pa4/cbox) path_mis 800x600 @1024spp per GPU"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch at the bench's pool size)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p)).get(kernel)
+        if t:
+            return float(t["dram_bytes_per_launch"])
+    return None
+
+
+def large_scene_probe(g, host_scene, peak):
+    """BASELINE config 4 (10M-triangle height field, path_mis, 3840x2160): a short supplementary measurement of
+    the large-scene kernels -- here the scene (0.7 GB) is far larger than L2, so the HBM fraction is a real one.
+    Untimed extra of rank 0; NOT part of `value`."""
+    import time as _t
+    t0 = _t.perf_counter()
+    sc = host_scene.heightfield_scene(n=2237)
+    build_s = _t.perf_counter() - t0
+    g.upload_scene(sc)
+    g.set_option("pool", 1 << 22)
+    g.render(0, 2, seed=1)
+    g.set_option("stats", 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); kc = g.kernel_stats(); g.set_option("stats", 0)
+    g.set_option("kernel_timing", 1); g.reset_stats(); g.clear_film(); g.render(0, 8, seed=1)
+    st, ks = g.stats(), g.kernel_stats()
+    g.set_option("kernel_timing", 0)
+    out = {"workload": "10M-triangle height field (9,999,392 triangles, reference-identical SAH tree) path_mis 3840x2160 @8spp",
+           "msamples_per_s": st.samples / st.render_ms / 1e3, "mrays_per_s": st.rays / st.render_ms / 1e3,
+           "ms": st.render_ms, "scene_build_s": build_s, "kernel_ms": {k: v["ms"] for k, v in ks.items() if v["ms"]},
+           "traversal": "near-child-first order on the child-box node layout (option order=2 auto)"}
+    for k in ("extend", "shadow"):
+        c, t = kc[k], ks[k]
+        if c["rays"] and t["ms"]:
+            b = 32.0 * c["nodes"] / c["rays"] + 48.0 * c["prims"] / c["rays"] + 48.0
+            ach = t["rays"] * b / (t["ms"] * 1e-3) / 1e9
+            out[f"k_{k}_sm"] = {"boxes_per_ray": c["nodes"] / c["rays"], "prims_per_ray": c["prims"] / c["rays"], "bytes_per_ray": b,
+                                "grays_per_s": t["rays"] / t["ms"] / 1e6, "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak}
+    return out
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -145,6 +185,7 @@ def main():
     ap.add_argument("--pool", type=int, default=1 << 22)
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one bounded reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-scene", action="store_true", help="skip the supplementary 10M-triangle measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -154,7 +195,7 @@ def main():
     import torch.distributed as dist
     from __graft_entry__ import import_package
     import_package()
-    from nori_ray_tracer_b200 import nscene, render
+    from nori_ray_tracer_b200 import host_scene, nscene, render
     from nori_ray_tracer_b200.gpu import NoriGpu
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -218,14 +259,22 @@ def main():
     scene_bytes = sum(int(a.nbytes) for k, a in sc.entries.items() if not k.startswith(("rays", "seq", "probe")))
     barrier()
     e0 = time.perf_counter()
+    parts = {"upload": 0.0, "render": 0.0, "reduce": 0.0, "download": 0.0}
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         g.upload_scene(sc)                                   # H2D of every scene array (also clears the film)
+        t1 = time.perf_counter()
         g.render(begin, spp, seed=0)
+        t2 = time.perf_counter()
         if world > 1:
             film_t = torch.as_tensor(g.film_device_array(), device=f"cuda:{local}")
             dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
             torch.cuda.synchronize()
+        t3 = time.perf_counter()
         g.download_film(host_film)                           # D2H of the (H+2b)x(W+2b)x4 accumulation buffer
+        t4 = time.perf_counter()
+        for k, v in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            parts[k] += 1e3 * v / args.steps
     barrier()
     e2e_s = (time.perf_counter() - e0) / args.steps
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
@@ -254,7 +303,7 @@ def main():
         peak, peak_src = measured_peak()
         achieved = k["rays"] * b_ray / max(k["ms"] * 1e-3, 1e-12) / 1e9
         roofline = {"bound": "hbm", "kernel": f"k_{trace_dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": measured_traffic(f"k_{trace_dom}"), "peak_source": peak_src,
                     "bytes_per_ray": b_ray, "rays_per_launch": k["rays"] / max(k["launches"], 1),
                     "avg_launch_ms": k["ms"] / max(k["launches"], 1), "kernel_ms_per_step": kernel_ms,
                     "note": "scene (14 primitives, <2 KB) is L1/L2-resident: HBM fraction is small by construction; "
@@ -273,8 +322,14 @@ def main():
                 "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes,
-                        "d2h_bytes_per_step": int(host_film.nbytes)},
+                        "d2h_bytes_per_step": int(host_film.nbytes), "ms_per_step": 1e3 * e2e_s,
+                        "host_ms_breakdown": {k: round(v, 3) for k, v in parts.items()}},
                 "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+        if world == 1 and not args.no_large_scene:
+            try:
+                line["large_scene"] = large_scene_probe(g, host_scene, peak)
+            except Exception as e:                                   # supplementary: never fail the headline line
+                line["large_scene"] = {"error": str(e)[:200]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
