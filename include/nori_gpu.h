@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NORI_GPU_ABI_VERSION 1
+#define NORI_GPU_ABI_VERSION 2
 #define NORI_FILTER_RESOLUTION 32          /* include/nori/rfilter.h:25 */
 #define NORI_BLOCK_SIZE 32                 /* include/nori/block.h:30   */
 
@@ -33,11 +33,21 @@ enum { NORI_SHAPE_MESH = 0, NORI_SHAPE_SPHERE = 1 };                     /* src/
 enum { NORI_BSDF_DIFFUSE = 0, NORI_BSDF_MIRROR = 1, NORI_BSDF_DIELECTRIC = 2,
        NORI_BSDF_MICROFACET = 3, NORI_BSDF_DISNEY = 4, NORI_BSDF_COUNT = 5 };
 enum { NORI_EMITTER_AREA = 0, NORI_EMITTER_POINT = 1, NORI_EMITTER_SPOT = 2, NORI_EMITTER_ENVMAP = 3 };
-enum { NORI_CAMERA_PERSPECTIVE = 0, NORI_CAMERA_THINLENS = 1 };
+enum { NORI_CAMERA_PERSPECTIVE = 0, NORI_CAMERA_THINLENS = 1, NORI_CAMERA_ADVANCED = 2 };   /* src/advancedCamera.cpp */
 enum { NORI_INTEGRATOR_NORMALS = 0, NORI_INTEGRATOR_PATH_MIS = 1, NORI_INTEGRATOR_PATH_MATS = 2,
        NORI_INTEGRATOR_DIRECT_EMS = 3, NORI_INTEGRATOR_DIRECT_MATS = 4, NORI_INTEGRATOR_DIRECT_MIS = 5,
        NORI_INTEGRATOR_DIRECT = 6, NORI_INTEGRATOR_AV = 7, NORI_INTEGRATOR_VOLUMETRIC = 8 };
-enum { NORI_TEXTURE_CONSTANT = 0, NORI_TEXTURE_CHECKERBOARD = 1 };
+enum { NORI_TEXTURE_CONSTANT = 0, NORI_TEXTURE_CHECKERBOARD = 1, NORI_TEXTURE_IMAGE = 2 };      /* src/imagetexture.cpp */
+enum { NORI_WRAP_REPEAT = 0, NORI_WRAP_CLAMP = 1 };                      /* common.h:273-283 */
+
+/* ---- 8-bit RGB images: ImageTexture::m_data / NormalMap::m_data as stbi_load(.., STBI_rgb) returns
+ *      them (imagetexture.cpp:73-87, normalmap.cpp:73-87): texel (x, y) at rgb[(x + width*y)*3] ------ */
+typedef struct {
+    int32_t width, height;
+    int32_t wrap;               /* NORI_WRAP_*                                               */
+    int32_t reserved;
+    const uint8_t *rgb;
+} nori_gpu_image;
 
 /* ---- BVH: the reference's 32-byte node, verbatim (include/nori/bvh.h:127-164) ------------ *
  * data[0]: bit 0 = leaf flag, bits 1..31 = leaf size (leaf) or split axis (inner, unused)
@@ -55,7 +65,7 @@ typedef struct {
     int32_t  emitter;           /* index into scene.emitters, or -1 (Shape::isEmitter)       */
     uint32_t n_vertices;        /* mesh: columns of m_V                                      */
     uint32_t n_triangles;       /* mesh: columns of m_F; sphere: 1 primitive                 */
-    uint32_t reserved;
+    int32_t  normal_map;        /* 1 + index into scene.images of the mesh's NormalMap (shape.cpp:59-66), 0 = none */
     const float    *V;          /* 3*n_vertices, column-major m_V: vertex i = V[3i..3i+2]    */
     const float    *N;          /* 3*n_vertices or NULL (m_N)                                */
     const float    *UV;         /* 2*n_vertices or NULL (m_UV)                               */
@@ -81,7 +91,8 @@ typedef struct {
     float   ks;                 /* microfacet.cpp:48 : 1 - max(kd)                           */
     float   baseColor[3];       /* disney.cpp:57                                             */
     float   metallic, specular, roughness, sheen, sheenTint, specularTint; /* disney.cpp:50-55 */
-    float   reserved[2];
+    int32_t albedo_image;       /* NORI_TEXTURE_IMAGE: index into scene.images               */
+    float   reserved;
 } nori_gpu_bsdf;
 
 /* ---- emitters (src/arealight.cpp, pointlight.cpp, spotlight.cpp, envmap.cpp) ------------- */
@@ -112,6 +123,10 @@ typedef struct {
     float   invOutputSize[2];
     float   nearClip, farClip;
     float   lensRadius, focalDistance;   /* thinlens.cpp:49-50                               */
+    float   distortion[2];      /* advancedCamera.cpp:54: radial distortion coefficients     */
+    float   chromatic[3];       /* advancedCamera.cpp:55: per-channel chromatic aberration strength; non-zero =>
+                                   three camera paths per sample, one per colour channel (render.cpp:106-121) */
+    float   reserved;
 } nori_gpu_camera;
 
 /* ---- reconstruction filter, pre-tabulated by the host exactly as ImageBlock::init does
@@ -145,6 +160,9 @@ typedef struct {
     nori_gpu_camera camera;
     nori_gpu_filter filter;
     nori_gpu_medium medium;
+    uint32_t n_images;
+    uint32_t reserved;
+    const nori_gpu_image *images;          /* image textures and normal maps                 */
 } nori_gpu_scene;
 
 /* ---- test hooks ---------------------------------------------------------------------------- */

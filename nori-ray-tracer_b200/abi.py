@@ -2,18 +2,19 @@
 must match the header exactly; tests/test_abi.py checks every sizeof against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FILTER_RESOLUTION = 32
 BLOCK_SIZE = 32
 
 SHAPE_MESH, SHAPE_SPHERE = 0, 1
 BSDF_DIFFUSE, BSDF_MIRROR, BSDF_DIELECTRIC, BSDF_MICROFACET, BSDF_DISNEY = range(5)
 EMITTER_AREA, EMITTER_POINT, EMITTER_SPOT, EMITTER_ENVMAP = range(4)
-CAMERA_PERSPECTIVE, CAMERA_THINLENS = 0, 1
+CAMERA_PERSPECTIVE, CAMERA_THINLENS, CAMERA_ADVANCED = 0, 1, 2
 (INTEGRATOR_NORMALS, INTEGRATOR_PATH_MIS, INTEGRATOR_PATH_MATS, INTEGRATOR_DIRECT_EMS,
  INTEGRATOR_DIRECT_MATS, INTEGRATOR_DIRECT_MIS, INTEGRATOR_DIRECT, INTEGRATOR_AV,
  INTEGRATOR_VOLUMETRIC) = range(9)
-TEXTURE_CONSTANT, TEXTURE_CHECKERBOARD = 0, 1
+TEXTURE_CONSTANT, TEXTURE_CHECKERBOARD, TEXTURE_IMAGE = 0, 1, 2
+WRAP_REPEAT, WRAP_CLAMP = 0, 1
 
 INTEGRATOR_NAMES = {
     "normals": INTEGRATOR_NORMALS, "path_mis": INTEGRATOR_PATH_MIS, "path_mats": INTEGRATOR_PATH_MATS,
@@ -32,7 +33,7 @@ class BvhNode(C.Structure):
 
 class Shape(C.Structure):
     _fields_ = [("type", i32), ("bsdf", i32), ("emitter", i32), ("n_vertices", u32),
-                ("n_triangles", u32), ("reserved", u32),
+                ("n_triangles", u32), ("normal_map", i32),
                 ("V", pf32), ("N", pf32), ("UV", pf32), ("F", pu32), ("area_cdf", pf32),
                 ("area_normalization", f32), ("center", f32 * 3), ("radius", f32),
                 ("reserved2", u32 * 3)]
@@ -43,7 +44,7 @@ class Bsdf(C.Structure):
                 ("tex_scale", f32 * 2), ("tex_delta", f32 * 2), ("intIOR", f32), ("extIOR", f32),
                 ("alpha", f32), ("kd", f32 * 3), ("ks", f32), ("baseColor", f32 * 3),
                 ("metallic", f32), ("specular", f32), ("roughness", f32), ("sheen", f32),
-                ("sheenTint", f32), ("specularTint", f32), ("reserved", f32 * 2)]
+                ("sheenTint", f32), ("specularTint", f32), ("albedo_image", i32), ("reserved", f32)]
 
 
 class Emitter(C.Structure):
@@ -57,7 +58,12 @@ class Emitter(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("type", i32), ("width", i32), ("height", i32), ("sampleToCamera", f32 * 16),
                 ("cameraToWorld", f32 * 16), ("invOutputSize", f32 * 2), ("nearClip", f32),
-                ("farClip", f32), ("lensRadius", f32), ("focalDistance", f32)]
+                ("farClip", f32), ("lensRadius", f32), ("focalDistance", f32),
+                ("distortion", f32 * 2), ("chromatic", f32 * 3), ("reserved", f32)]
+
+
+class Image(C.Structure):
+    _fields_ = [("width", i32), ("height", i32), ("wrap", i32), ("reserved", i32), ("rgb", C.POINTER(C.c_uint8))]
 
 
 class Filter(C.Structure):
@@ -75,7 +81,8 @@ class Scene(C.Structure):
                 ("nodes", C.POINTER(BvhNode)), ("indices", pu32), ("shape_offset", pu32),
                 ("shapes", C.POINTER(Shape)), ("bsdfs", C.POINTER(Bsdf)),
                 ("emitters", C.POINTER(Emitter)),
-                ("camera", Camera), ("filter", Filter), ("medium", Medium)]
+                ("camera", Camera), ("filter", Filter), ("medium", Medium),
+                ("n_images", u32), ("reserved", u32), ("images", C.POINTER(Image))]
 
 
 class Ray(C.Structure):

@@ -153,9 +153,10 @@ __global__ void k_probe_bsdf(DScene sc, uint32_t bsdf, unsigned long long n, con
     if (i >= n) return;
     const nori_gpu_bsdf &b = sc.bsdfs[bsdf];
     const float *q = &in[10 * i]; float *o = &out[12 * i];
-    BRec e; e.wi = mk(q[0], q[1], q[2]); e.wo = mk(q[3], q[4], q[5]); e.measure = M_SOLID_ANGLE; e.uv.x = q[6]; e.uv.y = q[7];
+    P2 uv; uv.x = q[6]; uv.y = q[7];
+    BRec e = mkBRec(sc, b, mk(q[0], q[1], q[2]), M_SOLID_ANGLE, uv); e.wo = mk(q[3], q[4], q[5]);
     V3 ev = bsdfEvalDyn(b, e); float pdf = bsdfPdfDyn(b, e);
-    BRec r; r.wi = e.wi; r.measure = M_UNKNOWN; r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
+    BRec r = mkBRec(sc, b, e.wi, M_UNKNOWN, uv); P2 s; s.x = q[8]; s.y = q[9];
     V3 w = bsdfSampleDyn(b, r, s); float pdf2 = bsdfPdfDyn(b, r);
     o[0] = ev.x; o[1] = ev.y; o[2] = ev.z; o[3] = pdf; o[4] = w.x; o[5] = w.y; o[6] = w.z;
     o[7] = r.wo.x; o[8] = r.wo.y; o[9] = r.wo.z; o[10] = (float) r.measure; o[11] = pdf2;

@@ -7,7 +7,8 @@
 #define NORI_Q_MISS NORI_BSDF_COUNT          // volumetric only: rays that left the scene may still scatter in the medium
 #define NORI_NQ (NORI_BSDF_COUNT + 1)
 
-enum { PF_ALIVE = 1u, PF_SHADOW = 2u, PF_TERMINATE = 4u, PF_FIRST = 8u, PF_DISCRETE = 16u };
+enum { PF_ALIVE = 1u, PF_SHADOW = 2u, PF_TERMINATE = 4u, PF_FIRST = 8u, PF_DISCRETE = 16u,
+       PF_CH_SHIFT = 8u, PF_CH_MASK = 3u << 8 };     // colour channel of the current camera path (chromatic aberration)
 
 struct PathState {
     V3 o, d;            // current ray (origin is the previous vertex: path_mis.cpp:83 `origin`)
@@ -63,7 +64,7 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
         float pdf_em = emitterPdf(sc, light, e);
         V3 woLocal = toLocal(its.sh, e.wi);
         float theta = fmaxf(0.0f, woLocal.z);
-        BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv = its.uv;
+        BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, its.uv); b.wo = woLocal;
         V3 f = evalT<BSDF>(bsdf, b);
         float pdf_mat = pdfT<BSDF>(bsdf, b);
         float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
@@ -76,7 +77,7 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
     if (st.rng.next1D() > p) { st.flags = flags | PF_TERMINATE; return; }
     st.thr = st.thr / p;
 
-    BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv = its.uv;  // path_mis.cpp:72-81
+    BRec b = mkBRec(sc, bsdf, wiLocal, M_UNKNOWN, its.uv);          // path_mis.cpp:72-81
     V3 w = sampleT<BSDF>(bsdf, b, st.rng.next2D());
     st.thr = st.thr * w;
     out.next = mkray(its.p, toWorld(its.sh, b.wo));
@@ -141,7 +142,7 @@ __device__ V3 liDirect(const DScene &sc, Pcg32 &rng, const Ray &ray, int kind, R
             float pdf_em = kind == NORI_INTEGRATOR_DIRECT_MIS ? emitterPdf(sc, light, e) : 0.f;
             if (!anyHit<COUNT>(sc, e.shadow, rs)) {
                 V3 wi = toLocal(its.sh, e.wi);
-                BRec b; b.measure = M_SOLID_ANGLE; b.uv = its.uv;
+                BRec b = mkBRec(sc, bsdf, wi, M_SOLID_ANGLE, its.uv);
                 if (kind == NORI_INTEGRATOR_DIRECT) { b.wi = wi; b.wo = dLocal; } else { b.wi = dLocal; b.wo = wi; }
                 V3 f = bsdfEvalDyn(bsdf, b);
                 if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
@@ -153,7 +154,7 @@ __device__ V3 liDirect(const DScene &sc, Pcg32 &rng, const Ray &ray, int kind, R
         }
     }
     if (kind == NORI_INTEGRATOR_DIRECT_MATS || kind == NORI_INTEGRATOR_DIRECT_MIS) {
-        BRec b; b.wi = dLocal; b.measure = M_UNKNOWN; b.uv = its.uv;
+        BRec b = mkBRec(sc, bsdf, dLocal, M_UNKNOWN, its.uv);
         V3 w = bsdfSampleDyn(bsdf, b, rng.next2D());
         float pdf_mat = kind == NORI_INTEGRATOR_DIRECT_MIS ? bsdfPdfDyn(bsdf, b) : 0.f;
         Ray nr = mkray(its.p, toWorld(its.sh, b.wo));
@@ -298,7 +299,8 @@ __device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, Path
             float pdf_em = emitterPdf(sc, light, e);
             V3 woLocal = toLocal(its.sh, e.wi);
             float theta = fmaxf(0.0f, woLocal.z);
-            BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv.x = 0.f; b.uv.y = 0.f;   // uv not set, :103
+            P2 uv0; uv0.x = 0.f; uv0.y = 0.f;                       // bRec.uv is not set (volumetric.cpp:103): Point2f() = 0
+            BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
             V3 f = evalT<BSDF>(bsdf, b);
             float pdf_mat = pdfT<BSDF>(bsdf, b);
             float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
@@ -307,7 +309,8 @@ __device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, Path
         float p = fminf(st.thr.x, 0.80f);
         if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
         st.thr = st.thr / p;
-        BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv.x = 0.f; b.uv.y = 0.f;
+        P2 uv1; uv1.x = 0.f; uv1.y = 0.f;
+        BRec b = mkBRec(sc, bsdf, wiLocal, M_UNKNOWN, uv1);
         V3 w = sampleT<BSDF>(bsdf, b, st.rng.next2D());
         st.thr = st.thr * w;
         st.pdf_mat = pdfT<BSDF>(bsdf, b);
@@ -366,7 +369,8 @@ __device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) 
                 float pdf_em = emitterPdf(sc, light, e);
                 V3 woLocal = toLocal(its.sh, e.wi);
                 float theta = fmaxf(0.0f, woLocal.z);
-                BRec b; b.wi = wiLocal; b.wo = woLocal; b.measure = M_SOLID_ANGLE; b.uv.x = 0.f; b.uv.y = 0.f;   // uv not set, :103
+                P2 uv0; uv0.x = 0.f; uv0.y = 0.f;                       // bRec.uv is not set (volumetric.cpp:103): Point2f() = 0
+            BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
                 V3 f = bsdfEvalDyn(bsdf, b);
                 float pdf_mat = bsdfPdfDyn(bsdf, b);
                 float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
@@ -375,7 +379,8 @@ __device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) 
             float p = fminf(att.x, 0.80f);
             if (rng.next1D() > p) return color;
             att = att / p;
-            BRec b; b.wi = wiLocal; b.measure = M_UNKNOWN; b.uv.x = 0.f; b.uv.y = 0.f;
+            P2 uv1; uv1.x = 0.f; uv1.y = 0.f;
+        BRec b = mkBRec(sc, bsdf, wiLocal, M_UNKNOWN, uv1);
             V3 w = bsdfSampleDyn(bsdf, b, rng.next2D());
             att = att * w;
             float pdf_mat = bsdfPdfDyn(bsdf, b);

@@ -25,6 +25,7 @@ struct Pool {
     float4 *hit;              // (t, u, v, leafpos): the 16-byte hit record
     float4 *thr;              // (throughput rgb, pdf_mat)
     float4 *rad;              // (radiance rgb, -)
+    float4 *acc;              // chromatic aberration only: value accumulated over the colour channels already traced
     float4 *shD, *shC;        // deferred NEE shadow ray (large scenes only): (direction, maxt) -- origin = rayO, mint = Epsilon --
                               // and its pending contribution; NULL when shadow rays are traced inside k_shade
     uint64_t *rng;            // pcg32 state (inc is a function of the pixel)
@@ -64,8 +65,9 @@ __device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uin
 
 // ------------------------------------------------------------------------------ raygen (device function)
 // One iteration of renderBlock's loop head (render.cpp:98-124): seed the path's pcg32 stream, draw the
-// film and aperture samples, build the camera ray.
-__device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, uint32_t sid, Ray &ray, uint64_t &rngState) {
+// film and aperture samples, build the camera ray (of colour channel `channel` when the camera has
+// chromatic aberration, render.cpp:106-121).
+__device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, uint32_t sid, int channel, Ray &ray, uint64_t &rngState) {
     const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
     const int W = sc.camera.width;
     const int py = pix / W, px = pix - py * W;
@@ -73,8 +75,39 @@ __device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, 
     P2 a = rng.next2D();
     P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
     P2 ap = rng.next2D();
-    ray = cameraRay(sc.camera, ps, ap);
+    V3 weight;
+    ray = cameraRay(sc.camera, ps, ap, channel, weight);
     rngState = rng.state;
+}
+
+// A camera path has ended with radiance `rad`.  Normally that is the sample's value.  With chromatic
+// aberration one sample is THREE paths, one per colour channel, traced one after the other on the same
+// random stream and summed with the camera's per-channel weights (render.cpp:106-121,
+// advancedCamera.cpp:176-183): the slot is restarted in place with the next channel's camera ray
+// (same film / aperture sample, re-derived from the stream's seed) until the third path has ended.
+__device__ __forceinline__ void endOfPath(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
+                                          uint32_t sid, V3 rad, uint64_t rngState, uint32_t flags, uint32_t &nDone) {
+    if (hasChromaticAberrations(sc.camera)) {
+        const int ch = (int) ((flags & PF_CH_MASK) >> PF_CH_SHIFT);
+        const V3 w = mk(ch == 0 ? 1.f : 0.f, ch == 1 ? 1.f : 0.f, ch == 2 ? 1.f : 0.f);
+        V3 acc = w * rad;                                          // value_ch = sampleRay(...) * Li
+        if (ch > 0) { const float4 a = pool.acc[slot]; acc = mk(a.x, a.y, a.z) + acc; }
+        if (ch < 2) {
+            Ray ray; uint64_t unused;
+            generatePath(sc, bt, sid, ch + 1, ray, unused);
+            pool.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.f);
+            pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+            pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+            pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+            pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pool.rng[slot] = rngState;                              // the sampler carries on where this path stopped
+            pool.flags[slot] = PF_ALIVE | PF_FIRST | ((uint32_t) (ch + 1) << PF_CH_SHIFT);
+            return;
+        }
+        rad = acc;
+    }
+    finalizePath(bt, ctr, sid, rad);
+    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
 }
 
 enum { MODE_MATS = 0, MODE_MIS = 1, MODE_VOL = 2 };

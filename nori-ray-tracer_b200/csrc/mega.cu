@@ -16,8 +16,18 @@ __global__ void __launch_bounds__(128) k_mega(DScene sc, Batch bt, Counters *ctr
         P2 a = rng.next2D();
         P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
         P2 ap = rng.next2D();
-        Ray ray = cameraRay(sc.camera, ps, ap);
-        V3 L = liDispatch<COUNT>(sc, rng, ray, rs);
+        V3 L, weight;
+        if (hasChromaticAberrations(sc.camera)) {                  // render.cpp:106-121: one path per colour channel
+            L = mk(0.f);
+            for (int ch = 0; ch < 3; ++ch) {
+                Ray ray = cameraRay(sc.camera, ps, ap, ch, weight);
+                V3 v = weight * liDispatch<COUNT>(sc, rng, ray, rs);
+                L = ch == 0 ? v : L + v;
+            }
+        } else {
+            Ray ray = cameraRay(sc.camera, ps, ap, -1, weight);
+            L = liDispatch<COUNT>(sc, rng, ray, rs);
+        }
         finalizePath(bt, ctr, sid, L);
     }
     warpAdd(&ctr->rays_ext, rs.rays - rs.shadow); warpAdd(&ctr->rays_sh, rs.shadow);

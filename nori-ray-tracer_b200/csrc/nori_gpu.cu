@@ -127,7 +127,7 @@ const char *nori_gpu_last_error(const nori_gpu_ctx *ctx) { return ctx ? ctx->err
 int nori_gpu_abi_sizes(uint32_t *out, int n) {
     const uint32_t s[] = {sizeof(nori_gpu_bvh_node), sizeof(nori_gpu_shape), sizeof(nori_gpu_bsdf), sizeof(nori_gpu_emitter),
                           sizeof(nori_gpu_camera), sizeof(nori_gpu_filter), sizeof(nori_gpu_medium), sizeof(nori_gpu_scene),
-                          sizeof(nori_gpu_ray), sizeof(nori_gpu_hit), sizeof(nori_gpu_stats)};
+                          sizeof(nori_gpu_ray), sizeof(nori_gpu_hit), sizeof(nori_gpu_stats), sizeof(nori_gpu_image)};
     int m = (int) (sizeof(s) / sizeof(s[0]));
     for (int i = 0; i < n && i < m; ++i) out[i] = s[i];
     return m;
@@ -172,6 +172,8 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     REQUIRE(s->abi_version == NORI_GPU_ABI_VERSION, "upload_scene: ABI version mismatch");
     REQUIRE(s->integrator >= 0 && s->integrator <= NORI_INTEGRATOR_VOLUMETRIC, "upload_scene: unknown integrator");
     REQUIRE(s->camera.width > 0 && s->camera.height > 0, "upload_scene: empty film");
+    REQUIRE(s->camera.type >= 0 && s->camera.type <= NORI_CAMERA_ADVANCED, "upload_scene: unknown camera type");
+    REQUIRE(s->n_images == 0 || s->images, "upload_scene: null image table");
     REQUIRE(s->filter.radius > 0.f && s->filter.radius <= 8.f, "upload_scene: filter radius must be in (0, 8]");
     REQUIRE(s->n_shapes == 0 || (s->nodes && s->indices && s->shape_offset && s->shapes && s->bsdfs), "upload_scene: null scene arrays");
     REQUIRE(s->integrator != NORI_INTEGRATOR_VOLUMETRIC || s->medium.present, "upload_scene: volumetric integrator needs a medium");
@@ -186,6 +188,21 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     ds.ordered = 0;
     ds.integrator = s->integrator; ds.av_length = s->av_length; ds.camera = s->camera; ds.medium = s->medium;
 
+    // ---- image textures / normal maps
+    std::vector<DImage> images(s->n_images);
+    for (uint32_t i = 0; i < s->n_images; ++i) {
+        const nori_gpu_image &h = s->images[i];
+        REQUIRE(h.width > 0 && h.height > 0 && h.rgb, "upload_scene: empty image");
+        REQUIRE(h.wrap == NORI_WRAP_REPEAT || h.wrap == NORI_WRAP_CLAMP, "upload_scene: unknown image wrap mode");
+        images[i].width = h.width; images[i].height = h.height; images[i].wrap = h.wrap; images[i].pad = 0;
+        if (devUpload(ctx, ctx->scene_allocs, h.rgb, (size_t) h.width * h.height * 3, &images[i].rgb)) return 1;
+    }
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
+        const nori_gpu_bsdf &b = s->bsdfs[i];
+        REQUIRE(b.albedo_texture >= NORI_TEXTURE_CONSTANT && b.albedo_texture <= NORI_TEXTURE_IMAGE, "upload_scene: unknown texture type");
+        REQUIRE(b.albedo_texture != NORI_TEXTURE_IMAGE || (b.albedo_image >= 0 && (uint32_t) b.albedo_image < s->n_images),
+                "upload_scene: BSDF references a missing image");
+    }
     // ---- per-shape arrays + shape table
     std::vector<DShape> shapes(s->n_shapes);
     uint32_t mask = 0;
@@ -197,6 +214,8 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
         d.type = h.type; d.bsdf = h.bsdf; d.emitter = h.emitter; d.bsdf_type = s->bsdfs[h.bsdf].type;
         REQUIRE(d.bsdf_type >= 0 && d.bsdf_type < NORI_BSDF_COUNT, "upload_scene: unknown BSDF type");
         mask |= 1u << d.bsdf_type;
+        REQUIRE(h.normal_map >= 0 && (uint32_t) h.normal_map <= s->n_images, "upload_scene: shape references a missing normal map");
+        d.normal_map = h.normal_map;
         d.n_triangles = h.n_triangles; d.area_normalization = h.area_normalization;
         d.cx = h.center[0]; d.cy = h.center[1]; d.cz = h.center[2]; d.radius = h.radius;
         if (h.type == NORI_SHAPE_MESH) {
@@ -304,6 +323,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     if (devUpload(ctx, ctx->scene_allocs, shapes.data(), shapes.size(), &ds.shapes)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, s->bsdfs, (size_t) s->n_bsdfs, &ds.bsdfs)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, ems.data(), ems.size(), &ds.emitters)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, images.data(), images.size(), &ds.images)) return 1;
     CK(cudaStreamSynchronize(ctx->stream));         // host staging vectors die at return
 
     ctx->ds = ds; ctx->filter = s->filter; ctx->bsdf_mask = mask; ctx->n_bsdfs = s->n_bsdfs;
@@ -321,13 +341,16 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
 } // extern "C"
 
 static int ensurePool(nori_gpu_ctx *ctx, bool deferShadow) {
-    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty() && (!deferShadow || ctx->pool.shD)) return 0;
+    const nori_gpu_camera &cam = ctx->ds.camera;
+    const bool chroma = cam.type == NORI_CAMERA_ADVANCED && !(cam.chromatic[0] == 0.f && cam.chromatic[1] == 0.f && cam.chromatic[2] == 0.f);
+    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty() && (!deferShadow || ctx->pool.shD) && (!chroma || ctx->pool.acc)) return 0;
     freeAll(ctx->pool_allocs);
     Pool p{}; p.P = (uint32_t) ctx->opt_pool;
     auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
-    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shD, &p.shC};
+    float4 **f4[] = {&p.rayO, &p.rayD, &p.hit, &p.thr, &p.rad, &p.shD, &p.shC, &p.acc};
     for (auto pp : f4) {
-        if (!deferShadow && (pp == &p.shD || pp == &p.shC)) continue; *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
+        if (!deferShadow && (pp == &p.shD || pp == &p.shC)) continue;
+        if (!chroma && pp == &p.acc) continue; *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
     for (int t = 0; t < NORI_NQ; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }

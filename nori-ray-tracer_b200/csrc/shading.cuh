@@ -29,6 +29,32 @@ __device__ __forceinline__ Frame makeFrame(V3 a) {
 __device__ __forceinline__ V3 toLocal(const Frame &f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }
 __device__ __forceinline__ V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }
 
+// ImageTexture::getData / NormalMap::getData (imagetexture.cpp:98-116, normalmap.cpp:98-120): the texel at the
+// truncated coordinates, wrapped with C's % (repeat) or clamped.  A negative remainder reads in front of the
+// array in the reference (undefined behaviour); here it is wrapped into range.
+__device__ __forceinline__ V3 imageTexel(const DImage &im, float xf, float yf) {
+    int x, y;
+    if (im.wrap == NORI_WRAP_REPEAT) {
+        x = (int) xf % im.width; y = (int) yf % im.height;
+        if (x < 0) x += im.width;
+        if (y < 0) y += im.height;
+    } else {
+        x = min(max((int) xf, 0), im.width - 1); y = min(max((int) yf, 0), im.height - 1);
+    }
+    const uint8_t *t = &im.rgb[((size_t) x + (size_t) im.width * y) * 3];
+    return mk((float) __ldg(t) / 255.f, (float) __ldg(t + 1) / 255.f, (float) __ldg(t + 2) / 255.f);
+}
+// ImageTexture::eval / NormalMap::eval (imagetexture.cpp:118-136, normalmap.cpp:122-139).  In the reference
+// `x` is the un-floored float uv.x * width, so dstdx = uv.x * width - x is exactly 0 and the "bilinear" blend
+// 1*1*v00 + 1*0*v01 + 0*1*v10 + 0*0*v11 is the texel at the truncated coordinates, bit for bit (the other
+// three texels are finite 8-bit values times zero).  NORMAL applies normalmap.cpp:115-119 (2c - 1).
+template <bool NORMAL>
+__device__ __forceinline__ V3 imageEval(const DImage &im, P2 uv) {
+    V3 c = imageTexel(im, uv.x * (float) im.width, uv.y * (float) im.height);
+    if (NORMAL) c = mk(2.0f * c.x - 1.0f, 2.0f * c.y - 1.0f, 2.0f * c.z - 1.0f);
+    return c;
+}
+
 // mesh.cpp:122-170, sphere.cpp:78-93
 __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit &h, Its &its) {
     const float4 r0 = __ldg(&sc.prims[3 * h.leafpos]);
@@ -51,6 +77,8 @@ __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit 
         if (m.has_n) n = normalizedDyn((b0 * ld3(&m.N[3 * i0]) + b1 * ld3(&m.N[3 * i1])) + b2 * ld3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         its.sh = makeFrame(n);
+        if (m.has_n && m.normal_map > 0)                          // mesh.cpp:149-154
+            its.sh = makeFrame(toWorld(its.sh, normalized(imageEval<true>(sc.images[m.normal_map - 1], its.uv))));
     } else {
         const V3 c = mk(r0.x, r0.y, r0.z);
         its.p = o + h.t * d;
@@ -114,9 +142,10 @@ __device__ __forceinline__ float tanTheta(V3 v) { float t = 1 - v.z * v.z; if (t
 
 // ------------------------------------------------------------------------------ BSDFs
 enum { M_UNKNOWN = 0, M_SOLID_ANGLE = 1, M_DISCRETE = 2 };
-struct BRec { V3 wi, wo; int measure; P2 uv; };                  // bsdf.h:30-58
+struct BRec { V3 wi, wo; int measure; P2 uv; V3 albedo; };       // bsdf.h:30-58; albedo = m_albedo->eval(uv), looked up once per vertex
 
-__device__ __forceinline__ V3 albedoAt(const nori_gpu_bsdf &b, P2 uv) {
+__device__ __forceinline__ V3 albedoAt(const DScene &sc, const nori_gpu_bsdf &b, P2 uv) {
+    if (b.albedo_texture == NORI_TEXTURE_IMAGE) return imageEval<false>(sc.images[b.albedo_image], uv);   // imagetexture.cpp:118-136
     if (b.albedo_texture == NORI_TEXTURE_CHECKERBOARD) {          // checkerboard.cpp:31-37
         int x = (int) fabsf(floorf(uv.x / b.tex_scale[0] - b.tex_delta[0]));
         int y = (int) fabsf(floorf(uv.y / b.tex_scale[1] - b.tex_delta[1]));
@@ -148,7 +177,7 @@ template <int TYPE>
 __device__ __forceinline__ V3 bsdfEval(const nori_gpu_bsdf &b, const BRec &r) {
     if (TYPE == NORI_BSDF_DIFFUSE) {                              // diffuse.cpp:72-82
         if (r.measure != M_SOLID_ANGLE || r.wi.z <= 0 || r.wo.z <= 0) return mk(0.f);
-        return albedoAt(b, r.uv) * NORI_INV_PI;
+        return r.albedo * NORI_INV_PI;
     } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:84-94
         V3 n = normalized(r.wi + r.wo);
         float D = evalBeckmann(b.alpha, n);
@@ -202,6 +231,14 @@ __device__ __forceinline__ float bsdfPdf(const nori_gpu_bsdf &b, const BRec &r) 
     return 0.0f;
 }
 
+// BSDFQueryRecord for a surface vertex: the diffuse albedo texture (constant / checkerboard / image) is evaluated
+// here, once, instead of inside every eval / sample call (it is a pure function of uv)
+__device__ __forceinline__ BRec mkBRec(const DScene &sc, const nori_gpu_bsdf &bsdf, V3 wi, int measure, P2 uv) {
+    BRec b; b.wi = wi; b.wo = mk(0.f); b.measure = measure; b.uv = uv;
+    b.albedo = bsdf.type == NORI_BSDF_DIFFUSE ? albedoAt(sc, bsdf, uv) : mk(0.f);
+    return b;
+}
+
 // returns the importance weight; on failure wo stays (0,0,0) like the reference's zero-filled
 // TVector (vector.h:49), which makes the next ray miss everything
 template <int TYPE>
@@ -210,7 +247,7 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
     if (TYPE == NORI_BSDF_DIFFUSE) {                              // diffuse.cpp:104-120
         if (r.wi.z <= 0) return mk(0.f);
         r.measure = M_SOLID_ANGLE; r.wo = squareToCosineHemisphere(s);
-        return albedoAt(b, r.uv);
+        return r.albedo;
     } else if (TYPE == NORI_BSDF_MIRROR) {                        // mirror.cpp:39-55
         if (r.wi.z <= 0) return mk(0.f);
         r.wo = mk(-r.wi.x, -r.wi.y, r.wi.z); r.measure = M_DISCRETE;
@@ -463,12 +500,61 @@ __device__ __forceinline__ V3 xfPoint(const float *m, V3 p) {                // 
 __device__ __forceinline__ V3 xfVector(const float *m, V3 v) {               // transform.h:68-70
     return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
 }
-// perspective.cpp:90-112, thinlens.cpp:126-171
-__device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as) {
+__device__ __forceinline__ P2 squareToUniformDisk(P2 s) {                    // warp.cpp:53-58
+    float angle = 2 * s.x * NORI_PI, size = sqrtf(s.y);
+    P2 r; r.x = cosf(angle) * size; r.y = sinf(angle) * size; return r;
+}
+__device__ __forceinline__ bool hasChromaticAberrations(const nori_gpu_camera &c) {   // advancedCamera.cpp:230-232
+    return c.type == NORI_CAMERA_ADVANCED && !(c.chromatic[0] == 0.f && c.chromatic[1] == 0.f && c.chromatic[2] == 0.f);
+}
+// perspective.cpp:90-112, thinlens.cpp:126-171, advancedCamera.cpp:133-228.  `weight` is the camera's importance
+// weight: Color3f(1), or the unit colour of `channel` when chromatic aberration is on (advancedCamera.cpp:176-183).
+__device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as, int channel, V3 &weight) {
     V3 nearP = xfPoint(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
     V3 d = normalized(nearP);
-    float invZ = 1.0f / d.z;
+    weight = mk(1.f);
     Ray ray;
+    if (c.type == NORI_CAMERA_ADVANCED) {
+        const bool chroma = hasChromaticAberrations(c);
+        if (!(c.distortion[0] == 0.f && c.distortion[1] == 0.f)) {           // advancedCamera.cpp:145-170
+            const float qx = nearP.x / nearP.z, qy = nearP.y / nearP.z;
+            const float y = sqrtf(qx * qx + qy * qy);
+            float r = y, r2, f, df; int i = 0;
+            while (true) {
+                r2 = r * r;
+                f = r * (1 + (c.distortion[0] * r2) + c.distortion[1] * (r2 * r2)) - y;
+                df = 1 + (3 * c.distortion[0] * r2) + (5 * c.distortion[1] * r2 * r2);
+                r = r - f / df;
+                if ((double) fabsf(f) < 1e-6 || i++ > 4) break;
+            }
+            const float distortionFactor = r / y;
+            nearP.x *= distortionFactor; nearP.y *= distortionFactor;
+            d = normalized(nearP);
+        }
+        float w = 0.0f;
+        if (chroma) { w = c.chromatic[channel]; weight = mk(channel == 0 ? 1.f : 0.f, channel == 1 ? 1.f : 0.f, channel == 2 ? 1.f : 0.f); }
+        const float invZ = 1.0f / d.z;
+        if (c.lensRadius > 0.0f || chroma) {                                  // advancedCamera.cpp:192-216
+            P2 disk = squareToUniformDisk(as);
+            float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
+            float ft = c.focalDistance / d.z;
+            V3 pFocus = mk(0.f) + ft * d;
+            float spx = ps.x - (0.5f * (float) c.width), spy = ps.y - (0.5f * (float) c.height);
+            const float mx = (float) max(c.width, c.height);
+            spx /= mx; spy /= mx;
+            const float sq = spx * spx + spy * spy;
+            const float dx = spx * sq * w, dy = spy * sq * w;
+            pFocus = pFocus + mk(-dx, dy, 0.0f);
+            V3 o = mk(lx, ly, 0.0f);
+            V3 dir = normalized(pFocus - o);
+            ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+        } else {
+            ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
+        }
+        ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
+        return ray;
+    }
+    float invZ = 1.0f / d.z;
     if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
         P2 disk = squareToConcentricDisk(as);
         float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;

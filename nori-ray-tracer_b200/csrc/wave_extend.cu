@@ -26,8 +26,7 @@ __device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, cons
         }
     }
     const float4 r = pool.rad[slot];
-    finalizePath(bt, ctr, pool.sid[slot], mk(r.x, r.y, r.z));
-    pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
+    endOfPath(sc, pool, bt, ctr, slot, pool.sid[slot], mk(r.x, r.y, r.z), pool.rng[slot], pool.flags[slot], nDone);
     return -1;
 }
 
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
                 if (id >= total) break;                          // batch exhausted: the slot stays free
                 const uint32_t slot = freeList[j];
                 Ray ray; uint64_t rs;
-                generatePath(sc, bt, (uint32_t) id, ray, rs);
+                generatePath(sc, bt, (uint32_t) id, 0, ray, rs);
                 pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
                 pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
                 pool.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
                         if (id >= total) break;
                         const uint32_t s = freeList[j];
                         Ray ray; uint64_t rs;
-                        generatePath(sc, bt, (uint32_t) id, ray, rs);
+                        generatePath(sc, bt, (uint32_t) id, 0, ray, rs);
                         pool.rayO[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
                         pool.rayD[s] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
                         pool.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
@@ -468,10 +467,8 @@ __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Bat
             L.st = ST_IDLE;
             float4 ra = pool.rad[L.slot];
             if (!L.r.found) { const float4 c = pool.shC[L.slot]; ra.x = __fadd_rn(ra.x, c.x); ra.y = __fadd_rn(ra.y, c.y); ra.z = __fadd_rn(ra.z, c.z); }
-            if (flags & PF_TERMINATE) {
-                finalizePath(bt, ctr, pool.sid[L.slot], mk(ra.x, ra.y, ra.z));
-                pool.sid[L.slot] = NORI_FREE_SLOT; pool.flags[L.slot] = 0; ++nDone;
-            } else {
+            if (flags & PF_TERMINATE) endOfPath(sc, pool, bt, ctr, L.slot, pool.sid[L.slot], mk(ra.x, ra.y, ra.z), pool.rng[L.slot], flags, nDone);
+            else {
                 if (!L.r.found) pool.rad[L.slot] = ra;
                 pool.flags[L.slot] = flags & ~PF_SHADOW;
             }

@@ -22,6 +22,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
     st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
     st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
     st.flags = pool.flags[slot];
+    const uint32_t chBits = st.flags & PF_CH_MASK;
     st.rng.state = pool.rng[slot]; st.rng.inc = ((uint64_t) (sid % bt.wh) << 1u) | 1u;
     Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
     Ray next;
@@ -36,7 +37,8 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
             if (!(st.flags & PF_ALIVE)) {                           // the roulette ended the path: k_shadow_sm finalises it
                 pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
                 if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
-                pool.flags[slot] = PF_SHADOW | PF_TERMINATE;
+                pool.rng[slot] = st.rng.state;
+                pool.flags[slot] = PF_SHADOW | PF_TERMINATE | chBits;
                 return;
             }
         } else if (MODE == MODE_MIS) {                              // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
@@ -52,11 +54,8 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
         pool.thr[slot] = make_float4(st.thr.x, st.thr.y, st.thr.z, st.pdf_mat);
         pool.rng[slot] = st.rng.state;
         if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
-        pool.flags[slot] = st.flags & (PF_ALIVE | PF_DISCRETE | (DEFER ? PF_SHADOW : 0u));
-    } else {                                                    // Russian roulette ended the path
-        finalizePath(bt, ctr, sid, st.rad);
-        pool.sid[slot] = NORI_FREE_SLOT; pool.flags[slot] = 0u; ++nDone;
-    }
+        pool.flags[slot] = (st.flags & (PF_ALIVE | PF_DISCRETE | (DEFER ? PF_SHADOW : 0u))) | chBits;
+    } else endOfPath(sc, pool, bt, ctr, slot, sid, st.rad, st.rng.state, chBits, nDone);   // Russian roulette ended the path
 }
 
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |

@@ -68,7 +68,7 @@ class SceneData:
         self.entries = entries
         e = entries
         hdr = e["header"]
-        if int(hdr[0]) != abi.ABI_VERSION:
+        if int(hdr[0]) not in (1, abi.ABI_VERSION):           # version-1 containers lack images and the advanced camera fields
             raise ValueError("ABI version mismatch in .nscene")
         self.sample_count = int(hdr[2])
         self.nodes = np.ascontiguousarray(e["bvh.nodes"], dtype=np.uint32)
@@ -101,8 +101,22 @@ class SceneData:
                     arr = np.ascontiguousarray(arr, dtype=np.float32)
                     self._keep.append(arr)
                 setattr(em, field, _ptr(arr, C.c_float))
+        # image textures / normal maps: "image.<i>.rgb" (H, W, 3) u8 + "image.<i>.wrap" (1,) i32
+        n_images = 0
+        while f"image.{n_images}.rgb" in e:
+            n_images += 1
+        self.images = (abi.Image * max(n_images, 1))()
+        for i in range(n_images):
+            rgb = np.ascontiguousarray(e[f"image.{i}.rgb"], dtype=np.uint8)
+            self._keep.append(rgb)
+            im = self.images[i]
+            im.height, im.width = rgb.shape[0], rgb.shape[1]
+            im.wrap = int(e[f"image.{i}.wrap"][0])
+            im.rgb = rgb.ctypes.data_as(C.POINTER(C.c_uint8))
         pod = abi.Scene()
         pod.abi_version = abi.ABI_VERSION
+        pod.n_images = n_images
+        pod.images = C.cast(self.images, C.POINTER(abi.Image))
         pod.integrator = int(hdr[1])
         pod.av_length = float(e["av_length"][0])
         pod.n_nodes = self.nodes.shape[0]
@@ -114,7 +128,7 @@ class SceneData:
         pod.shapes = C.cast(self.shapes, C.POINTER(abi.Shape))
         pod.bsdfs = C.cast(self.bsdfs, C.POINTER(abi.Bsdf))
         pod.emitters = C.cast(self.emitters, C.POINTER(abi.Emitter))
-        pod.camera = abi.Camera.from_buffer_copy(e["camera.pod"].tobytes())
+        pod.camera = abi.Camera.from_buffer_copy(e["camera.pod"].tobytes().ljust(C.sizeof(abi.Camera), b"\0"))
         pod.filter = abi.Filter.from_buffer_copy(e["filter.pod"].tobytes())
         pod.medium = abi.Medium.from_buffer_copy(e["medium.pod"].tobytes())
         self.pod = pod

@@ -117,8 +117,10 @@ struct Emitter {
     nori_gpu_emitter pod;
     std::vector<float> image, pdf, cdf, pm, cm;
 };
+struct Image { int w = 0, h = 0, wrap = 0; std::vector<uint8_t> rgb; };
 struct Scene {
     nori_gpu_scene pod;
+    std::vector<Image> images;
     std::vector<nori_gpu_bvh_node> nodes; std::vector<uint32_t> indices, shapeOffset;
     std::vector<Shape> shapes; std::vector<nori_gpu_bsdf> bsdfs; std::vector<Emitter> emitters;
     int border = 0; float lookupFactor = 0;
@@ -214,6 +216,32 @@ inline uint32_t findShape(const Scene &sc, uint32_t &idx) {
     return (uint32_t) (it - sc.shapeOffset.begin());
 }
 
+/* ImageTexture::getData / NormalMap::getData (imagetexture.cpp:98-116, normalmap.cpp:98-120): the texel at
+ * the truncated coordinates, wrapped with C's % (Repeat) or clamped.  A negative remainder indexes in
+ * front of the array in the reference (undefined behaviour); here it is wrapped into range instead. */
+inline V3 imageTexel(const Image &im, float xf, float yf) {
+    int x, y;
+    if (im.wrap == NORI_WRAP_REPEAT) {
+        x = (int) xf % im.w; y = (int) yf % im.h;
+        if (x < 0) x += im.w;
+        if (y < 0) y += im.h;
+    } else {
+        x = std::min(std::max((int) xf, 0), im.w - 1); y = std::min(std::max((int) yf, 0), im.h - 1);
+    }
+    const uint8_t *t = &im.rgb[((size_t) x + (size_t) im.w * y) * 3];
+    return V3((float) t[0] / 255, (float) t[1] / 255, (float) t[2] / 255);
+}
+/* ImageTexture::eval / NormalMap::eval (imagetexture.cpp:118-136, normalmap.cpp:122-139).  `x` is a float,
+ * not a floor, so dstdx = uv.x * w - x is exactly 0 and the "bilinear" blend is 1*1*v00 + 1*0*v01 +
+ * 0*1*v10 + 0*0*v11: the value of the texel at the truncated coordinates.  The blend is evaluated as
+ * written so that the result is bit-identical (0 * finite terms, added in the same order). */
+template <typename F> inline V3 imageEval(const Image &im, P2 uv, F map) {
+    float x = uv.x * im.w, y = uv.y * im.h;
+    V3 v00 = map(imageTexel(im, x, y)), v01 = map(imageTexel(im, x, y + 1.0f)), v10 = map(imageTexel(im, x + 1.0f, y)), v11 = map(imageTexel(im, x + 1.0f, y + 1.0f));
+    float dstdx = uv.x * im.w - x, dstdy = uv.y * im.h - y;
+    return (((1.0f - dstdx) * (1.0f - dstdy) * v00 + (1.0f - dstdx) * dstdy * v01) + dstdx * (1.0f - dstdy) * v10) + dstdx * dstdy * v11;
+}
+
 /* mesh.cpp:122-170, sphere.cpp:78-93 */
 void setHitInformation(const Scene &sc, const Ray &ray, Its &its) {
     const Shape &m = sc.shapes[its.shape];
@@ -231,6 +259,11 @@ void setHitInformation(const Scene &sc, const Ray &ray, Its &its) {
         if (!m.N.empty()) {
             V3 n = (b0 * load3(&m.N[3 * i0]) + b1 * load3(&m.N[3 * i1])) + b2 * load3(&m.N[3 * i2]);
             its.sh = makeFrame(normalizedDyn(n));
+            if (m.pod.normal_map > 0) {                                        /* mesh.cpp:149-154 */
+                V3 nm = imageEval(sc.images[m.pod.normal_map - 1], its.uv,
+                                  [](V3 c) { return V3(2.0f * c.x - 1.0f, 2.0f * c.y - 1.0f, 2.0f * c.z - 1.0f); });   /* normalmap.cpp:115-119 */
+                its.sh = makeFrame(toWorld(its.sh, normalized(nm)));
+            }
         } else its.sh = its.geo;
     } else {
         /* by now ray.maxt == its.t (bvh.cpp:444) */
@@ -356,9 +389,12 @@ inline float tanTheta(V3 v) { float temp = 1 - v.z * v.z; if (temp <= 0.0f) retu
 
 /* ------------------------------------------------------------------ BSDFs ---------------------- */
 enum Measure { EUnknown = 0, ESolidAngle = 1, EDiscrete = 2 };
-struct BRec { V3 wi, wo; float eta = 0; int measure = EUnknown; P2 uv; };     /* bsdf.h:30-58 */
+struct BRec { V3 wi, wo; float eta = 0; int measure = EUnknown; P2 uv; const Scene *scene = nullptr; };     /* bsdf.h:30-58 (+ the texture table) */
 
-inline V3 albedoAt(const nori_gpu_bsdf &b, P2 uv) {
+inline V3 albedoAt(const nori_gpu_bsdf &b, const BRec &r) {
+    const P2 uv = r.uv;
+    if (b.albedo_texture == NORI_TEXTURE_IMAGE)                                /* imagetexture.cpp:118-136 */
+        return imageEval(r.scene->images[b.albedo_image], uv, [](V3 c) { return c; });
     if (b.albedo_texture == NORI_TEXTURE_CHECKERBOARD) {                      /* checkerboard.cpp:31-37 */
         int x = (int) std::abs(std::floor(uv.x / b.tex_scale[0] - b.tex_delta[0]));
         int y = (int) std::abs(std::floor(uv.y / b.tex_scale[1] - b.tex_delta[1]));
@@ -392,7 +428,7 @@ V3 bsdfEval(const nori_gpu_bsdf &b, const BRec &r) {
     switch (b.type) {
     case NORI_BSDF_DIFFUSE:                                                   /* diffuse.cpp:72-82 */
         if (r.measure != ESolidAngle || r.wi.z <= 0 || r.wo.z <= 0) return V3(0.f);
-        return albedoAt(b, r.uv) * kInvPi;
+        return albedoAt(b, r) * kInvPi;
     case NORI_BSDF_MICROFACET: {                                              /* microfacet.cpp:84-94 */
         V3 n = normalized(r.wi + r.wo);
         float D = evalBeckmann(b.alpha, n);
@@ -455,7 +491,7 @@ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) {
     case NORI_BSDF_DIFFUSE:                                                   /* diffuse.cpp:104-120 */
         if (r.wi.z <= 0) return V3(0.f);
         r.measure = ESolidAngle; r.wo = squareToCosineHemisphere(s); r.eta = 1.0f;
-        return albedoAt(b, r.uv);
+        return albedoAt(b, r);
     case NORI_BSDF_MIRROR:                                                    /* mirror.cpp:39-55 */
         if (r.wi.z <= 0) return V3(0.f);
         r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z); r.measure = EDiscrete; r.eta = 1.0f;
@@ -657,10 +693,62 @@ inline V3 xfVector(const float *m, V3 v) {                                    /*
     return V3((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
 }
 
-/* perspective.cpp:90-112, thinlens.cpp:126-171 */
-void sampleRay(const nori_gpu_camera &c, Ray &ray, P2 ps, P2 as) {
+/* warp.cpp:53-58 (M_PI is the reference's float literal; unqualified cos/sin/sqrt pick the float overloads,
+ * as in squareToConcentricDisk above, which is pinned bit-exact) */
+inline P2 squareToUniformDisk(P2 sample) {
+    float angle = 2 * sample.x * kPi;
+    float size = std::sqrt(sample.y);
+    P2 r; r.x = std::cos(angle) * size; r.y = std::sin(angle) * size; return r;
+}
+
+/* perspective.cpp:90-112, thinlens.cpp:126-171, advancedCamera.cpp:133-228.  Returns the camera weight:
+ * Color3f(1), or the unit vector of `channel` when chromatic aberration is on (advancedCamera.cpp:176-183). */
+V3 sampleRay(const nori_gpu_camera &c, Ray &ray, P2 ps, P2 as, int channel = -1) {
     V3 nearP = xfPoint(c.sampleToCamera, V3(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
     V3 d = normalized(nearP);
+    V3 weight(1.0f);
+    if (c.type == NORI_CAMERA_ADVANCED) {
+        const bool distort = !(c.distortion[0] == 0.f && c.distortion[1] == 0.f);
+        const bool chroma = !(c.chromatic[0] == 0.f && c.chromatic[1] == 0.f && c.chromatic[2] == 0.f);
+        if (distort) {                                                        /* advancedCamera.cpp:145-170 */
+            float qx = nearP.x / nearP.z, qy = nearP.y / nearP.z;
+            float y = std::sqrt(qx * qx + qy * qy);
+            float r = y, r2, f, df; int i = 0;
+            while (true) {
+                r2 = r * r;
+                f = r * (1 + (c.distortion[0] * r2) + c.distortion[1] * (r2 * r2)) - y;
+                df = 1 + (3 * c.distortion[0] * r2) + (5 * c.distortion[1] * r2 * r2);
+                r = r - f / df;
+                if ((double) std::abs(f) < 1e-6 || i++ > 4) break;             /* F_EPSILON is a double literal */
+            }
+            float distortionFactor = r / y;
+            nearP.x *= distortionFactor; nearP.y *= distortionFactor;
+            d = normalized(nearP);
+        }
+        float w = 0.0f;
+        if (chroma) { w = c.chromatic[channel]; weight = V3(channel == 0 ? 1.f : 0.f, channel == 1 ? 1.f : 0.f, channel == 2 ? 1.f : 0.f); }
+        float invZ = 1.0f / d.z;
+        if (c.lensRadius > 0.0f || chroma) {                                  /* advancedCamera.cpp:192-216 */
+            P2 disk = squareToUniformDisk(as);
+            float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
+            float ft = c.focalDistance / d.z;
+            V3 pFocus = V3(0.f) + ft * d;
+            float spx = ps.x - (0.5f * c.width), spy = ps.y - (0.5f * c.height);
+            float mx = (float) std::max(c.width, c.height);
+            spx /= mx; spy /= mx;
+            float sq = spx * spx + spy * spy;
+            float dx = spx * sq * w, dy = spy * sq * w;
+            pFocus = pFocus + V3(-dx, dy, 0.0f);
+            V3 o(lx, ly, 0.0f);
+            V3 dir = normalized(pFocus - o);
+            ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+        } else {
+            ray.o = xfPoint(c.cameraToWorld, V3(0, 0, 0)); ray.d = xfVector(c.cameraToWorld, d);
+        }
+        ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
+        ray.update();
+        return weight;
+    }
     float invZ = 1.0f / d.z;
     if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
         P2 disk = squareToConcentricDisk(as);
@@ -675,6 +763,10 @@ void sampleRay(const nori_gpu_camera &c, Ray &ray, P2 ps, P2 as) {
     }
     ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
     ray.update();
+    return weight;
+}
+inline bool hasChromaticAberrations(const nori_gpu_camera &c) {              /* advancedCamera.cpp:230-232 */
+    return c.type == NORI_CAMERA_ADVANCED && !(c.chromatic[0] == 0.f && c.chromatic[1] == 0.f && c.chromatic[2] == 0.f);
 }
 
 /* ------------------------------------------------------------------ integrators ---------------- */
@@ -701,7 +793,7 @@ V3 LiPathMis(Scene &sc, Pcg32 &rng, const Ray &ray) {                         /*
         float pdf_em = emitterPdf(sc, light, e);
         if (!occluded(sc, e.shadowRay)) {
             float theta = std::max(0.0f, toLocal(its.sh, e.wi).z);
-            BRec b; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle; b.uv = its.uv;
+            BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle; b.uv = its.uv;
             V3 f = bsdfEval(bsdfOf(sc, its), b);
             float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
             float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
@@ -710,7 +802,7 @@ V3 LiPathMis(Scene &sc, Pcg32 &rng, const Ray &ray) {                         /*
         float p = std::min(att.x, 0.99f);
         if (rng.next1D() > p) return color;
         att = att / p;
-        BRec b; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
+        BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
         V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
         att = att * w;
         cur = Ray(its.p, toWorld(its.sh, b.wo));
@@ -738,7 +830,7 @@ V3 LiPathMats(Scene &sc, Pcg32 &rng, const Ray &ray) {                        /*
         float p = std::min(att.x, 0.99f);
         if (rng.next1D() > p) return color;
         att = att / p;
-        BRec b; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
+        BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -cur.d); b.uv = its.uv;
         V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
         att = att * w;
         cur = Ray(its.p, toWorld(its.sh, b.wo));
@@ -761,7 +853,7 @@ V3 LiDirect(Scene &sc, Pcg32 &rng, const Ray &ray, int kind) {
             float pdf_em = kind == NORI_INTEGRATOR_DIRECT_MIS ? emitterPdf(sc, light, e) : 0.f;
             if (!occluded(sc, e.shadowRay)) {
                 V3 wi = toLocal(its.sh, e.wi), d = toLocal(its.sh, -ray.d);
-                BRec b; b.measure = ESolidAngle; b.uv = its.uv;
+                BRec b; b.scene = &sc; b.measure = ESolidAngle; b.uv = its.uv;
                 if (kind == NORI_INTEGRATOR_DIRECT) { b.wi = wi; b.wo = d; } else { b.wi = d; b.wo = wi; }
                 V3 f = bsdfEval(bsdfOf(sc, its), b);
                 if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
@@ -773,7 +865,7 @@ V3 LiDirect(Scene &sc, Pcg32 &rng, const Ray &ray, int kind) {
         }
     }
     if (kind == NORI_INTEGRATOR_DIRECT_MATS || kind == NORI_INTEGRATOR_DIRECT_MIS) {   /* direct_mats.cpp:33-43, direct_mis.cpp:62-83 */
-        BRec b; b.wi = toLocal(its.sh, -ray.d); b.uv = its.uv;
+        BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -ray.d); b.uv = its.uv;
         V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
         float pdf_mat = kind == NORI_INTEGRATOR_DIRECT_MIS ? bsdfPdf(bsdfOf(sc, its), b) : 0.f;
         Ray nr(its.p, toWorld(its.sh, b.wo)); Its its2;
@@ -886,7 +978,7 @@ V3 LiVolumetric(Scene &sc, Pcg32 &rng, const Ray &ray) {                      /*
             if (!occluded(sc, e.shadowRay)) {
                 float pdf_em = emitterPdf(sc, light, e);
                 float theta = std::max(0.0f, toLocal(its.sh, e.wi).z);
-                BRec b; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle;   /* uv left default, :103 */
+                BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -cur.d); b.wo = toLocal(its.sh, e.wi); b.measure = ESolidAngle;   /* uv left default, :103 */
                 V3 f = bsdfEval(bsdfOf(sc, its), b);
                 float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
                 float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
@@ -895,7 +987,7 @@ V3 LiVolumetric(Scene &sc, Pcg32 &rng, const Ray &ray) {                      /*
             float p = std::min(att.x, 0.80f);
             if (rng.next1D() > p) return color;
             att = att / p;
-            BRec b; b.wi = toLocal(its.sh, -cur.d);
+            BRec b; b.scene = &sc; b.wi = toLocal(its.sh, -cur.d);
             V3 w = bsdfSample(bsdfOf(sc, its), b, rng.next2D());
             att = att * w;
             float pdf_mat = bsdfPdf(bsdfOf(sc, its), b);
@@ -929,8 +1021,16 @@ V3 Li(Scene &sc, Pcg32 &rng, const Ray &ray) {
 inline V3 cameraSample(Scene &sc, Pcg32 &rng, int px, int py, P2 &pixelSample) {
     P2 a = rng.next2D(); pixelSample.x = (float) px + a.x; pixelSample.y = (float) py + a.y;
     P2 aperture = rng.next2D();
-    Ray ray; sampleRay(sc.pod.camera, ray, pixelSample, aperture);
-    return Li(sc, rng, ray);          /* camera weight is Color3f(1) for both cameras */
+    if (hasChromaticAberrations(sc.pod.camera)) {     /* render.cpp:106-121: one path per colour channel, one sampler */
+        V3 value(0.f);
+        for (int ch = 0; ch < 3; ++ch) {
+            Ray rc; V3 wgt = sampleRay(sc.pod.camera, rc, pixelSample, aperture, ch);
+            value += wgt * Li(sc, rng, rc);
+        }
+        return value;
+    }
+    Ray ray; V3 wgt = sampleRay(sc.pod.camera, ray, pixelSample, aperture);
+    return wgt * Li(sc, rng, ray);
 }
 
 inline bool validColor(V3 c) {                                                /* common.cpp:224-231 */
@@ -991,6 +1091,11 @@ void *nori_oracle_create(const nori_gpu_scene *s) {
             e.cm.assign(e.pod.env_cmarginal, e.pod.env_cmarginal + R + 1);
         }
         sc->emitters.push_back(std::move(e));
+    }
+    for (uint32_t i = 0; i < s->n_images; ++i) {
+        Image im; im.w = s->images[i].width; im.h = s->images[i].height; im.wrap = s->images[i].wrap;
+        im.rgb.assign(s->images[i].rgb, s->images[i].rgb + (size_t) im.w * im.h * 3);
+        sc->images.push_back(std::move(im));
     }
     sc->border = (int) std::ceil(s->filter.radius - 0.5f);                    /* block.cpp:57 */
     sc->lookupFactor = NORI_FILTER_RESOLUTION / s->filter.radius;             /* block.cpp:64 */
@@ -1118,9 +1223,9 @@ void nori_oracle_bsdf_probe(void *h, uint32_t bsdf, uint64_t n, const float *in,
     Scene *sc = (Scene *) h; const nori_gpu_bsdf &b = sc->bsdfs[bsdf];
     for (uint64_t i = 0; i < n; ++i) {
         const float *q = &in[10 * i]; float *o = &out[12 * i];
-        BRec e; e.wi = load3(q); e.wo = load3(q + 3); e.measure = ESolidAngle; e.uv.x = q[6]; e.uv.y = q[7];
+        BRec e; e.scene = sc; e.wi = load3(q); e.wo = load3(q + 3); e.measure = ESolidAngle; e.uv.x = q[6]; e.uv.y = q[7];
         V3 ev = bsdfEval(b, e); float pdf = bsdfPdf(b, e);
-        BRec r; r.wi = load3(q); r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
+        BRec r; r.scene = sc; r.wi = load3(q); r.uv = e.uv; P2 s; s.x = q[8]; s.y = q[9];
         V3 w = bsdfSample(b, r, s); float pdf2 = bsdfPdf(b, r);
         o[0] = ev.x; o[1] = ev.y; o[2] = ev.z; o[3] = pdf; o[4] = w.x; o[5] = w.y; o[6] = w.z;
         o[7] = r.wo.x; o[8] = r.wo.y; o[9] = r.wo.z; o[10] = (float) r.measure; o[11] = pdf2;

@@ -33,6 +33,7 @@
 #include <nori/block.h>
 #include <filesystem/resolver.h>
 #include <pcg32.h>
+#include <stb_image.h>
 #include <Eigen/Geometry>
 #include <fstream>
 #include <map>
@@ -133,6 +134,30 @@ static EnvTables buildEnvTables(const PropertyList &props) {
     return t;
 }
 
+/* ------------------------------------------------------------------ image textures ----------- *
+ * ImageTexture / NormalMap are classes local to imagetexture.cpp / normalmap.cpp; both load their file
+ * with stbi_load(path, .., STBI_rgb) (imagetexture.cpp:73-80, normalmap.cpp:73-80).  The exporter loads
+ * the same file with the same call and stores the 8-bit RGB texels verbatim. */
+struct ImageTable {
+    std::vector<std::vector<uint8_t>> rgb; std::vector<int> w, h, wrap;
+    int add(const PropertyList &props, const char *defaultFile) {
+        std::string fn = getFileResolver()->resolve(props.getString("fileName", defaultFile)).str();
+        int wrapMode = wrapTypeFromString(props.getString("wrap", "repeat")) == ImageWrap::Repeat ? NORI_WRAP_REPEAT : NORI_WRAP_CLAMP;
+        int W = 0, H = 0, C = 0;
+        uint8_t *data = stbi_load(fn.c_str(), &W, &H, &C, STBI_rgb);
+        if (!data) throw NoriException("nori_export: cannot load image '%s'", fn);
+        rgb.emplace_back(data, data + (size_t) W * H * 3); stbi_image_free(data);
+        w.push_back(W); h.push_back(H); wrap.push_back(wrapMode);
+        return (int) rgb.size() - 1;
+    }
+    void write(Writer &wr) const {
+        for (size_t i = 0; i < rgb.size(); ++i) {
+            wr.add("image." + std::to_string(i) + ".rgb", 3, {(uint64_t) h[i], (uint64_t) w[i], 3}, rgb[i].data());
+            int32_t wm = wrap[i]; wr.i32("image." + std::to_string(i) + ".wrap", {1}, &wm);
+        }
+    }
+};
+
 /* ------------------------------------------------------------------ traversal replay --------- */
 struct Replay { bool hit; float t, u, v; uint32_t shape, prim, nodes, prims; };
 
@@ -213,6 +238,7 @@ int main(int argc, char **argv) {
         std::vector<nori_gpu_shape> pods(shapes.size());
         std::vector<nori_gpu_bsdf> bsdfs;
         std::map<const BSDF *, int> bsdfIndex;
+        ImageTable images;
         for (size_t s = 0; s < shapes.size(); ++s) {
             nori_gpu_shape &p = pods[s]; memset(&p, 0, sizeof(p));
             const Shape *sh = shapes[s];
@@ -226,7 +252,11 @@ int main(int argc, char **argv) {
                 w.u32(pre + "F", {p.n_triangles, 3}, m->m_F.data());
                 w.f32(pre + "area_cdf", {m->m_pdf.m_cdf.size()}, m->m_pdf.m_cdf.data());
                 p.area_normalization = m->m_pdf.getNormalization();
-                if (sh->m_normalMap) throw NoriException("nori_export: normal maps are outside the hot-path scope (SURVEY 8f)");
+                if (sh->m_normalMap) {                               /* shape.cpp:59-66, used by mesh.cpp:147-155 */
+                    const Created &ni = info(sh->m_normalMap);
+                    if (ni.type != "NormalMap") throw NoriException("nori_export: normal texture '%s' is not supported", ni.type);
+                    p.normal_map = 1 + images.add(ni.props, "textures/default.png");
+                }
             } else if (info(sh).type == "sphere") {
                 p.type = NORI_SHAPE_SPHERE; p.n_triangles = 1;
                 copy3(p.center, info(sh).props.getPoint3("center", Point3f()));
@@ -254,6 +284,9 @@ int main(int argc, char **argv) {
                             copy3(q.albedo2, tex->props.getColor("value2", Color3f(1)));
                             Point2f d = tex->props.getPoint2("delta", Point2f(0)); Vector2f sc = tex->props.getVector2("scale", Vector2f(1));
                             q.tex_delta[0] = d.x(); q.tex_delta[1] = d.y(); q.tex_scale[0] = sc.x(); q.tex_scale[1] = sc.y();
+                        } else if (tex->type == "ImageTexture") {
+                            q.albedo_texture = NORI_TEXTURE_IMAGE;
+                            q.albedo_image = images.add(tex->props, "textures/default.png");
                         } else throw NoriException("nori_export: texture '%s' is outside the hot-path scope (SURVEY 8f)", tex->type);
                     }
                 } else if (bi.type == "mirror") q.type = NORI_BSDF_MIRROR;
@@ -313,6 +346,7 @@ int main(int argc, char **argv) {
         w.bytes("shapes.pod", pods.data(), pods.size() * sizeof(nori_gpu_shape));
         w.bytes("bsdfs.pod", bsdfs.data(), bsdfs.size() * sizeof(nori_gpu_bsdf));
         w.bytes("emitters.pod", ems.data(), ems.size() * sizeof(nori_gpu_emitter));
+        images.write(w);
 
         /* ---- camera: the matrices are private to perspective.cpp / thinlens.cpp, so rebuild them
          *      with the same Eigen expressions (perspective.cpp:53-80) ---- */
@@ -321,6 +355,13 @@ int main(int argc, char **argv) {
         nori_gpu_camera c; memset(&c, 0, sizeof(c));
         if (ci.type == "perspective") c.type = NORI_CAMERA_PERSPECTIVE;
         else if (ci.type == "thinlens") c.type = NORI_CAMERA_THINLENS;
+        else if (ci.type == "advancedCamera") {                       /* advancedCamera.cpp:34-57 */
+            c.type = NORI_CAMERA_ADVANCED;
+            Vector2f dist = ci.props.getVector2("distortion", Vector2f::Zero());
+            Vector3f chroma = ci.props.getVector3("chromaticAberation", Vector3f::Zero());
+            c.distortion[0] = dist.x(); c.distortion[1] = dist.y();
+            c.chromatic[0] = chroma.x(); c.chromatic[1] = chroma.y(); c.chromatic[2] = chroma.z();
+        }
         else throw NoriException("nori_export: camera '%s' is outside the hot-path scope (SURVEY 8f)", ci.type);
         c.width = cam->getOutputSize().x(); c.height = cam->getOutputSize().y();
         Vector2f inv = cam->getOutputSize().cast<float>().cwiseInverse();
@@ -430,9 +471,19 @@ int main(int argc, char **argv) {
                     for (int x = 0; x < bw && done < nSeq; ++x, ++done) {
                         Point2f pixelSample = Point2f((float) x, (float) y) + sampler->next2D();
                         Point2f apertureSample = sampler->next2D();
-                        Ray3f ray;
-                        Color3f value = cam->sampleRay(ray, pixelSample, apertureSample);
-                        value *= scene->getIntegrator()->Li(scene, sampler.get(), ray);
+                        Color3f value(0.0f);
+                        if (cam->hasChromaticAberrations()) {         /* render.cpp:106-121: one path per colour channel */
+                            for (int ch = 0; ch < 3; ++ch) {
+                                Ray3f rc;
+                                Color3f vc = cam->sampleRay(rc, pixelSample, apertureSample, ch);
+                                vc *= scene->getIntegrator()->Li(scene, sampler.get(), rc);
+                                value += vc;
+                            }
+                        } else {
+                            Ray3f ray;
+                            value = cam->sampleRay(ray, pixelSample, apertureSample);
+                            value *= scene->getIntegrator()->Li(scene, sampler.get(), ray);
+                        }
                         seq.insert(seq.end(), {pixelSample.x(), pixelSample.y(), value[0], value[1], value[2]});
                     }
             w.f32("seq", {nSeq, 5}, seq.data());

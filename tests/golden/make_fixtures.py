@@ -72,6 +72,19 @@ FIXTURES = [
          extra='<emitter type="spotlight"><point name="position" value="0,1.5,0.5"/><color name="color" value="30,20,10"/>'
                '<vector name="direction" value="0.2,-1,-0.1"/><float name="falloffStart" value="15"/><float name="totalWidth" value="35"/></emitter>'),
 ]
+# image textures, normal maps, advancedCamera (what scenes/project/final.xml uses)
+FLOOR = '<bsdf type="diffuse">\n\t\t\t<color name="albedo" value=".5,.5,.5"/>\n\t\t</bsdf>'        # the table scene's floor quad
+FIXTURES += [
+    dict(name="table_textured", src="pa4/table/table_path_mis.xml", res=(200, 150), rays=4000, seq=1000, ref_spp=[4, 64], images=True,
+         swap=[(FLOOR, '<texture type="NormalMap" name="normal"><string name="fileName" value="synth_normal.bmp"/><string name="wrap" value="clamp"/></texture>'
+                '<bsdf type="diffuse"><texture type="ImageTexture" name="albedo"><string name="fileName" value="synth_albedo.bmp"/>'
+                '<string name="wrap" value="repeat"/></texture></bsdf>')]),
+    dict(name="cbox_advcam", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 64],
+         camera=("advancedCamera", '<float name="lensRadius" value="0.04"/><float name="focalDist" value="4.6"/>'
+                 '<vector name="chromaticAberation" value="4, 2, 3.3"/><vector name="distortion" value="3, 3"/>')),
+    dict(name="cbox_advcam_distortion", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 64],
+         camera=("advancedCamera", '<vector name="distortion" value="1.7, 1.7"/>')),
+]
 TTESTS = [
     dict(name="ttest_pa4_direct", src="pa4/tests/test-direct.xml"),
     dict(name="ttest_pa4_furnace", src="pa4/tests/test-furnace.xml"),
@@ -101,6 +114,20 @@ def synthetic_envmap(path, rows=64, cols=128, seed=5):
     cv2.imwrite(path, img[..., ::-1], [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT,
                                         cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_NO])
 
+
+
+def synthetic_images(work, w=64, h=48, seed=9):
+    """Small seeded 8-bit images as 24-bit BMP (the reference's stb_image 1.4x reads PNG/JPEG/BMP/TGA): a colourful albedo and a normal map
+    perturbed around +z.  Deliberately non-square so that a width/height swap cannot go unnoticed."""
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    alb = np.stack([128 + 100 * np.sin(x * 0.4), 128 + 100 * np.cos(y * 0.5), 40 + 3 * ((x // 8 + y // 8) % 2) * 60], -1)
+    alb = np.clip(alb + rng.randint(-10, 10, alb.shape), 0, 255).astype(np.uint8)
+    n = np.stack([0.35 * np.sin(x * 0.7), 0.35 * np.cos(y * 0.9), np.ones_like(x, dtype=np.float64)], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    nrm = np.clip((n * 0.5 + 0.5) * 255 + rng.randint(-3, 3, n.shape), 0, 255).astype(np.uint8)
+    for name, img in (("synth_albedo.bmp", alb), ("synth_normal.bmp", nrm)):
+        cv2.imwrite(os.path.join(work, name), np.ascontiguousarray(img[..., ::-1]))
 
 
 def mirror_scene_dir(rel_dir, tmp_root):
@@ -152,6 +179,8 @@ def make_scene_fixture(fx, tmp, meta):
     work = mirror_scene_dir(os.path.dirname(fx["src"]), os.path.join(tmp, name))
     if fx.get("envmap"):
         synthetic_envmap(os.path.join(work, "envmap_synth.exr"))
+    if fx.get("images"):
+        synthetic_images(work)
     src_xml = open(os.path.join(work, os.path.basename(fx["src"]))).read()
     entry = dict(source=fx["src"], res=fx.get("res"), ref_spp=fx["ref_spp"], rays=fx["rays"], seq=fx["seq"])
     first = True

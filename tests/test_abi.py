@@ -32,7 +32,7 @@ def test_struct_sizes_match_compiled_library():
     out = (C.c_uint32 * 16)()
     n = lib.nori_gpu_abi_sizes(out, 16)
     mirror = [abi.BvhNode, abi.Shape, abi.Bsdf, abi.Emitter, abi.Camera, abi.Filter, abi.Medium,
-              abi.Scene, abi.Ray, abi.Hit, abi.Stats]
+              abi.Scene, abi.Ray, abi.Hit, abi.Stats, abi.Image]
     assert n == len(mirror)
     assert [out[i] for i in range(n)] == [C.sizeof(t) for t in mirror]
     assert C.sizeof(abi.BvhNode) == 32          # the reference's BVHNode (bvh.cpp:344)
