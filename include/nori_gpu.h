@@ -228,6 +228,9 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
  * reference's; 1: the child on the ray's side of the node's split axis first -- same hits, same
  * primitive ids incl. the reference's tie rule, fewer node visits; 2 (default): 1 when rendering
  * scenes with more than 4096 primitives, 0 otherwise and always for nori_gpu_trace),
+ * "drain" (finish a batch with one
+ * thread per remaining path once at most this many paths are alive and none is left to start; default
+ * 32768, 0 = never),
  * "shadow_pass" (path_mis NEE rays: 1 their own state-machine pass, 2 inside the shade kernel,
  * 0 (default) by scene size), "traversal" (1 plain per-lane loops, 2 warp state machine, 0 by size). */
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);

@@ -122,4 +122,5 @@ void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc,
 int noriShadowSmOccupancy(bool count, bool childBoxLayout);
 void noriLaunchShadeMis(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchDrain(bool mis, bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr);
 void noriLaunchMega(bool count, unsigned grid, cudaStream_t st, const DScene &sc, const Batch &bt, Counters *ctr, unsigned long long total);

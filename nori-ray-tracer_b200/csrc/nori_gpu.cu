@@ -36,6 +36,7 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
     // 0 reference child order (counters equal the reference's), 1 near child first, 2 auto: near child first when
     // rendering scenes with deep trees, reference order for small scenes and for the nori_gpu_trace test hook
@@ -154,6 +155,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
+    else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
@@ -418,6 +420,14 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
         CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_ctr->done >= total) break;
+        // drain: no camera path left to start and only a few paths alive => finish them in one launch (mega.cu)
+        const unsigned long long live = total - ctx->h_ctr->done;
+        if (mode != MODE_VOL && ctx->opt_drain > 0 && ctx->h_ctr->next_sample >= total && live <= (unsigned long long) ctx->opt_drain) {
+            LAUNCH(NORI_K_SINGLE, noriLaunchDrain(mode == MODE_MIS, count, sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
+            CK(cudaGetLastError());
+            ctx->stats.iterations += 1;
+            break;
+        }
     }
     return 0;
 }

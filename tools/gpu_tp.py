@@ -6,6 +6,8 @@ from nori_ray_tracer_b200 import abi, nscene
 from nori_ray_tracer_b200.gpu import NoriGpu
 sc = nscene.load_scene('tests/golden/cbox_path_mis.nscene'); sc.set_resolution(800, 600)
 g = NoriGpu(0); g.upload_scene(sc)
+import os
+if 'NORI_DRAIN' in os.environ: g.set_option('drain', int(os.environ['NORI_DRAIN']))
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 pools = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1 << 19, 1 << 20, 1 << 21]
 g.render(0, spp, seed=1)
