@@ -249,74 +249,82 @@ static __device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg3
 // of the reference (:76-82, :133-142) is a function of the pdf of the direction that produced the
 // current ray, of whether it came from a discrete BSDF, and of the emitter that was hit -- it is
 // recomputed here from st.pdf_mat / PF_DISCRETE / PF_FIRST with the same expression.
-template <int BSDF, bool COUNT>
+template <bool COUNT>
 __device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, PathState &st, Ray &next,
                                           uint32_t &nClosest, uint32_t &nShadow, TraceCounters &cnt) {
+    // ONE copy of the emitter sampling, of the NEE traversal and of the transmittance serves both vertex
+    // kinds, and the BSDF is reached through the (warp-uniform) type switch: a copy of this body per BSDF type
+    // and per vertex kind made the volumetric k_shade instruction-fetch bound (ncu: 28.7 warps stalled on
+    // `no instruction` per issue, 16 % issue-active).  Random numbers are drawn in the reference's order.
     const nori_gpu_medium &med = sc.medium;
-    constexpr bool intersection = BSDF != NORI_Q_MISS;
+    const bool intersection = hit.leafpos != NORI_NO_HIT;
     const uint32_t inFlags = st.flags;
     Its its;
     float tmax = hit.t;
-    if constexpr (intersection) { hitInfo(sc, st.o, st.d, hit, its); tmax = norm(its.p - st.o); }
+    if (intersection) { hitInfo(sc, st.o, st.d, hit, its); tmax = norm(its.p - st.o); }
     bool hitObject; V3 mp = mk(0.f);
     const Ray cur = mkray(st.o, st.d);
     const V3 sampled = mediumSample(med, cur, st.rng, tmax, hitObject, mp);
-    if (!hitObject) {
-        V3 wo = squareToUniformSphere(st.rng.next2D()); const float pdf_mat = NORI_INV_FOURPI;   // phasefunction.cpp:13-16
-        const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
-        ERec e = makeERec(mp);
-        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
-        st.thr = st.thr * sampled;
-        // a closest-hit query in the reference (volumetric.cpp:63); only its boolean is used, which an
-        // any-hit query answers identically -- the closest-hit form is kept when the counters are on
-        Hit tmp; ++nClosest;
-        if (!traverse<!COUNT, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt))
-            st.rad = st.rad + st.thr * mediumTr(med, mp, e.p) * Li * pdf_mat;
-        float p = fminf(st.thr.x, 0.80f);
-        if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
-        st.thr = st.thr / p;
-        next = mkray(mp, normalized(wo));
-        st.pdf_mat = pdf_mat; st.flags = PF_ALIVE;
-    } else if constexpr (intersection) {
-        const DShape &shp = sc.shapes[its.shape];
-        const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
-        if (shp.emitter >= 0) {
-            const nori_gpu_emitter &em = sc.emitters[shp.emitter].pod;
-            ERec e = makeERec(st.o, its.p, its.sh.n);
+    if (hitObject && !intersection) { st.flags = PF_TERMINATE; return; }   // volumetric.cpp:147-151
+    const bool medium = !hitObject;                                 // medium vertex (:47-87) or surface vertex (:89-145)
+    V3 wo = mk(0.f);
+    const DShape *shp = nullptr; const nori_gpu_bsdf *bsdf = nullptr;
+    if (medium) wo = squareToUniformSphere(st.rng.next2D());        // phasefunction.cpp:13-16, pdf = 1/(4 pi)
+    else {
+        shp = &sc.shapes[its.shape]; bsdf = &sc.bsdfs[shp->bsdf];
+        if (shp->emitter >= 0) {
+            const nori_gpu_emitter &em = sc.emitters[shp->emitter].pod;
+            ERec l = makeERec(st.o, its.p, its.sh.n);
             float w_mats = 1.0f;
             if (!(inFlags & (PF_FIRST | PF_DISCRETE))) {
-                float pdf_em = emitterPdf(sc, em, e);
+                float pdf_em = emitterPdf(sc, em, l);
                 w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
             }
-            st.rad = st.rad + st.thr * w_mats * emitterEval(sc, em, e) * mediumTr(med, its.p, e.p);
+            st.rad = st.rad + st.thr * w_mats * emitterEval(sc, em, l) * mediumTr(med, its.p, l.p);
         }
-        const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
-        ERec e = makeERec(its.p);
-        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
-        const V3 wiLocal = toLocal(its.sh, -st.d);
-        Hit tmp; ++nShadow;
-        if (!traverse<true, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt)) {
+    }
+    const V3 ref = medium ? mp : its.p;
+    const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
+    ERec e = makeERec(ref);
+    V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
+    if (medium) { st.thr = st.thr * sampled; ++nClosest; } else ++nShadow;
+    // the medium vertex's query is a closest-hit one in the reference (volumetric.cpp:63); only its boolean is
+    // used, which an any-hit query answers identically -- the closest-hit form is kept when the counters are on
+    Hit tmp; bool occluded;
+    if (COUNT && medium) occluded = traverse<false, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt);
+    else occluded = traverse<true, COUNT>(sc, e.shadow.o, e.shadow.d, e.shadow.mint, e.shadow.maxt, tmp, cnt);
+    V3 wiLocal = mk(0.f);
+    if (!medium) wiLocal = toLocal(its.sh, -st.d);
+    if (!occluded) {
+        const V3 Tr = mediumTr(med, ref, e.p);
+        if (medium) st.rad = st.rad + st.thr * Tr * Li * NORI_INV_FOURPI;
+        else {
             float pdf_em = emitterPdf(sc, light, e);
             V3 woLocal = toLocal(its.sh, e.wi);
             float theta = fmaxf(0.0f, woLocal.z);
             P2 uv0; uv0.x = 0.f; uv0.y = 0.f;                       // bRec.uv is not set (volumetric.cpp:103): Point2f() = 0
-            BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
-            V3 f = evalT<BSDF>(bsdf, b);
-            float pdf_mat = pdfT<BSDF>(bsdf, b);
+            BRec b = mkBRec(sc, *bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
+            V3 f = bsdfEvalDyn(*bsdf, b);
+            float pdf_mat = bsdfPdfDyn(*bsdf, b);
             float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
-            st.rad = st.rad + st.thr * w_ems * f * theta * Li * mediumTr(med, its.p, e.p);
+            st.rad = st.rad + st.thr * w_ems * f * theta * Li * Tr;
         }
-        float p = fminf(st.thr.x, 0.80f);
-        if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
-        st.thr = st.thr / p;
+    }
+    float p = fminf(st.thr.x, 0.80f);
+    if (st.rng.next1D() > p) { st.flags = PF_TERMINATE; return; }
+    st.thr = st.thr / p;
+    if (medium) {
+        next = mkray(mp, normalized(wo));
+        st.pdf_mat = NORI_INV_FOURPI; st.flags = PF_ALIVE;
+    } else {
         P2 uv1; uv1.x = 0.f; uv1.y = 0.f;
-        BRec b = mkBRec(sc, bsdf, wiLocal, M_UNKNOWN, uv1);
-        V3 w = sampleT<BSDF>(bsdf, b, st.rng.next2D());
+        BRec b = mkBRec(sc, *bsdf, wiLocal, M_UNKNOWN, uv1);
+        V3 w = bsdfSampleDyn(*bsdf, b, st.rng.next2D());
         st.thr = st.thr * w;
-        st.pdf_mat = pdfT<BSDF>(bsdf, b);
+        st.pdf_mat = bsdfPdfDyn(*bsdf, b);
         next = mkray(its.p, toWorld(its.sh, b.wo));
         st.flags = PF_ALIVE | (b.measure == M_DISCRETE ? PF_DISCRETE : 0u);
-    } else st.flags = PF_TERMINATE;                                 // volumetric.cpp:147-151
+    }
 }
 
 // volumetric.cpp:18-156

@@ -27,7 +27,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
     Hit h; h.t = hh.x; h.u = hh.y; h.v = hh.z; h.leafpos = __float_as_uint(hh.w);
     Ray next;
     if constexpr (MODE == MODE_VOL) {
-        volVertex<BSDF, COUNT>(sc, h, st, next, nClosest, nShadow, cnt);
+        volVertex<COUNT>(sc, h, st, next, nClosest, nShadow, cnt);
     } else {
         VertexOut out;
         pathVertex<BSDF, MODE == MODE_MIS>(sc, h, st, out);
@@ -61,9 +61,6 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 // All material queues in ONE launch: the queues are concatenated (diffuse | mirror | dielectric |
 // microfacet | disney | [volumetric: misses]) and work item i belongs to the queue whose range contains
 // it, so warps are material-coherent except where a boundary falls inside one.
-#ifndef NORI_SHADE_DIFFUSE_COPY
-#define NORI_SHADE_DIFFUSE_COPY 0
-#endif
 #ifndef NORI_SHADE_TEMPLATED
 #define NORI_SHADE_TEMPLATED 0
 #endif
@@ -79,7 +76,7 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-#if NORI_SHADE_TEMPLATED
+#if NORI_SHADE_TEMPLATED && NORI_SHADE_MODE != 2
         if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
         else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
         else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
@@ -94,11 +91,7 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 #pragma unroll
         for (int t = 1; t < NORI_NQ; ++t) q += i >= off[t];
         const uint32_t slot = pool.queue[q][i - off[q]];
-        if (MODE == MODE_VOL && q == NORI_Q_MISS) shadeSlot<NORI_Q_MISS, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-#if NORI_SHADE_DIFFUSE_COPY
-        else if (q == NORI_BSDF_DIFFUSE) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-#endif
-        else shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
 #endif
     }
     warpAdd(&ctr->done, nDone);
