@@ -103,6 +103,101 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
     }
 }
 
+// Same accumulation with the separable filter weights tabulated ONCE per staged sample instead of once per
+// (sample, film pixel) pair: the thread that stages a sample also evaluates its 2*HALO+1 column weights and
+// 2*HALO+1 row weights (window test of block.cpp:107-110 and table lookup of :114-117, in the reference's
+// block-relative arithmetic; 0 outside the window), and a film pixel then costs two shared-memory weight
+// reads and the reference's `value * wx * wy` products per candidate sample.  A weight of 0 adds +0 to the
+// sums, which leaves them bit-identical to skipping the sample (invalid samples are staged as zeros already).
+// Shared memory per CTA: (32+2*HALO)^2 x (16 + 8*(2*HALO+1)) bytes = 72.6 KB for the default Gaussian.
+template <bool VARIANCE, int HALO>
+__global__ void __launch_bounds__(1024) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
+    extern __shared__ float4 s_mem[];
+    constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1;
+    float4 *s_val = s_mem;
+    float *s_wx = (float *) (s_mem + nS), *s_wy = s_wx + nS * NW;
+    __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
+    const int tid = threadIdx.y * T + threadIdx.x;
+    if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
+    const int b = fp.border;                                           // == HALO
+    const int fx = blockIdx.x * T + threadIdx.x, fy = blockIdx.y * T + threadIdx.y;
+    const int sx0 = blockIdx.x * T - b - HALO, sy0 = blockIdx.y * T - b - HALO;
+    const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 vs = make_float3(0.f, 0.f, 0.f), vs2 = make_float3(0.f, 0.f, 0.f);
+    const bool owner = fx < fcols && fy < frows;
+    if (VARIANCE && owner) acc = fp.film[(size_t) fy * fcols + fx];
+    for (uint32_t k = 0; k < nLayers; ++k) {
+        __syncthreads();
+        for (int i = tid; i < nS; i += T * T) {
+            const int ly = i / S, lx = i - ly * S;
+            const int sx = sx0 + lx, sy = sy0 + ly;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float wx[NW], wy[NW];
+#pragma unroll
+            for (int j = 0; j < NW; ++j) { wx[j] = 0.f; wy[j] = 0.f; }
+            if (sx >= 0 && sx < fp.W && sy >= 0 && sy < fp.H) {
+                const uint32_t pix = (uint32_t) sy * fp.W + sx;
+                v = bt.results[(size_t) k * bt.wh + pix];
+                Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
+                P2 a = rng.next2D();
+                const float psx = (float) sx + a.x, psy = (float) sy + a.y;
+                // block.cpp:101-104 with the offset of the 32x32 block that rendered the sample
+                const int ox = sx & ~(NORI_BLOCK_SIZE - 1), oy = sy & ~(NORI_BLOCK_SIZE - 1);
+                const float px = __fsub_rn(__fsub_rn(psx, 0.5f), (float) (ox - b));
+                const float py = __fsub_rn(__fsub_rn(psy, 0.5f), (float) (oy - b));
+                const float xlo = __fsub_rn(px, fp.radius), xhi = __fadd_rn(px, fp.radius);
+                const float ylo = __fsub_rn(py, fp.radius), yhi = __fadd_rn(py, fp.radius);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {                          // film column / row (sx + b + j - HALO) in block coordinates
+                    const float xb = (float) (sx - ox + b + j - HALO), yb = (float) (sy - oy + b + j - HALO);
+                    if (!(xb < xlo || xb > xhi)) wx[j] = s_table[(int) __fmul_rn(fabsf(__fsub_rn(xb, px)), fp.lookupFactor)];
+                    if (!(yb < ylo || yb > yhi)) wy[j] = s_table[(int) __fmul_rn(fabsf(__fsub_rn(yb, py)), fp.lookupFactor)];
+                }
+            }
+            s_val[i] = v;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) { s_wx[i * NW + j] = wx[j]; s_wy[i * NW + j] = wy[j]; }
+        }
+        __syncthreads();
+        if (owner) {
+            const int cx = threadIdx.x + HALO, cy = threadIdx.y + HALO;   // own source pixel (image x = fx - b)
+#pragma unroll
+            for (int dy = -HALO; dy <= HALO; ++dy) {
+#pragma unroll
+                for (int dx = -HALO; dx <= HALO; ++dx) {
+                    const int i = (cy + dy) * S + (cx + dx);
+                    // this film pixel is column (HALO - dx) of the sample's 2*HALO+1 candidate columns
+                    const float wx = s_wx[i * NW + (HALO - dx)], wy = s_wy[i * NW + (HALO - dy)];
+                    const float4 v = s_val[i];
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                }
+            }
+            if (VARIANCE) {                                      // Color4f::divideByFilterWeight (color.h:84-89)
+                const float mx = acc.w != 0.f ? acc.x / acc.w : 0.f, my = acc.w != 0.f ? acc.y / acc.w : 0.f, mz = acc.w != 0.f ? acc.z / acc.w : 0.f;
+                vs.x += mx; vs.y += my; vs.z += mz;
+                vs2.x += mx * mx; vs2.y += my * my; vs2.z += mz * mz;
+            }
+        }
+    }
+    if (owner) {
+        float4 *dst = &fp.film[(size_t) fy * fcols + fx];
+        if (VARIANCE) {
+            *dst = acc;
+            float4 a = fp.vsum[(size_t) fy * fcols + fx], b2 = fp.vsum2[(size_t) fy * fcols + fx];
+            a.x += vs.x; a.y += vs.y; a.z += vs.z; b2.x += vs2.x; b2.y += vs2.y; b2.z += vs2.z;
+            fp.vsum[(size_t) fy * fcols + fx] = a; fp.vsum2[(size_t) fy * fcols + fx] = b2;
+        } else {
+            float4 f = *dst;
+            f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+            *dst = f;
+        }
+    }
+}
+
 // var = sum2/N - (sum/N)^2 per channel (render.cpp:268-275)
 __global__ void k_variance(const float4 *vsum, const float4 *vsum2, float *rgb, int W, int H, int b, float n) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;

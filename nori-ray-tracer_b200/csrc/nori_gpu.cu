@@ -36,6 +36,7 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_film_sep = 1;          // radius-2 filters: film kernel with per-sample tabulated weights (0: generic kernel)
     int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
     // 0 reference child order (counters equal the reference's), 1 near child first, 2 auto: near child first when
@@ -155,6 +156,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
+    else if (k == "film_sep") ctx->opt_film_sep = value != 0;
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
@@ -483,15 +485,27 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
             CK(cudaStreamSynchronize(ctx->stream));
         } else {
             const int S = 32 + 2 * fp.halo;
-            size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
-            CK(cudaFuncSetAttribute(k_film<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             dim3 grid((ctx->W + 2 * ctx->border + 31) / 32, (ctx->H + 2 * ctx->border + 31) / 32);
-            if (ctx->opt_variance) {
-                fp.vsum = ctx->vsum; fp.vsum2 = ctx->vsum2;
-                CK(cudaFuncSetAttribute(k_film<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                LAUNCH(NORI_K_FILM, (k_film<true><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
-                ctx->var_passes += n;
-            } else LAUNCH(NORI_K_FILM, (k_film<false><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+            if (ctx->opt_variance) { fp.vsum = ctx->vsum; fp.vsum2 = ctx->vsum2; ctx->var_passes += n; }
+            if (fp.halo == 2 && ctx->opt_film_sep) {                 // default Gaussian (radius 2): separable weights tabulated per sample
+                size_t smem = (size_t) S * S * (sizeof(float4) + 2 * 5 * sizeof(float));
+                if (ctx->opt_variance) {
+                    CK(cudaFuncSetAttribute(k_film_sep<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    LAUNCH(NORI_K_FILM, (k_film_sep<true, 2><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+                } else {
+                    CK(cudaFuncSetAttribute(k_film_sep<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    LAUNCH(NORI_K_FILM, (k_film_sep<false, 2><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+                }
+            } else {
+                size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
+                if (ctx->opt_variance) {
+                    CK(cudaFuncSetAttribute(k_film<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    LAUNCH(NORI_K_FILM, (k_film<true><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+                } else {
+                    CK(cudaFuncSetAttribute(k_film<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    LAUNCH(NORI_K_FILM, (k_film<false><<<grid, dim3(32, 32), smem, ctx->stream>>>(fp, bt, n)));
+                }
+            }
             CK(cudaGetLastError());
         }
         if (foldStats(ctx, (unsigned long long) n * wh)) return 1;
