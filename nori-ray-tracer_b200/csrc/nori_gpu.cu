@@ -19,7 +19,12 @@ struct nori_gpu_ctx {
     bool has_scene = false;
 
     DScene ds{};
-    std::vector<void *> scene_allocs;
+    std::vector<void *> scene_allocs;  // unused by the arena path; kept for freeAll symmetry
+    // all scene arrays live in ONE device allocation that is reused by the next upload when it is large enough:
+    // re-uploading a scene (the e2e loop, progressive rendering) then costs no cudaMalloc / cudaFree at all
+    // (their occasional 100+ ms driver stalls showed up in the end-to-end numbers)
+    char *arena = nullptr; size_t arena_cap = 0, arena_used = 0;
+    size_t film_cap = 0;
     nori_gpu_filter filter{};
     int W = 0, H = 0, border = 0;
     uint32_t bsdf_mask = 0;            // which BSDF types occur in the scene
@@ -72,15 +77,39 @@ static inline void launchEnd(nori_gpu_ctx *ctx) {
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
 #define REQUIRE(cond, msg) do { if (!(cond)) { ctx->err = (msg); return 1; } } while (0)
 
-template <typename T> static int devUpload(nori_gpu_ctx *ctx, std::vector<void *> &owner, const T *src, size_t n, const T **out) {
+template <typename T> static int devUpload(nori_gpu_ctx *ctx, std::vector<void *> &, const T *src, size_t n, const T **out) {
     *out = nullptr;
     if (!n) return 0;
-    void *d = nullptr;
-    CK(cudaMalloc(&d, n * sizeof(T)));
-    owner.push_back(d);
-    CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t off = (ctx->arena_used + 255) & ~(size_t) 255, bytes = n * sizeof(T);
+    if (off + bytes > ctx->arena_cap) { ctx->err = "upload_scene: scene arena too small (internal size estimate is wrong)"; return 1; }
+    void *d = ctx->arena + off;
+    ctx->arena_used = off + bytes;
+    CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     *out = (const T *) d;
     return 0;
+}
+
+// upper bound of the device bytes nori_gpu_upload_scene needs for `s` (every array padded to 256 bytes)
+static size_t sceneArenaBytes(const nori_gpu_scene *s) {
+    size_t total = 0, arrays = 16;
+    auto add = [&](size_t bytes) { total += bytes; ++arrays; };
+    for (uint32_t i = 0; i < s->n_images; ++i) add((size_t) s->images[i].width * s->images[i].height * 3);
+    for (uint32_t i = 0; i < s->n_shapes; ++i) {
+        const nori_gpu_shape &h = s->shapes[i];
+        if (h.type != NORI_SHAPE_MESH) continue;
+        add(12 * (size_t) h.n_vertices); add(12 * (size_t) h.n_vertices); add(8 * (size_t) h.n_vertices);
+        add(12 * (size_t) h.n_triangles); add(4 * ((size_t) h.n_triangles + 1));
+    }
+    for (uint32_t i = 0; i < s->n_emitters; ++i) {
+        const nori_gpu_emitter &e = s->emitters[i];
+        if (e.type != NORI_EMITTER_ENVMAP) continue;
+        const size_t R = e.env_rows > 0 ? e.env_rows : 0, C = e.env_cols > 0 ? e.env_cols : 0;
+        add(R * C * 12); add(R * C * 4); add(R * (C + 1) * 4); add(R * 4); add((R + 1) * 4);
+    }
+    add(32 * (size_t) s->n_nodes); add(64 * (size_t) s->n_nodes); add(48 * (size_t) s->n_indices);
+    add(sizeof(DShape) * (size_t) s->n_shapes); add(sizeof(nori_gpu_bsdf) * (size_t) s->n_bsdfs);
+    add(sizeof(DEmitter) * (size_t) s->n_emitters); add(sizeof(DImage) * (size_t) s->n_images);
+    return total + 256 * arrays;
 }
 
 static void freeAll(std::vector<void *> &v) { for (void *p : v) cudaFree(p); v.clear(); }
@@ -116,6 +145,7 @@ void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     freeAll(ctx->scene_allocs); freeAll(ctx->pool_allocs);
+    cudaFree(ctx->arena);
     cudaFree(ctx->film); cudaFree(ctx->vsum); cudaFree(ctx->vsum2); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
     cudaFreeHost(ctx->h_ctr);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -187,6 +217,13 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     CK(cudaStreamSynchronize(ctx->stream));
     freeAll(ctx->scene_allocs);
     ctx->has_scene = false;
+    const size_t need = sceneArenaBytes(s);
+    if (need > ctx->arena_cap) {
+        cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_cap = 0;
+        CK(cudaMalloc((void **) &ctx->arena, need));
+        ctx->arena_cap = need;
+    }
+    ctx->arena_used = 0;
     DScene ds{};
     ds.n_nodes = s->n_nodes; ds.n_prims = s->n_indices; ds.n_shapes = s->n_shapes; ds.n_emitters = s->n_emitters;
     ds.ordered = 0;
@@ -333,10 +370,14 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     ctx->ds = ds; ctx->filter = s->filter; ctx->bsdf_mask = mask; ctx->n_bsdfs = s->n_bsdfs;
     ctx->W = s->camera.width; ctx->H = s->camera.height;
     ctx->border = (int) std::ceil(s->filter.radius - 0.5f);              // block.cpp:57
-    cudaFree(ctx->film); ctx->film = nullptr;
-    cudaFree(ctx->vsum); cudaFree(ctx->vsum2); ctx->vsum = ctx->vsum2 = nullptr; ctx->opt_variance = 0; ctx->var_passes = 0;
+    if (ctx->vsum) { cudaFree(ctx->vsum); cudaFree(ctx->vsum2); ctx->vsum = ctx->vsum2 = nullptr; }
+    ctx->opt_variance = 0; ctx->var_passes = 0;
     size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
-    CK(cudaMalloc((void **) &ctx->film, nf * sizeof(float4)));
+    if (nf > ctx->film_cap) {
+        cudaFree(ctx->film); ctx->film = nullptr; ctx->film_cap = 0;
+        CK(cudaMalloc((void **) &ctx->film, nf * sizeof(float4)));
+        ctx->film_cap = nf;
+    }
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
     ctx->has_scene = true;
     return 0;
