@@ -286,6 +286,16 @@ int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq,
  * nodes_out: capacity 2 * (total primitives); indices_out: total primitives; shape_offset_out: n_shapes+1. */
 int nori_gpu_build_bvh(const nori_gpu_shape *shapes, uint32_t n_shapes, nori_gpu_bvh_node *nodes_out,
                        uint32_t *indices_out, uint32_t *shape_offset_out, uint32_t *n_nodes_out, int threads);
+/* The same job on the GPU, for scenes whose host build time matters: a linear BVH (Morton codes,
+ * radix sort, Karras' parallel radix tree, bottom-up box fitting; subtrees of at most leaf_size primitives
+ * become one leaf) written in the SAME format -- reference nodes in depth-first order, left child behind its
+ * parent, split axis recorded -- so it can be uploaded, traversed and checked like a reference tree.  An
+ * alternative, not a replacement: the tree differs from the reference's, so exact ties between primitives may
+ * resolve differently (traverse.cuh).  Same output capacities as nori_gpu_build_bvh; build_ms_out (optional)
+ * receives the device time of the build kernels. */
+int nori_gpu_build_bvh_device(int device, const nori_gpu_shape *shapes, uint32_t n_shapes, nori_gpu_bvh_node *nodes_out,
+                              uint32_t *indices_out, uint32_t *shape_offset_out, uint32_t *n_nodes_out,
+                              uint32_t leaf_size, float *build_ms_out);
 /* Mesh::activate (mesh.cpp:30-38): per-triangle area CDF (n_triangles+1 floats) and 1/total area. */
 int nori_gpu_mesh_area_cdf(const float *V, const uint32_t *F, uint32_t n_triangles, float *cdf_out,
                            float *normalization_out);

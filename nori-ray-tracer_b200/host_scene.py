@@ -127,8 +127,11 @@ class SceneBuilder:
         self.camera = c
 
     # ---- finish -------------------------------------------------------------------------------
-    def build(self, threads=0):
+    def build(self, threads=0, builder="sah", leaf_size=4, device=0):
+        """builder="sah": the host restatement of the reference's SAH builder (reference-identical trees);
+        builder="lbvh": the GPU builder (nori_gpu_build_bvh_device) -- same node format, different tree."""
         lib = gpu.load_library()
+        self.build_ms = None
         n_shapes = len(self.shapes)
         shapes = (abi.Shape * max(n_shapes, 1))(*self.shapes)
         keep = []
@@ -142,10 +145,16 @@ class SceneBuilder:
         indices = np.zeros(max(total, 1), np.uint32)
         offsets = np.zeros(n_shapes + 1, np.uint32)
         n_nodes = C.c_uint32()
-        rc = lib.nori_gpu_build_bvh(shapes, n_shapes, nodes.ctypes.data, indices.ctypes.data, offsets.ctypes.data,
-                                    C.byref(n_nodes), threads)
+        if builder == "lbvh":
+            ms = C.c_float()
+            rc = lib.nori_gpu_build_bvh_device(device, shapes, n_shapes, nodes.ctypes.data, indices.ctypes.data, offsets.ctypes.data,
+                                               C.byref(n_nodes), leaf_size, C.byref(ms))
+            self.build_ms = ms.value
+        else:
+            rc = lib.nori_gpu_build_bvh(shapes, n_shapes, nodes.ctypes.data, indices.ctypes.data, offsets.ctypes.data,
+                                        C.byref(n_nodes), threads)
         if rc != 0:
-            raise RuntimeError("nori_gpu_build_bvh failed")
+            raise RuntimeError(f"BVH build ({builder}) failed")
         for s in shapes:                                   # the container stores PODs with null pointers
             s.V = s.N = s.UV = s.area_cdf = None; s.F = None
         e = dict(self.arrays)
@@ -165,7 +174,7 @@ class SceneBuilder:
         return nscene.SceneData(e)
 
 
-def heightfield_scene(n=2237, width=3840, height=2160, seed=0, integrator="path_mis"):
+def heightfield_scene(n=2237, width=3840, height=2160, seed=0, integrator="path_mis", builder="sah", leaf_size=4, return_builder=False):
     """BASELINE config 4: an n x n-vertex height field (2*(n-1)^2 triangles; n = 2237 -> 9,999,392),
     z = seeded value noise, diffuse, lit by one area-light quad, viewed from above at an angle."""
     rng = np.random.RandomState(seed)
@@ -188,4 +197,33 @@ def heightfield_scene(n=2237, width=3840, height=2160, seed=0, integrator="path_
     lv = np.array([[-0.4, -0.4, 1.5], [0.4, -0.4, 1.5], [0.4, 0.4, 1.5], [-0.4, 0.4, 1.5]], f32)
     sb.add_mesh(lv, np.array([[0, 2, 1], [0, 3, 2]], np.uint32), sb.diffuse((0, 0, 0)), emitter=light)   # faces down
     sb.perspective(width, height, 40.0, origin=(0.0, -2.2, 1.6), target=(0, 0, 0.1), up=(0, 0, 1))
-    return sb.build()
+    sc = sb.build(builder=builder, leaf_size=leaf_size)
+    return (sc, sb) if return_builder else sc
+
+
+def rebuild_bvh(scene, builder="lbvh", leaf_size=4, device=0, threads=0):
+    """A copy of `scene` (nscene.SceneData) whose BVH was rebuilt from its shapes by the host SAH builder
+    ("sah": nori_gpu_build_bvh) or the GPU linear-BVH builder ("lbvh": nori_gpu_build_bvh_device).  Returns
+    (new scene, device build time in ms or None)."""
+    lib = gpu.load_library()
+    n_shapes = scene.pod.n_shapes
+    total = int(scene.indices.size)
+    nodes = np.zeros((max(2 * total, 1), 8), np.uint32)
+    indices = np.zeros(max(total, 1), np.uint32)
+    offsets = np.zeros(n_shapes + 1, np.uint32)
+    n_nodes = C.c_uint32(); ms = C.c_float()
+    shapes = C.cast(scene.shapes, C.POINTER(abi.Shape))
+    if builder == "lbvh":
+        rc = lib.nori_gpu_build_bvh_device(device, shapes, n_shapes, nodes.ctypes.data, indices.ctypes.data, offsets.ctypes.data,
+                                           C.byref(n_nodes), leaf_size, C.byref(ms))
+    else:
+        rc = lib.nori_gpu_build_bvh(shapes, n_shapes, nodes.ctypes.data, indices.ctypes.data, offsets.ctypes.data, C.byref(n_nodes), threads)
+    if rc != 0:
+        raise RuntimeError(f"BVH build ({builder}) failed")
+    e = dict(scene.entries)
+    e["bvh.nodes"] = nodes[:n_nodes.value].copy()
+    e["bvh.indices"] = indices[:total].copy()
+    e["bvh.shape_offset"] = offsets
+    for k in [k for k in e if k.startswith("rays")]:       # reference-answered ray batches belong to the reference tree's counters
+        del e[k]
+    return nscene.SceneData(e), (ms.value if builder == "lbvh" else None)

@@ -7,7 +7,9 @@ from nori_ray_tracer_b200.gpu import NoriGpu
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2237
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 integ = sys.argv[3] if len(sys.argv) > 3 else 'path_mis'
-t = time.time(); sc = host_scene.heightfield_scene(n=n, integrator=integ); print('build s', round(time.time() - t, 1), 'prims', sc.pod.n_indices, 'nodes', sc.pod.n_nodes, flush=True)
+import os
+builder = os.environ.get('NORI_BUILDER', 'sah'); leaf = int(os.environ.get('NORI_LEAF', '4'))
+t = time.time(); sc, sb = host_scene.heightfield_scene(n=n, integrator=integ, builder=builder, leaf_size=leaf, return_builder=True); print('builder', builder, 'leaf', leaf, 'scene+build s', round(time.time() - t, 2), 'device build ms', sb.build_ms, 'prims', sc.pod.n_indices, 'nodes', sc.pod.n_nodes, flush=True)
 g = NoriGpu(0); t = time.time(); g.upload_scene(sc); print('upload s', round(time.time() - t, 2))
 g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '2')))
 g.render(0, 2, seed=1)
