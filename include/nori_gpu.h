@@ -29,7 +29,7 @@ extern "C" {
 typedef struct nori_gpu_ctx nori_gpu_ctx;  /* opaque; owns all device memory */
 
 /* ---- enumerations (values are part of the ABI) ------------------------------------------- */
-enum { NORI_SHAPE_MESH = 0, NORI_SHAPE_SPHERE = 1 };                     /* src/mesh.cpp, src/sphere.cpp */
+enum { NORI_SHAPE_MESH = 0, NORI_SHAPE_SPHERE = 1, NORI_SHAPE_PERLIN = 2 };   /* src/mesh.cpp, src/sphere.cpp, src/perlinnoise.cpp */
 enum { NORI_BSDF_DIFFUSE = 0, NORI_BSDF_MIRROR = 1, NORI_BSDF_DIELECTRIC = 2,
        NORI_BSDF_MICROFACET = 3, NORI_BSDF_DISNEY = 4, NORI_BSDF_COUNT = 5 };
 enum { NORI_EMITTER_AREA = 0, NORI_EMITTER_POINT = 1, NORI_EMITTER_SPOT = 2, NORI_EMITTER_ENVMAP = 3 };
@@ -72,9 +72,11 @@ typedef struct {
     const uint32_t *F;          /* 3*n_triangles, column-major m_F                           */
     const float    *area_cdf;   /* n_triangles+1 floats: DiscretePDF::m_cdf (dpdf.h:194)     */
     float    area_normalization;/* DiscretePDF::getNormalization() = 1/total area            */
-    float    center[3];         /* sphere                                                    */
-    float    radius;            /* sphere                                                    */
-    uint32_t reserved2[3];
+    float    center[3];         /* sphere / perlin sphere                                    */
+    float    radius;            /* sphere / perlin sphere                                    */
+    float    perlin_height;     /* perlinnoise.cpp:15 "height": base frequency is 1/height   */
+    float    perlin_scale;      /* perlinnoise.cpp:16 "scale": radius += scale * clamp(noise, 0, 1) */
+    uint32_t reserved2;
 } nori_gpu_shape;
 
 /* ---- BSDFs (src/diffuse.cpp, mirror.cpp, dielectric.cpp, microfacet.cpp, disney.cpp) ----- */

@@ -6,7 +6,7 @@ ABI_VERSION = 2
 FILTER_RESOLUTION = 32
 BLOCK_SIZE = 32
 
-SHAPE_MESH, SHAPE_SPHERE = 0, 1
+SHAPE_MESH, SHAPE_SPHERE, SHAPE_PERLIN = 0, 1, 2
 BSDF_DIFFUSE, BSDF_MIRROR, BSDF_DIELECTRIC, BSDF_MICROFACET, BSDF_DISNEY = range(5)
 EMITTER_AREA, EMITTER_POINT, EMITTER_SPOT, EMITTER_ENVMAP = range(4)
 CAMERA_PERSPECTIVE, CAMERA_THINLENS, CAMERA_ADVANCED = 0, 1, 2
@@ -36,7 +36,7 @@ class Shape(C.Structure):
                 ("n_triangles", u32), ("normal_map", i32),
                 ("V", pf32), ("N", pf32), ("UV", pf32), ("F", pu32), ("area_cdf", pf32),
                 ("area_normalization", f32), ("center", f32 * 3), ("radius", f32),
-                ("reserved2", u32 * 3)]
+                ("perlin_height", f32), ("perlin_scale", f32), ("reserved2", u32)]
 
 
 class Bsdf(C.Structure):

@@ -1,6 +1,7 @@
 // nori_gpu.cu -- the extern "C" boundary of include/nori_gpu.h over the kernels in kernels.cuh.
 // One context = one CUDA device + one stream.  No torch, no exceptions across the ABI, no CPU
 // fallback: every entry point that computes does so on the device or fails with an error string.
+#define NORI_WITH_PERLIN 1      // see traverse.cuh
 #include "film_kernels.cuh"
 #include <algorithm>
 #include <cmath>
@@ -16,7 +17,7 @@ struct nori_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    bool has_scene = false;
+    bool has_scene = false, has_perlin = false;
 
     DScene ds{};
     std::vector<void *> scene_allocs;  // unused by the arena path; kept for freeAll symmetry
@@ -247,6 +248,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     // ---- per-shape arrays + shape table
     std::vector<DShape> shapes(s->n_shapes);
     uint32_t mask = 0;
+    bool hasPerlin = false;
     for (uint32_t i = 0; i < s->n_shapes; ++i) {
         const nori_gpu_shape &h = s->shapes[i];
         DShape &d = shapes[i]; memset(&d, 0, sizeof(d));
@@ -269,7 +271,10 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             d.has_n = h.N != nullptr; d.has_uv = h.UV != nullptr;
             REQUIRE(h.emitter < 0 || h.area_cdf, "upload_scene: emitter mesh without an area CDF");
         } else {
-            REQUIRE(h.type == NORI_SHAPE_SPHERE, "upload_scene: unknown shape type");
+            REQUIRE(h.type == NORI_SHAPE_SPHERE || h.type == NORI_SHAPE_PERLIN, "upload_scene: unknown shape type");
+            REQUIRE(h.type != NORI_SHAPE_PERLIN || h.perlin_height != 0.f, "upload_scene: perlin sphere with height 0");
+            d.perlin_height = h.perlin_height; d.perlin_scale = h.perlin_scale;
+            hasPerlin = hasPerlin || h.type == NORI_SHAPE_PERLIN;
             // sphere.cpp:99: std::pow(1.f / r, 2) [double] * 0.25f * INV_PI [float]
             double ir = (double) (1.f / h.radius);
             d.sphere_pdf = (float) (ir * ir * (double) (0.25f * NORI_INV_PI));
@@ -296,9 +301,9 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             tag = 0u;
         } else {
             r[0] = make_float4(h.center[0], h.center[1], h.center[2], 0.f);
-            r[1] = make_float4(h.radius, 0.f, 0.f, 0.f);
+            r[1] = make_float4(h.radius, h.perlin_height, h.perlin_scale, 0.f);
             r[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            tag = 1u;
+            tag = h.type == NORI_SHAPE_PERLIN ? 2u : 1u;
         }
         memcpy(&r[0].w, &idx, 4); memcpy(&r[1].w, &shape, 4); memcpy(&r[2].w, &tag, 4);
     }
@@ -379,7 +384,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
         ctx->film_cap = nf;
     }
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
-    ctx->has_scene = true;
+    ctx->has_scene = true; ctx->has_perlin = hasPerlin;
     return 0;
 }
 
@@ -420,8 +425,9 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const bool count = ctx->opt_stats != 0;
     const int integ = ctx->ds.integrator;
     ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
+    // scenes with a Perlin-noise sphere are rendered by the one-thread-per-sample kernel (traverse.cuh: NORI_WITH_PERLIN)
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
-                      && !ctx->opt_megakernel;
+                      && !ctx->opt_megakernel && !ctx->has_perlin;
     if (!wave) {
         const unsigned grid = (unsigned) ((total + 127) / 128);
         LAUNCH(NORI_K_SINGLE, noriLaunchMega(count, grid, ctx->stream, ctx->ds, bt, ctx->ctr, total));

@@ -86,8 +86,13 @@ __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit 
         its.sh = makeFrame(n);
         float th = acosf(n.z), ph = atan2f(n.y, n.x);            // common.cpp:264-272
         if (ph < 0) ph += 2 * NORI_PI;
-        its.uv.x = (float) (0.5 + th / (2 * NORI_PI));
-        its.uv.y = ph / NORI_PI;
+        if (__float_as_uint(r2.w) == 1u) {                          // sphere.cpp:88-91
+            its.uv.x = (float) (0.5 + th / (2 * NORI_PI));
+            its.uv.y = ph / NORI_PI;
+        } else {                                                    // perlinnoise.cpp:71-74
+            its.uv.x = (float) (0.5 + (double) (th * 0.15915494309189533577f));
+            its.uv.y = ph * NORI_INV_PI;
+        }
     }
 }
 
@@ -363,13 +368,30 @@ __device__ __forceinline__ void sampleSurface(const DShape &m, P2 s, V3 &p, V3 &
         if (m.has_n) n = normalizedDyn((bc.x * ld3(&m.N[3 * i0]) + bc.y * ld3(&m.N[3 * i1])) + bc.z * ld3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         pdf = m.area_normalization;
+#if NORI_WITH_PERLIN
+    } else if (m.type == NORI_SHAPE_PERLIN) {                       // perlinnoise.cpp:77-86
+        V3 q = squareToUniformSphere(s);
+        p = mk(m.cx, m.cy, m.cz) + m.radius * q;
+        const float r = perlinNoisedRadius(m.radius, m.perlin_height, m.perlin_scale, p);
+        p = mk(m.cx, m.cy, m.cz) + r * q; n = q;
+        const double ir = (double) (1.f / r);
+        pdf = (float) (ir * ir * (double) (0.25f * NORI_INV_PI));
+#endif
     } else {
         V3 q = squareToUniformSphere(s);
         p = mk(m.cx, m.cy, m.cz) + m.radius * q; n = q;
         pdf = m.sphere_pdf;
     }
 }
-__device__ __forceinline__ float pdfSurface(const DShape &m) { return m.type == NORI_SHAPE_MESH ? m.area_normalization : m.sphere_pdf; }
+__device__ __forceinline__ float pdfSurface(const DShape &m, V3 p) {
+#if NORI_WITH_PERLIN
+    if (m.type == NORI_SHAPE_PERLIN) {                              // perlinnoise.cpp:88-91
+        const double ir = (double) (1.f / perlinNoisedRadius(m.radius, m.perlin_height, m.perlin_scale, p));
+        return (float) (ir * ir * (double) (0.25f * NORI_INV_PI));
+    }
+#endif
+    return m.type == NORI_SHAPE_MESH ? m.area_normalization : m.sphere_pdf;
+}
 
 // envmap.cpp:60-76
 __device__ __forceinline__ P2 envMapIntersect(const nori_gpu_emitter &e, V3 vec) {
@@ -408,7 +430,7 @@ __device__ __forceinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitt
 
 __device__ __forceinline__ float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
     switch (e.type) {
-    case NORI_EMITTER_AREA: return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.shape]) : 0.0f;   // arealight.cpp:64-76
+    case NORI_EMITTER_AREA: return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.shape], l.p) : 0.0f;   // arealight.cpp:64-76
     case NORI_EMITTER_POINT: return 1.0f;                         // pointlight.cpp:30-33
     case NORI_EMITTER_SPOT: return l.pdf;                         // spotlight.cpp:44-47
     default: {                                                    // envmap.cpp:184-192

@@ -231,7 +231,7 @@ __device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack
     if (__float_as_uint(r2.w) == 0u)
         h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
     else
-        h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
+        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.maxt, t);
     if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
         r.found = true;
         if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }
@@ -312,7 +312,7 @@ __device__ __forceinline__ void smPrim(const DScene &sc, LaneTrav &L, LaneStack 
     if (__float_as_uint(r2.w) == 0u)
         h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
     else
-        h = sphereTest(mk(r0.x, r0.y, r0.z), r1.x, r.o, r.d, r.mint, r.maxt, t);
+        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.maxt, t);
     if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
         r.found = true;
         if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }

@@ -209,6 +209,76 @@ inline bool sphereHit(const Shape &s, const Ray &ray, float &t) {
     return false;
 }
 
+/* ---- PerlinSphere (perlinnoise.cpp:25-203): a sphere whose radius is perturbed by 2D value noise of the hit
+ * point.  The integer hash overflows `int` in the reference (wraps on x86); unsigned arithmetic gives the same
+ * bits.  Interpolation runs in double (cos(double), literals 0.5 / 1073741824.0), octave weights are
+ * pow(2, i) (double) and pow(2.0f, (float) i) (float) -- both exact powers of two. */
+inline float perlinNoise(int x, int y) {                                       /* :200-204 */
+    uint32_t n = (uint32_t) x + (uint32_t) y * 57u;
+    n = (n << 13) ^ n;
+    int32_t v = (int32_t) ((n * ((n * n * 15731u) + 789221u) + 1376312589u) & 0x7fffffffu);
+    return (float) (1.0f - v / 1073741824.0);
+}
+inline float perlinBilinear(int x, int y) {                                    /* :193-197 */
+    return ((perlinNoise(x - 1, y) + perlinNoise(x + 1, y) + perlinNoise(x, y - 1) + perlinNoise(x, y + 1)) / 8.0f) +
+           ((perlinNoise(x - 1, y - 1) + perlinNoise(x + 1, y - 1) + perlinNoise(x - 1, y + 1) + perlinNoise(x + 1, y + 1)) / 16.0f) +
+           (perlinNoise(x, y) / 4.0f);
+}
+inline float perlinCosine(float a, float b, float x) {                        /* :186-190 */
+    double ft = x * kPi;
+    double f = (1 - std::cos(ft)) * 0.5;
+    return (float) (a * (1 - f) + b * f);
+}
+inline float perlinInterpolated(float x, float y) {                           /* :167-183 */
+    int x_ = (int) x, y_ = (int) y;
+    float dx = x - x_, dy = y - y_;
+    float v0 = perlinBilinear(x_, y_), v1 = perlinBilinear(x_ + 1, y_), v2 = perlinBilinear(x_, y_ + 1), v3 = perlinBilinear(x_ + 1, y_ + 1);
+    float i0 = perlinCosine(v0, v1, dx), i1 = perlinCosine(v2, v3, dx);
+    return perlinCosine(i0, i1, dy);
+}
+inline float perlinNoisedRadius(const nori_gpu_shape &s, V3 p) {              /* :143-164 */
+    float res = 0.0f, freq = 1.0f / s.perlin_height, amp = 1.0f, lac = 2.0f;
+    for (int i = 0; i < 9; ++i) {
+        res += perlinInterpolated(p.x * freq, p.y * freq) * amp;
+        freq = (float) std::pow(2, i);
+        amp = std::pow(lac, static_cast<float>(i));
+    }
+    float r_scale = res / 256.0f;
+    return s.radius + s.perlin_scale * std::min(std::max(0.0f, r_scale), 1.0f);
+}
+inline size_t solveQuadratic(float a, float b, float c, float *t0, float *t1) { /* common.h:251-268 */
+    float delta = (b * b) - (4 * a * c);
+    if (delta < 0) return 0;
+    if (delta == 0) { *t0 = (-b) / (2 * a); return 1; }
+    *t0 = ((-b) + std::sqrt(delta)) / (2 * a);
+    *t1 = ((-b) - std::sqrt(delta)) / (2 * a);
+    return 2;
+}
+/* the root selection shared by rayIntersect (:36-58) and perlinRayIntersect (:118-139); note `t < maxt` */
+inline bool perlinPick(size_t n, float t0, float t1, const Ray &ray, float &t) {
+    if (n == 0) return false;
+    if (n == 1) { t = t0; return ray.mint <= t && t < ray.maxt; }
+    t = std::min(t0, t1);
+    if (ray.mint <= t && t < ray.maxt) return true;
+    t = std::max(t0, t1);
+    return ray.mint <= t && t < ray.maxt;
+}
+inline bool perlinHit(const Shape &s, const Ray &ray, float &t) {             /* :25-59 + :106-140 */
+    V3 c = load3(s.pod.center);
+    V3 oc = ray.o - c;
+    float a = dot(ray.d, ray.d);
+    float b = (float) (2.0 * dot(oc, ray.d));
+    float cc = dot(oc, oc) - s.pod.radius * s.pod.radius;
+    float t0 = 0, t1 = 0;
+    size_t n = solveQuadratic(a, b, cc, &t0, &t1);
+    if (!perlinPick(n, t0, t1, ray, t)) return false;        /* n == 1 with an invalid root also returns false (:41-47) */
+    V3 its_p = ray.at(t);
+    float r = perlinNoisedRadius(s.pod, its_p);
+    float c2 = dot(oc, oc) - r * r;
+    n = solveQuadratic(a, b, c2, &t0, &t1);
+    return perlinPick(n, t0, t1, ray, t);
+}
+
 /* bvh.h:105-109 */
 inline uint32_t findShape(const Scene &sc, uint32_t &idx) {
     auto it = std::lower_bound(sc.shapeOffset.begin(), sc.shapeOffset.end(), idx + 1) - 1;
@@ -265,6 +335,15 @@ void setHitInformation(const Scene &sc, const Ray &ray, Its &its) {
                 its.sh = makeFrame(toWorld(its.sh, normalized(nm)));
             }
         } else its.sh = its.geo;
+    } else if (m.pod.type == NORI_SHAPE_PERLIN) {                              /* perlinnoise.cpp:61-75 */
+        V3 c = load3(m.pod.center);
+        its.p = ray.o + its.t * ray.d;
+        V3 n = normalized(its.p - c);
+        its.sh = its.geo = makeFrame(n);
+        float th = std::acos(n.z), ph = std::atan2(n.y, n.x);
+        if (ph < 0) ph += 2 * kPi;
+        its.uv.x = (float) (0.5 + th * (0.15915494309189533577f));             /* INV_TWOPI, common.h:61 */
+        its.uv.y = ph * kInvPi;
     } else {
         /* by now ray.maxt == its.t (bvh.cpp:444) */
         V3 c = load3(m.pod.center);
@@ -308,7 +387,8 @@ bool rayIntersect(Scene &sc, const Ray &_ray, Its &its, bool shadowRay, bool cou
                 float u = 0, v = 0, t = 0;
                 ++its.prims;
                 const Shape &shp = sc.shapes[s];
-                bool hit = shp.pod.type == NORI_SHAPE_MESH ? triHit(shp, idx, ray, u, v, t) : sphereHit(shp, ray, t);
+                bool hit = shp.pod.type == NORI_SHAPE_MESH ? triHit(shp, idx, ray, u, v, t)
+                         : shp.pod.type == NORI_SHAPE_PERLIN ? perlinHit(shp, ray, t) : sphereHit(shp, ray, t);
                 if (hit) {
                     if (shadowRay) { its.t = 0; goto done_shadow; }
                     found = true;
@@ -565,15 +645,22 @@ void sampleSurface(const Shape &m, P2 s, V3 &p, V3 &n, float &pdf) {
         if (!m.N.empty()) n = normalizedDyn((bc.x * load3(&m.N[3 * i0]) + bc.y * load3(&m.N[3 * i1])) + bc.z * load3(&m.N[3 * i2]));
         else n = normalized(cross(p1 - p0, p2 - p0));
         pdf = m.pod.area_normalization;
+    } else if (m.pod.type == NORI_SHAPE_PERLIN) {                              /* perlinnoise.cpp:77-86 */
+        V3 q = squareToUniformSphere(s);
+        p = load3(m.pod.center) + m.pod.radius * q;
+        float r = perlinNoisedRadius(m.pod, p);
+        p = load3(m.pod.center) + r * q; n = q;
+        pdf = (float) (std::pow((double) (1.f / r), 2) * (0.25f * kInvPi));
     } else {
         V3 q = squareToUniformSphere(s);
         p = load3(m.pod.center) + m.pod.radius * q; n = q;
         pdf = (float) (std::pow((double) (1.f / m.pod.radius), 2) * (0.25f * kInvPi));
     }
 }
-inline float pdfSurface(const Shape &m) {
-    return m.pod.type == NORI_SHAPE_MESH ? m.pod.area_normalization
-        : (float) (std::pow((double) (1.f / m.pod.radius), 2) * (0.25f * kInvPi));
+inline float pdfSurface(const Shape &m, V3 p) {
+    if (m.pod.type == NORI_SHAPE_MESH) return m.pod.area_normalization;
+    float r = m.pod.type == NORI_SHAPE_PERLIN ? perlinNoisedRadius(m.pod, p) : m.pod.radius;   /* perlinnoise.cpp:88-91 */
+    return (float) (std::pow((double) (1.f / r), 2) * (0.25f * kInvPi));
 }
 
 /* envmap.cpp:60-88 */
@@ -615,7 +702,7 @@ V3 emitterEval(const Scene &sc, const Emitter &e, const ERec &l) {
 float emitterPdf(const Scene &sc, const Emitter &e, const ERec &l) {
     switch (e.pod.type) {
     case NORI_EMITTER_AREA:                                                   /* arealight.cpp:64-76 */
-        return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.pod.shape]) : 0.0f;
+        return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.pod.shape], l.p) : 0.0f;
     case NORI_EMITTER_POINT: return 1.0f;                                     /* pointlight.cpp:30-33 */
     case NORI_EMITTER_SPOT: return l.pdf;                                     /* spotlight.cpp:44-47 */
     case NORI_EMITTER_ENVMAP: {                                               /* envmap.cpp:184-192 */

@@ -261,6 +261,12 @@ int main(int argc, char **argv) {
                 p.type = NORI_SHAPE_SPHERE; p.n_triangles = 1;
                 copy3(p.center, info(sh).props.getPoint3("center", Point3f()));
                 p.radius = info(sh).props.getFloat("radius", 1.f);
+            } else if (info(sh).type == "perlinsphere") {             /* perlinnoise.cpp:12-20 */
+                p.type = NORI_SHAPE_PERLIN; p.n_triangles = 1;
+                copy3(p.center, info(sh).props.getPoint3("center", Point3f()));
+                p.radius = info(sh).props.getFloat("radius", 1.f);
+                p.perlin_height = info(sh).props.getFloat("height", 1.0f);
+                p.perlin_scale = info(sh).props.getFloat("scale", 1.0f);
             } else throw NoriException("nori_export: shape '%s' is outside the hot-path scope", info(sh).type);
 
             const BSDF *b = sh->getBSDF();

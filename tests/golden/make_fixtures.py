@@ -82,6 +82,13 @@ FIXTURES += [
     dict(name="cbox_advcam", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 64],
          camera=("advancedCamera", '<float name="lensRadius" value="0.04"/><float name="focalDist" value="4.6"/>'
                  '<vector name="chromaticAberation" value="4, 2, 3.3"/><vector name="distortion" value="3, 3"/>')),
+    dict(name="cbox_perlin", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=6000, seq=1000, ref_spp=[4, 64],
+         extra='<mesh type="perlinsphere"><point name="center" value="0.0 0.9 0.1"/><float name="radius" value="0.22"/>'
+               '<float name="height" value="0.07"/><float name="scale" value="0.09"/>'
+               '<bsdf type="diffuse"><color name="albedo" value="0.3 0.6 0.8"/></bsdf></mesh>'
+               '<mesh type="perlinsphere"><point name="center" value="0.55 1.25 -0.3"/><float name="radius" value="0.06"/>'
+               '<float name="height" value="0.03"/><float name="scale" value="0.03"/>'
+               '<emitter type="area"><color name="radiance" value="25 20 12"/></emitter></mesh>'),
     dict(name="cbox_advcam_distortion", src="pa4/cbox/cbox_path_mis.xml", res=(200, 150), rays=0, seq=1000, ref_spp=[4, 64],
          camera=("advancedCamera", '<vector name="distortion" value="1.7, 1.7"/>')),
 ]
