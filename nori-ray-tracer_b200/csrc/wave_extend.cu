@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 #define NORI_LEAF_MIN 8
 #endif
 #ifndef NORI_REFILL_MIN
-#define NORI_REFILL_MIN 4
+#define NORI_REFILL_MIN 8
 #endif
 enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
