@@ -117,6 +117,9 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 //   * the stepping loop (smRun) costs two ballots per step; publishing answers and refilling lanes from
 //     the warp's slot chunk happens only once NORI_REFILL_MIN lanes are out of work, so short rays do
 //     not wait for the longest ray of the warp and long rays do not pay for the bookkeeping.
+#ifndef NORI_LEAF_BURST
+#define NORI_LEAF_BURST 4
+#endif
 #ifndef NORI_LEAF_MIN
 #define NORI_LEAF_MIN 8
 #endif
@@ -249,7 +252,13 @@ __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2
         const uint32_t mWork = mNode | mLeaf;
         if (!mWork || (canRefill && __popc(mWork) <= 32 - NORI_REFILL_MIN)) return;
         if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
-            if (L.st == ST_LEAF) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+            if (L.st == ST_LEAF) {
+                const uint32_t leafEnd = L.leafEnd;                  // up to NORI_LEAF_BURST primitives of THIS leaf per step
+                smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+#pragma unroll 1
+                for (int k = 1; k < NORI_LEAF_BURST; ++k)
+                    if (L.st == ST_LEAF && L.leafEnd == leafEnd && L.leafI > 0) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+            }
         } else {
             if (L.st == ST_NODE) smNode2<COUNT>(sc, L, stack, cnt);
         }
