@@ -6,6 +6,7 @@
 
 #define NORI_Q_MISS NORI_BSDF_COUNT          // volumetric only: rays that left the scene may still scatter in the medium
 #define NORI_NQ (NORI_BSDF_COUNT + 1)
+#define NORI_NEQ (NORI_BSDF_COUNT * 4)     // (bsdf type, emitter type) keys of the emitter-sorted queues
 
 enum { PF_ALIVE = 1u, PF_SHADOW = 2u, PF_TERMINATE = 4u, PF_FIRST = 8u, PF_DISCRETE = 16u,
        PF_CH_SHIFT = 8u, PF_CH_MASK = 3u << 8 };     // colour channel of the current camera path (chromatic aberration)

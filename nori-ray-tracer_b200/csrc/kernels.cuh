@@ -32,6 +32,7 @@ struct Pool {
     uint32_t *sid;            // sample id inside the batch, NORI_FREE_SLOT when the slot is free
     uint32_t *flags;          // PF_*
     uint32_t *queue[NORI_NQ];
+    uint32_t *equeue;         // emitter-sorted mode: NORI_NEQ sub-queues of P entries each (key = bsdf type * 4 + emitter type), or NULL
     uint32_t P;
 };
 
@@ -42,6 +43,7 @@ struct Counters {
     // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
     // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
     uint32_t qcount[2][NORI_NQ];
+    uint32_t eqcount[2][NORI_NEQ];            // emitter-sorted mode: entries per (bsdf type, emitter type)
     uint32_t work_extend[2], work_shadow[2];
 };
 
@@ -122,5 +124,6 @@ void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc,
 int noriShadowSmOccupancy(bool count, bool childBoxLayout);
 void noriLaunchShadeMis(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchDrain(bool mis, bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr);
 void noriLaunchMega(bool count, unsigned grid, cudaStream_t st, const DScene &sc, const Batch &bt, Counters *ctr, unsigned long long total);

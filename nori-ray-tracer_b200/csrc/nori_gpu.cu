@@ -42,6 +42,8 @@ struct nori_gpu_ctx {
 
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_emitter_sort = 1;      // path_mis with emitters of several types: (material, emitter type)-sorted shading queues
+    uint32_t n_emitter_types = 0; bool has_envmap = false;
     int64_t opt_film_sep = 1;          // radius-2 filters: film kernel with per-sample tabulated weights (0: generic kernel)
     int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
@@ -187,6 +189,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
+    else if (k == "emitter_sort") { REQUIRE(value >= 0 && value <= 2, "emitter_sort must be 0 (off), 1 (auto) or 2 (always)"); ctx->opt_emitter_sort = value; }
     else if (k == "film_sep") ctx->opt_film_sep = value != 0;
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
@@ -309,8 +312,10 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     }
     // ---- emitters
     std::vector<DEmitter> ems(s->n_emitters);
+    uint32_t emitterTypeMask = 0;
     for (uint32_t i = 0; i < s->n_emitters; ++i) {
         ems[i].pod = s->emitters[i];
+        if (s->emitters[i].type >= 0 && s->emitters[i].type < 4) emitterTypeMask |= 1u << s->emitters[i].type;
         nori_gpu_emitter &e = ems[i].pod;
         REQUIRE(e.type >= 0 && e.type <= NORI_EMITTER_ENVMAP, "upload_scene: unknown emitter type");
         if (e.type == NORI_EMITTER_AREA || e.type == NORI_EMITTER_ENVMAP)
@@ -384,16 +389,18 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
         ctx->film_cap = nf;
     }
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
-    ctx->has_scene = true; ctx->has_perlin = hasPerlin;
+    ctx->has_scene = true; ctx->has_perlin = hasPerlin; ctx->n_emitter_types = (uint32_t) __builtin_popcount(emitterTypeMask);
+    ctx->has_envmap = (emitterTypeMask >> NORI_EMITTER_ENVMAP) & 1u;
     return 0;
 }
 
 } // extern "C"
 
-static int ensurePool(nori_gpu_ctx *ctx, bool deferShadow) {
+static int ensurePool(nori_gpu_ctx *ctx, bool deferShadow, bool esort) {
     const nori_gpu_camera &cam = ctx->ds.camera;
     const bool chroma = cam.type == NORI_CAMERA_ADVANCED && !(cam.chromatic[0] == 0.f && cam.chromatic[1] == 0.f && cam.chromatic[2] == 0.f);
-    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty() && (!deferShadow || ctx->pool.shD) && (!chroma || ctx->pool.acc)) return 0;
+    if (ctx->pool.P == (uint32_t) ctx->opt_pool && !ctx->pool_allocs.empty() && (!deferShadow || ctx->pool.shD) && (!chroma || ctx->pool.acc)
+        && (!esort || ctx->pool.equeue)) return 0;
     freeAll(ctx->pool_allocs);
     Pool p{}; p.P = (uint32_t) ctx->opt_pool;
     auto alloc = [&](size_t bytes) -> void * { void *d = nullptr; if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr; ctx->pool_allocs.push_back(d); return d; };
@@ -403,6 +410,7 @@ static int ensurePool(nori_gpu_ctx *ctx, bool deferShadow) {
         if (!chroma && pp == &p.acc) continue; *pp = (float4 *) alloc(p.P * sizeof(float4)); REQUIRE(*pp, "out of device memory (pool)"); }
     p.rng = (uint64_t *) alloc(p.P * sizeof(uint64_t)); p.sid = (uint32_t *) alloc(p.P * 4); p.flags = (uint32_t *) alloc(p.P * 4);
     REQUIRE(p.rng && p.sid && p.flags, "out of device memory (pool)");
+    if (esort) { p.equeue = (uint32_t *) alloc((size_t) NORI_NEQ * p.P * 4); REQUIRE(p.equeue, "out of device memory (emitter-sorted queues)"); }
     for (int t = 0; t < NORI_NQ; ++t) { p.queue[t] = (uint32_t *) alloc(p.P * 4); REQUIRE(p.queue[t], "out of device memory (queues)"); }
     k_fill_u32<<<(p.P + 255) / 256, 256, 0, ctx->stream>>>(p.sid, NORI_FREE_SLOT, p.P);
     CK(cudaMemsetAsync(p.flags, 0, p.P * 4, ctx->stream));
@@ -440,7 +448,11 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const int mode = integ == NORI_INTEGRATOR_PATH_MIS ? MODE_MIS : integ == NORI_INTEGRATOR_PATH_MATS ? MODE_MATS : MODE_VOL;
     // NEE shadow rays: traced inside k_shade on small scenes, by their own state-machine pass on deep trees
     const bool defer = mode == MODE_MIS && (ctx->opt_shadow_pass == 1 || (ctx->opt_shadow_pass == 0 && sm && ctx->ds.n_prims > (1u << 18)));
-    if (ensurePool(ctx, defer)) return 1;
+    // emitter-sorted queues pay off when lanes would otherwise diverge between a cheap and an expensive light
+    // (environment map: two binary searches + trigonometry); option 2 forces them for any mix of types
+    const bool esort = mode == MODE_MIS && ctx->n_emitter_types > 1 && (ctx->opt_emitter_sort == 2 || (ctx->opt_emitter_sort == 1 && ctx->has_envmap));
+    ctx->ds.esort = esort ? 1 : 0;
+    if (ensurePool(ctx, defer, esort)) return 1;
     // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
     Counters zero{}; zero.total_samples = total;
     *ctx->h_ctr = zero;
@@ -457,6 +469,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
             LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
+            if (esort) LAUNCH(NORI_K_GENERATE, noriLaunchRebin(sms * 4, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             if (defer) {
                 LAUNCH(NORI_K_SHADE, noriLaunchShadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
                 LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));

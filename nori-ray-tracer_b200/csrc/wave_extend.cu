@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        for (int i = 0; i < NORI_NEQ; ++i) ctr->eqcount[par ^ 1u][i] = 0;
         ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
     uint32_t *freeList = s_free[warp];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int i = 0; i < NORI_NQ; ++i) ctr->qcount[par ^ 1u][i] = 0;
+        for (int i = 0; i < NORI_NEQ; ++i) ctr->eqcount[par ^ 1u][i] = 0;
         ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;

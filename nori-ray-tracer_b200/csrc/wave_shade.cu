@@ -67,30 +67,45 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
-template <int MODE, bool COUNT, bool DEFER>
+template <int MODE, bool COUNT, bool DEFER, bool ESORT>
 __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
-    uint32_t off[NORI_NQ + 1]; off[0] = 0;
+    // work list = the concatenated queues: by material (NQ queues), or -- ESORT: path_mis with emitters of several
+    // types, after k_rebin -- by (material, emitter type), so that the lanes of a warp also sample the same kind of light
+    constexpr int NQ = ESORT ? NORI_NEQ : NORI_NQ;
+    uint32_t off[NQ + 1]; off[0] = 0;
 #pragma unroll
-    for (int t = 0; t < NORI_NQ; ++t) off[t + 1] = off[t] + ctr->qcount[it & 1u][t];
-    const uint32_t n = off[NORI_NQ];
+    for (int t = 0; t < NQ; ++t) off[t + 1] = off[t] + (ESORT ? ctr->eqcount[it & 1u][t] : ctr->qcount[it & 1u][t]);
+    const uint32_t n = off[NQ];
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 #if NORI_SHADE_TEMPLATED && NORI_SHADE_MODE != 2
-        if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
-        else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
-        else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
-        else if constexpr (MODE == MODE_VOL) shadeSlot<NORI_Q_MISS, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[NORI_Q_MISS][i - off[5]], nDone, nShadow, nClosest, cnt);
+        if constexpr (ESORT) {
+            int k = 0;
+#pragma unroll
+            for (int t = 1; t < NQ; ++t) k += i >= off[t];
+            const uint32_t slot = pool.equeue[(size_t) k * pool.P + (i - off[k])];
+            const int q = k >> 2;
+            if (q == NORI_BSDF_DIFFUSE) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_MIRROR) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_DIELECTRIC) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_MICROFACET) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        } else {
+            if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
+            else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
+        }
 #else
-        // ONE copy of the vertex code for every material: the BSDF's eval / pdf / sample are reached through
-        // a switch on the BSDF type, which is warp-uniform because the queues are sorted by type.  (A copy
-        // of the whole vertex per BSDF type made the kernel 0.5 MB of SASS and instruction-fetch bound.)
+        // ONE copy of the vertex code for every material: the BSDF's eval / pdf / sample are reached through a
+        // switch on the BSDF type, which is warp-uniform because the queues are sorted by type (volumetric mode:
+        // a copy per BSDF type and vertex kind made the kernel instruction-fetch bound)
         int q = 0;
 #pragma unroll
-        for (int t = 1; t < NORI_NQ; ++t) q += i >= off[t];
-        const uint32_t slot = pool.queue[q][i - off[q]];
+        for (int t = 1; t < NQ; ++t) q += i >= off[t];
+        const uint32_t slot = ESORT ? pool.equeue[(size_t) q * pool.P + (i - off[q])] : pool.queue[q][i - off[q]];
         shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
 #endif
     }
@@ -108,12 +123,57 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 #define LAUNCHER noriLaunchShadeVol
 #endif
 void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    if (count) k_shade<NORI_SHADE_MODE, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<NORI_SHADE_MODE, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+#if NORI_SHADE_MODE == 1
+    if (sc.esort) {
+        if (count) k_shade<MODE_MIS, true, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        return;
+    }
+#endif
+    if (count) k_shade<NORI_SHADE_MODE, true, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<NORI_SHADE_MODE, false, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #if NORI_SHADE_MODE == 1
+// Emitter-sorted shading queues.  The light a path_mis vertex samples is picked by the FIRST random number of the
+// vertex (path_mis.cpp:42), so it can be peeked from the path's stream before shading.  k_rebin splits every
+// material queue k_extend built into (material, emitter type) sub-queues, one warp-aggregated atomic per
+// distinct key (__match_any_sync).  Only launched when the scene has emitters of several types.
+__global__ void __launch_bounds__(256) k_rebin(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    const uint32_t par = it & 1u, lane = threadIdx.x & 31;
+    uint32_t off[NORI_BSDF_COUNT + 1]; off[0] = 0;
+#pragma unroll
+    for (int t = 0; t < NORI_BSDF_COUNT; ++t) off[t + 1] = off[t] + ctr->qcount[par][t];
+    const uint32_t n = off[NORI_BSDF_COUNT];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {      // warp-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        uint32_t key = 0xffffffffu, slot = 0;
+        if (i < n) {
+            int q = 0;
+#pragma unroll
+            for (int t = 1; t < NORI_BSDF_COUNT; ++t) q += i >= off[t];
+            slot = pool.queue[q][i - off[q]];
+            Pcg32 peek; peek.state = pool.rng[slot]; peek.inc = ((uint64_t) (pool.sid[slot] % bt.wh) << 1u) | 1u;
+            key = (uint32_t) q * 4u + (uint32_t) sc.emitters[randomEmitter(sc, peek.next1D())].pod.type;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if ((int) lane == leader && key != 0xffffffffu) pos = atomicAdd(&ctr->eqcount[par][key], (uint32_t) __popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (key != 0xffffffffu) pool.equeue[(size_t) key * pool.P + pos + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+}
+void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    k_rebin<<<grid, 256, 0, st>>>(sc, pool, bt, ctr, it);
+}
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    if (count) k_shade<MODE_MIS, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<MODE_MIS, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    if (sc.esort) {
+        if (count) k_shade<MODE_MIS, true, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        return;
+    }
+    if (count) k_shade<MODE_MIS, true, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<MODE_MIS, false, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #endif
