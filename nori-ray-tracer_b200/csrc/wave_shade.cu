@@ -64,11 +64,14 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 #ifndef NORI_SHADE_TEMPLATED
 #define NORI_SHADE_TEMPLATED 0
 #endif
+#ifndef NORI_SHADE_THREADS
+#define NORI_SHADE_THREADS 128
+#endif
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
 template <int MODE, bool COUNT, bool DEFER, bool ESORT>
-__global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+__global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     // work list = the concatenated queues: by material (NQ queues), or -- ESORT: path_mis with emitters of several
     // types, after k_rebin -- by (material, emitter type), so that the lanes of a warp also sample the same kind of light
     constexpr int NQ = ESORT ? NORI_NEQ : NORI_NQ;
@@ -125,13 +128,13 @@ __global__ void __launch_bounds__(128, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, 
 void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
 #if NORI_SHADE_MODE == 1
     if (sc.esort) {
-        if (count) k_shade<MODE_MIS, true, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-        else k_shade<MODE_MIS, false, false, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        if (count) k_shade<MODE_MIS, true, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
         return;
     }
 #endif
-    if (count) k_shade<NORI_SHADE_MODE, true, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<NORI_SHADE_MODE, false, false, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    if (count) k_shade<NORI_SHADE_MODE, true, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<NORI_SHADE_MODE, false, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #if NORI_SHADE_MODE == 1
 // Emitter-sorted shading queues.  The light a path_mis vertex samples is picked by the FIRST random number of the
@@ -169,11 +172,11 @@ void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &po
 }
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
     if (sc.esort) {
-        if (count) k_shade<MODE_MIS, true, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-        else k_shade<MODE_MIS, false, true, true><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+        if (count) k_shade<MODE_MIS, true, true, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, true, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
         return;
     }
-    if (count) k_shade<MODE_MIS, true, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<MODE_MIS, false, true, false><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+    if (count) k_shade<MODE_MIS, true, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<MODE_MIS, false, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #endif
