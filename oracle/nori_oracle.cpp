@@ -12,7 +12,7 @@
  * dot(a,b) = a0*b0 + (a1*b1 + a2*b2)  (Redux.h redux_novec_unroller), cross as OrthoMethods.h:36-38,
  * normalized() = v / sqrt(squaredNorm) with true division (Dot.h:114-120).
  *
- * Pinning (see tests/test_oracle_vs_reference.py, tests/golden/):
+ * Pinning (see tests/test_oracle_golden.py, tests/golden/):
  *   - traversal: bit-exact (t,u,v,shape,prim,#nodes,#prims) against ray batches answered by the real
  *     reference (oracle/_ref/nori_export);
  *   - pcg32: ext/pcg32/pcg32-demo.out known answers;
