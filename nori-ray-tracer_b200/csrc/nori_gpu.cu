@@ -447,7 +447,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const bool sm = ctx->opt_traversal == 2 || (ctx->opt_traversal == 0 && ctx->ds.n_prims > 4096);
     const int mode = integ == NORI_INTEGRATOR_PATH_MIS ? MODE_MIS : integ == NORI_INTEGRATOR_PATH_MATS ? MODE_MATS : MODE_VOL;
     // NEE shadow rays: traced inside k_shade on small scenes, by their own state-machine pass on deep trees
-    const bool defer = mode == MODE_MIS && (ctx->opt_shadow_pass == 1 || (ctx->opt_shadow_pass == 0 && sm && ctx->ds.n_prims > (1u << 18)));
+    const bool defer = mode == MODE_MIS && (ctx->opt_shadow_pass == 1 || (ctx->opt_shadow_pass == 0 && sm));
     // emitter-sorted queues pay off when lanes would otherwise diverge between a cheap and an expensive light
     // (environment map: two binary searches + trigonometry); option 2 forces them for any mix of types
     const bool esort = mode == MODE_MIS && ctx->n_emitter_types > 1 && (ctx->opt_emitter_sort == 2 || (ctx->opt_emitter_sort == 1 && ctx->has_envmap));

@@ -9,6 +9,8 @@ for arg in sys.argv[1:]:
     name, w, h, spp = arg.split(':'); w, h, spp = int(w), int(h), int(spp)
     sc = nscene.load_scene(f'tests/golden/{name}.nscene'); sc.set_resolution(w, h)
     g.upload_scene(sc); g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '2')))
+    if 'NORI_SHADOW_PASS' in os.environ: g.set_option('shadow_pass', int(os.environ['NORI_SHADOW_PASS']))
+    if 'NORI_TRAVERSAL' in os.environ: g.set_option('traversal', int(os.environ['NORI_TRAVERSAL']))
     if 'NORI_DRAIN' in os.environ: g.set_option('drain', int(os.environ['NORI_DRAIN']))
     g.render(0, 4, seed=1)
     g.set_option('stats', 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); s0 = g.stats(); g.set_option('stats', 0)
