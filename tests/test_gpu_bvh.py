@@ -77,3 +77,55 @@ def test_lbvh_render_matches_sah_render(gpu):
         imgs.append(got)
     differ = (np.abs(imgs[0] - imgs[1]).max(-1) > 0).mean()        # same paths unless a tie resolved differently somewhere
     assert differ < 2e-3, differ
+
+
+def _soup(seed, n_tri=3000, degenerate=True):
+    """A seeded triangle soup with the cases real meshes contain: slivers, zero-area and duplicated triangles,
+    axis-aligned (flat-box) triangles, very different scales, plus a few spheres."""
+    rng = np.random.RandomState(seed)
+    c = rng.rand(n_tri, 1, 3).astype(np.float32) * 4 - 2
+    V = (c + (rng.rand(n_tri, 3, 3).astype(np.float32) - 0.5) * rng.choice([0.02, 0.2, 1.0], (n_tri, 1, 1)).astype(np.float32))
+    if degenerate:
+        V[0:20, 2] = V[0:20, 1]                                   # zero area: two equal vertices
+        V[20:40, :, 2] = np.float32(0.5)                          # axis-aligned: flat bounding boxes
+        V[40:60] = V[60:80]                                       # exact duplicates (ties at equal t)
+        V[80:90, 1] = V[80:90, 0] + np.float32(1e-7)              # slivers
+    V = V.reshape(-1, 3)
+    F = np.arange(3 * n_tri, dtype=np.uint32).reshape(-1, 3)
+    sb = host_scene.SceneBuilder("normals")
+    d = sb.diffuse((0.5, 0.5, 0.5))
+    sb.add_mesh(V[: 3 * (n_tri // 2)], F[: n_tri // 2], d)
+    sb.add_mesh(V[3 * (n_tri // 2):], F[: n_tri - n_tri // 2], d)
+    for k in range(5):
+        sb.add_sphere(rng.rand(3) * 3 - 1.5, 0.1 + 0.3 * rng.rand(), d)
+    sb.perspective(64, 48, 40.0, origin=(0, -6, 1), target=(0, 0, 0), up=(0, 0, 1))
+    return sb
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_soups_trace_like_the_oracle(seed, gpu, make_oracle):
+    """Host SAH builder and GPU LBVH builder on random geometry incl. degenerate triangles: the GPU traversal
+    equals the oracle's on the same tree bit for bit (reference child order: counters too; near child first: hits),
+    and both trees give the same closest distances."""
+    sb = _soup(seed)
+    sah = sb.build()
+    lb, _ = host_scene.rebuild_bvh(sah, "lbvh", leaf_size=1 + seed)
+    _check_structure(lb)
+    rays = _rays(sah, 20000, 100 + seed)
+    ts = []
+    for sc in (sah, lb):
+        o = make_oracle(sc)
+        gpu.upload_scene(sc)
+        for order in (0, 1):
+            gpu.set_option("order", order)
+            for shadow in (0, 1):
+                got, want = gpu.trace(rays, shadow), o.trace(rays, shadow)
+                fields = ("t",) if shadow else ("t", "u", "v", "shape", "prim")
+                if order == 0:
+                    fields += ("nodes_visited", "prims_tested")
+                for f in fields:
+                    assert np.array_equal(got[f], want[f]), (seed, order, shadow, f, int((got[f] != want[f]).sum()))
+                if not shadow and order == 0:
+                    ts.append(got["t"])
+        gpu.set_option("order", 2)
+    assert np.array_equal(ts[0], ts[1])
