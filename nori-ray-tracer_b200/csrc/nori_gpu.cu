@@ -469,7 +469,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
             LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            if (esort) LAUNCH(NORI_K_GENERATE, noriLaunchRebin(sms * 4, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            if (esort) LAUNCH(NORI_K_GENERATE, noriLaunchRebin((int) ((ctx->pool.P + 1023u) / 1024u), ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             if (defer) {
                 LAUNCH(NORI_K_SHADE, noriLaunchShadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
                 LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));

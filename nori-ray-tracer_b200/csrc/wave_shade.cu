@@ -141,34 +141,40 @@ void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Poo
 // vertex (path_mis.cpp:42), so it can be peeked from the path's stream before shading.  k_rebin splits every
 // material queue k_extend built into (material, emitter type) sub-queues, one warp-aggregated atomic per
 // distinct key (__match_any_sync).  Only launched when the scene has emitters of several types.
-__global__ void __launch_bounds__(256) k_rebin(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+__global__ void __launch_bounds__(1024) k_rebin(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+    // one work item per thread; counts are aggregated per warp (match_any) and per CTA (shared memory) so that
+    // each CTA issues one global atomic per key: with one atomic per warp the ~20 hot counters serialised the pass
+    __shared__ uint32_t s_cnt[NORI_NEQ], s_base[NORI_NEQ];
     const uint32_t par = it & 1u, lane = threadIdx.x & 31;
     uint32_t off[NORI_BSDF_COUNT + 1]; off[0] = 0;
 #pragma unroll
     for (int t = 0; t < NORI_BSDF_COUNT; ++t) off[t + 1] = off[t] + ctr->qcount[par][t];
     const uint32_t n = off[NORI_BSDF_COUNT];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {      // warp-uniform trip count
-        const uint32_t i = base + threadIdx.x;
-        uint32_t key = 0xffffffffu, slot = 0;
-        if (i < n) {
-            int q = 0;
+    if (blockIdx.x * blockDim.x >= n) return;                             // whole CTA past the end
+    if (threadIdx.x < NORI_NEQ) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key = 0xffffffffu, slot = 0;
+    if (i < n) {
+        int q = 0;
 #pragma unroll
-            for (int t = 1; t < NORI_BSDF_COUNT; ++t) q += i >= off[t];
-            slot = pool.queue[q][i - off[q]];
-            Pcg32 peek; peek.state = pool.rng[slot]; peek.inc = ((uint64_t) (pool.sid[slot] % bt.wh) << 1u) | 1u;
-            key = (uint32_t) q * 4u + (uint32_t) sc.emitters[randomEmitter(sc, peek.next1D())].pod.type;
-        }
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(peers) - 1;
-        uint32_t pos = 0;
-        if ((int) lane == leader && key != 0xffffffffu) pos = atomicAdd(&ctr->eqcount[par][key], (uint32_t) __popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (key != 0xffffffffu) pool.equeue[(size_t) key * pool.P + pos + __popc(peers & ((1u << lane) - 1u))] = slot;
+        for (int t = 1; t < NORI_BSDF_COUNT; ++t) q += i >= off[t];
+        slot = pool.queue[q][i - off[q]];
+        Pcg32 peek; peek.state = pool.rng[slot]; peek.inc = ((uint64_t) (pool.sid[slot] % bt.wh) << 1u) | 1u;
+        key = (uint32_t) q * 4u + (uint32_t) sc.emitters[randomEmitter(sc, peek.next1D())].pod.type;
     }
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t pos = 0;
+    if ((int) lane == leader && key != 0xffffffffu) pos = atomicAdd(&s_cnt[key], (uint32_t) __popc(peers));
+    pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x < NORI_NEQ && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&ctr->eqcount[par][threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (key != 0xffffffffu) pool.equeue[(size_t) key * pool.P + s_base[key] + pos] = slot;
 }
 void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    k_rebin<<<grid, 256, 0, st>>>(sc, pool, bt, ctr, it);
+    k_rebin<<<grid, 1024, 0, st>>>(sc, pool, bt, ctr, it);
 }
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
     if (sc.esort) {
