@@ -2,6 +2,9 @@
 // regeneration and material binning (see kernels.cuh for the overview).
 #include "kernels.cuh"
 
+#ifndef NORI_EXTEND_PIPELINE
+#define NORI_EXTEND_PIPELINE 0
+#endif
 #define NORI_FETCH 256u      // pool slots claimed per warp per atomic (8 rounds of 32)
 
 // ------------------------------------------------------------------------------ extend (+ regeneration)
@@ -77,11 +80,27 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
             __syncwarp();
         }
         // ---- phase 2: trace; the material of every hit is parked in the warp's shared list (free again after phase 1)
+#if NORI_EXTEND_PIPELINE
+        // software pipeline: the next round's flags and ray are requested before this round is traversed
+        uint32_t nfl = (base + lane) < pool.P ? pool.flags[base + lane] : 0u;
+        float4 nro = make_float4(0.f, 0.f, 0.f, 0.f), nrd = nro;
+        if (nfl & PF_ALIVE) { nro = pool.rayO[base + lane]; nrd = pool.rayD[base + lane]; }
+#endif
         for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
             const uint32_t slot = base + round * 32u + lane;
             int type = -1;
+#if NORI_EXTEND_PIPELINE
+            const uint32_t fl = nfl; const float4 ro = nro, rd = nrd;
+            if (round + 1 < NORI_FETCH / 32u) {
+                const uint32_t ns = slot + 32u;
+                nfl = ns < pool.P ? pool.flags[ns] : 0u;
+                if (nfl & PF_ALIVE) { nro = pool.rayO[ns]; nrd = pool.rayD[ns]; }
+            }
+            if (fl & PF_ALIVE) {
+#else
             if (slot < pool.P && (pool.flags[slot] & PF_ALIVE)) {
                 const float4 ro = pool.rayO[slot], rd = pool.rayD[slot];
+#endif
                 Hit h; ++nRays;
                 if (traverse<false, COUNT>(sc, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, h, cnt)) {
                     pool.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.leafpos));
