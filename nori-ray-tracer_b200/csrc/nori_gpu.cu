@@ -332,6 +332,27 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             if (devUpload(ctx, ctx->scene_allocs, h.env_cmarginal, R + 1, &e.env_cmarginal)) return 1;
         } else { e.env_image = e.env_pdf = e.env_cdf = e.env_pmarginal = e.env_cmarginal = nullptr; }
     }
+    // ---- the tree must be one the traversal can walk: children and leaf ranges in range, and no deeper than the
+    // 64-entry traversal stack (the reference's own limit, bvh.cpp:405)
+    if (s->n_nodes) {
+        const uint32_t *w = (const uint32_t *) s->nodes;
+        std::vector<std::pair<uint32_t, uint32_t>> st; st.reserve(128);
+        st.push_back({0u, 1u});
+        uint32_t maxDepth = 0; uint64_t visited = 0;
+        while (!st.empty()) {
+            const uint32_t i = st.back().first, depth = st.back().second; st.pop_back();
+            ++visited;
+            REQUIRE(visited <= s->n_nodes, "upload_scene: BVH nodes do not form a tree");
+            maxDepth = std::max(maxDepth, depth);
+            const uint32_t w0 = w[8 * (size_t) i], w1 = w[8 * (size_t) i + 1];
+            if (w0 & 1u) REQUIRE((uint64_t) w1 + (w0 >> 1) <= s->n_indices, "upload_scene: BVH leaf range out of bounds");
+            else {
+                REQUIRE(i + 1 < s->n_nodes && w1 > i && w1 < s->n_nodes, "upload_scene: BVH child index out of range");
+                st.push_back({w1, depth + 1}); st.push_back({i + 1, depth + 1});
+            }
+        }
+        REQUIRE(maxDepth <= 64, "upload_scene: BVH deeper than the 64-entry traversal stack (bvh.cpp:405)");
+    }
     // ---- child-box layout for the large-scene kernels (wave_extend.cu): one 64-byte record per inner node
     // with both children's boxes and references.  Built only when every leaf fits the reference encoding.
     std::vector<uint4> nodes2;
