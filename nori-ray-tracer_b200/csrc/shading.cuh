@@ -335,6 +335,16 @@ static __device__ NORI_DYN V3 bsdfSampleDyn(const nori_gpu_bsdf &b, BRec &r, P2 
 }
 
 // ------------------------------------------------------------------------------ emitters
+// NORI_EMITTERS_OUT_OF_LINE: one out-of-line copy of the emitter code per kernel instead of one inline expansion
+// per call site (code size: the path_mis shade kernel is 680 KB of SASS with everything inline)
+#ifndef NORI_EMITTERS_OUT_OF_LINE
+#define NORI_EMITTERS_OUT_OF_LINE 0
+#endif
+#if NORI_EMITTERS_OUT_OF_LINE
+#define NORI_EMITTER_FN static __device__ __noinline__
+#else
+#define NORI_EMITTER_FN __device__ __forceinline__
+#endif
 struct ERec { V3 ref, p, n, wi; float pdf; Ray shadow; };        // emitter.h:31-59
 __device__ __forceinline__ ERec makeERec(V3 ref, V3 p, V3 n) {
     ERec e; e.ref = ref; e.p = p; e.n = n; e.wi = normalized(p - ref); e.pdf = 0.f; return e;
@@ -403,7 +413,7 @@ __device__ __forceinline__ P2 envMapIntersect(const nori_gpu_emitter &e, V3 vec)
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
-__device__ __forceinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+NORI_EMITTER_FN V3 emitterEval(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
     switch (e.type) {
     case NORI_EMITTER_AREA:                                       // arealight.cpp:39-44
         return dot(l.n, -l.wi) > 0.0f ? arr3(e.radiance) : mk(0.f);
@@ -428,7 +438,7 @@ __device__ __forceinline__ V3 emitterEval(const DScene &sc, const nori_gpu_emitt
     }
 }
 
-__device__ __forceinline__ float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
+NORI_EMITTER_FN float emitterPdf(const DScene &sc, const nori_gpu_emitter &e, const ERec &l) {
     switch (e.type) {
     case NORI_EMITTER_AREA: return dot(l.n, -l.wi) > 0.0f ? pdfSurface(sc.shapes[e.shape], l.p) : 0.0f;   // arealight.cpp:64-76
     case NORI_EMITTER_POINT: return 1.0f;                         // pointlight.cpp:30-33
@@ -461,7 +471,7 @@ __device__ __forceinline__ void envSample1D(const float *pfRow, const float *PfR
     prob = __ldg(&pfRow[i]);
 }
 
-__device__ __forceinline__ V3 emitterSample(const DScene &sc, const nori_gpu_emitter &e, ERec &l, P2 s) {
+NORI_EMITTER_FN V3 emitterSample(const DScene &sc, const nori_gpu_emitter &e, ERec &l, P2 s) {
     switch (e.type) {
     case NORI_EMITTER_AREA: {                                     // arealight.cpp:46-62
         float spdf;
