@@ -37,7 +37,7 @@ template <int BSDF> __device__ __forceinline__ V3 sampleT(const nori_gpu_bsdf &b
 // PathMatsIntegrator::Li (path_mats.cpp:23-55; MIS=false) at a surface hit.  On return
 // st.flags has PF_TERMINATE (Russian roulette ended the path) or PF_ALIVE (out.next is the new
 // ray); PF_SHADOW is set when out.shadow / out.contrib are valid.
-template <int BSDF, bool MIS>
+template <int BSDF, bool MIS, bool AO = false>
 __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, PathState &st, VertexOut &out) {
     Its its; hitInfo(sc, st.o, st.d, hit, its);
     const DShape &shp = sc.shapes[its.shape];
@@ -50,10 +50,10 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
         ERec e = makeERec(st.o, its.p, its.sh.n);
         float w_mats = 1.0f;
         if (MIS && !(inFlags & (PF_FIRST | PF_DISCRETE))) {
-            float pdf_em = emitterPdf(sc, em, e);
+            float pdf_em = emitterPdf<AO>(sc, em, e);
             w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
         }
-        V3 Le = emitterEval(sc, em, e);
+        V3 Le = emitterEval<AO>(sc, em, e);
         st.rad = st.rad + (MIS ? st.thr * w_mats * Le : st.thr * Le);
     }
 
@@ -61,8 +61,8 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
     if (MIS) {                                                     // path_mis.cpp:42-61
         const nori_gpu_emitter &light = sc.emitters[randomEmitter(sc, st.rng.next1D())].pod;
         ERec e = makeERec(its.p);
-        V3 Li = emitterSample(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
-        float pdf_em = emitterPdf(sc, light, e);
+        V3 Li = emitterSample<AO>(sc, light, e, st.rng.next2D()) * (float) sc.n_emitters;
+        float pdf_em = emitterPdf<AO>(sc, light, e);
         V3 woLocal = toLocal(its.sh, e.wi);
         float theta = fmaxf(0.0f, woLocal.z);
         BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, its.uv); b.wo = woLocal;

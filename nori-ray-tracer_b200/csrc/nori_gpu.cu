@@ -43,7 +43,8 @@ struct nori_gpu_ctx {
     // options
     int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
     int64_t opt_emitter_sort = 1;      // path_mis with emitters of several types: (material, emitter type)-sorted shading queues
-    uint32_t n_emitter_types = 0; bool has_envmap = false;
+    uint32_t n_emitter_types = 0, emitter_type_mask = 0; bool has_envmap = false;
+    int64_t opt_area_only = 1;         // scenes lit by area lights only: shade kernels compiled without the other emitter types
     int64_t opt_film_sep = 1;          // radius-2 filters: film kernel with per-sample tabulated weights (0: generic kernel)
     int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
@@ -189,6 +190,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
+    else if (k == "area_only") ctx->opt_area_only = value != 0;
     else if (k == "emitter_sort") { REQUIRE(value >= 0 && value <= 2, "emitter_sort must be 0 (off), 1 (auto) or 2 (always)"); ctx->opt_emitter_sort = value; }
     else if (k == "film_sep") ctx->opt_film_sep = value != 0;
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
@@ -411,7 +413,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     }
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
     ctx->has_scene = true; ctx->has_perlin = hasPerlin; ctx->n_emitter_types = (uint32_t) __builtin_popcount(emitterTypeMask);
-    ctx->has_envmap = (emitterTypeMask >> NORI_EMITTER_ENVMAP) & 1u;
+    ctx->has_envmap = (emitterTypeMask >> NORI_EMITTER_ENVMAP) & 1u; ctx->emitter_type_mask = emitterTypeMask;
     return 0;
 }
 
@@ -473,6 +475,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     // (environment map: two binary searches + trigonometry); option 2 forces them for any mix of types
     const bool esort = mode == MODE_MIS && ctx->n_emitter_types > 1 && (ctx->opt_emitter_sort == 2 || (ctx->opt_emitter_sort == 1 && ctx->has_envmap));
     ctx->ds.esort = esort ? 1 : 0;
+    ctx->ds.area_only = (ctx->opt_area_only && ctx->emitter_type_mask == (1u << NORI_EMITTER_AREA)) ? 1 : 0;
     if (ensurePool(ctx, defer, esort)) return 1;
     // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
     Counters zero{}; zero.total_samples = total;

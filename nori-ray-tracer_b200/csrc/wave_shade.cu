@@ -13,7 +13,7 @@
 // + far end; it starts at the next ray's origin with mint = Epsilon, arealight.cpp:56) together with its
 // pending contribution, and k_shadow_sm traces it with the warp state machine -- on deep trees a
 // plain per-lane loop inside this kernel leaves most lanes idle.
-template <int BSDF, int MODE, bool COUNT, bool DEFER>
+template <int BSDF, int MODE, bool COUNT, bool DEFER, bool AO>
 __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
                                           uint32_t &nDone, uint32_t &nShadow, uint32_t &nClosest, TraceCounters &cnt) {
     const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
@@ -30,7 +30,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
         volVertex<COUNT>(sc, h, st, next, nClosest, nShadow, cnt);
     } else {
         VertexOut out;
-        pathVertex<BSDF, MODE == MODE_MIS>(sc, h, st, out);
+        pathVertex<BSDF, MODE == MODE_MIS, AO>(sc, h, st, out);
         if (DEFER) {
             pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
             pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
@@ -70,7 +70,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 #ifndef NORI_SHADE_MINBLOCKS
 #define NORI_SHADE_MINBLOCKS 6
 #endif
-template <int MODE, bool COUNT, bool DEFER, bool ESORT>
+template <int MODE, bool COUNT, bool DEFER, bool ESORT, bool AO>
 __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     // work list = the concatenated queues: by material (NQ queues), or -- ESORT: path_mis with emitters of several
     // types, after k_rebin -- by (material, emitter type), so that the lanes of a warp also sample the same kind of light
@@ -89,17 +89,17 @@ __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_sh
             for (int t = 1; t < NQ; ++t) k += i >= off[t];
             const uint32_t slot = pool.equeue[(size_t) k * pool.P + (i - off[k])];
             const int q = k >> 2;
-            if (q == NORI_BSDF_DIFFUSE) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-            else if (q == NORI_BSDF_MIRROR) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-            else if (q == NORI_BSDF_DIELECTRIC) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-            else if (q == NORI_BSDF_MICROFACET) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
-            else shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            if (q == NORI_BSDF_DIFFUSE) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_MIRROR) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_DIELECTRIC) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else if (q == NORI_BSDF_MICROFACET) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+            else shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
         } else {
-            if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
-            else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
-            else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
-            else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
-            else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
+            if (i < off[1]) shadeSlot<NORI_BSDF_DIFFUSE, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, pool.queue[0][i], nDone, nShadow, nClosest, cnt);
+            else if (i < off[2]) shadeSlot<NORI_BSDF_MIRROR, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, pool.queue[1][i - off[1]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[3]) shadeSlot<NORI_BSDF_DIELECTRIC, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, pool.queue[2][i - off[2]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[4]) shadeSlot<NORI_BSDF_MICROFACET, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, pool.queue[3][i - off[3]], nDone, nShadow, nClosest, cnt);
+            else if (i < off[5]) shadeSlot<NORI_BSDF_DISNEY, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, pool.queue[4][i - off[4]], nDone, nShadow, nClosest, cnt);
         }
 #else
         // ONE copy of the vertex code for every material: the BSDF's eval / pdf / sample are reached through a
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_sh
 #pragma unroll
         for (int t = 1; t < NQ; ++t) q += i >= off[t];
         const uint32_t slot = ESORT ? pool.equeue[(size_t) q * pool.P + (i - off[q])] : pool.queue[q][i - off[q]];
-        shadeSlot<-1, MODE, COUNT, DEFER>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
+        shadeSlot<-1, MODE, COUNT, DEFER, AO>(sc, pool, bt, ctr, slot, nDone, nShadow, nClosest, cnt);
 #endif
     }
     warpAdd(&ctr->done, nDone);
@@ -127,14 +127,19 @@ __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_sh
 #endif
 void LAUNCHER(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
 #if NORI_SHADE_MODE == 1
+    if (sc.area_only) {
+        if (count) k_shade<MODE_MIS, true, false, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, false, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        return;
+    }
     if (sc.esort) {
-        if (count) k_shade<MODE_MIS, true, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
-        else k_shade<MODE_MIS, false, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        if (count) k_shade<MODE_MIS, true, false, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, false, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
         return;
     }
 #endif
-    if (count) k_shade<NORI_SHADE_MODE, true, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<NORI_SHADE_MODE, false, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    if (count) k_shade<NORI_SHADE_MODE, true, false, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<NORI_SHADE_MODE, false, false, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #if NORI_SHADE_MODE == 1
 // Emitter-sorted shading queues.  The light a path_mis vertex samples is picked by the FIRST random number of the
@@ -177,12 +182,17 @@ void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &po
     k_rebin<<<grid, 1024, 0, st>>>(sc, pool, bt, ctr, it);
 }
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    if (sc.esort) {
-        if (count) k_shade<MODE_MIS, true, true, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
-        else k_shade<MODE_MIS, false, true, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    if (sc.area_only) {
+        if (count) k_shade<MODE_MIS, true, true, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, true, false, true><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
         return;
     }
-    if (count) k_shade<MODE_MIS, true, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
-    else k_shade<MODE_MIS, false, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    if (sc.esort) {
+        if (count) k_shade<MODE_MIS, true, true, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        else k_shade<MODE_MIS, false, true, true, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+        return;
+    }
+    if (count) k_shade<MODE_MIS, true, true, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
+    else k_shade<MODE_MIS, false, true, false, false><<<grid * 128 / NORI_SHADE_THREADS, NORI_SHADE_THREADS, 0, st>>>(sc, pool, bt, ctr, it);
 }
 #endif
