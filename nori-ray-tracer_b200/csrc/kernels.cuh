@@ -117,11 +117,12 @@ enum { MODE_MATS = 0, MODE_MIS = 1, MODE_VOL = 2 };
 // ---- host-side launchers; each group of kernels lives in its own translation unit so that the
 // library builds in parallel (wave_extend.cu, wave_shade.cu x3 modes, mega.cu, nori_gpu.cu)
 typedef void (*ExtendKernel)(DScene, Pool, Batch, Counters *, uint32_t);
-ExtendKernel noriPickExtend(bool stateMachine, bool count, bool vol, bool childBoxLayout);
+ExtendKernel noriPickExtend(bool stateMachine, bool count, bool vol, int layout);   // layout: 0 reference nodes, 1 child-box pairs, 2 4-wide
 void noriLaunchShadeMats(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
-int noriShadowSmOccupancy(bool count, bool childBoxLayout);
+int noriShadowSmOccupancy(bool count, int layout);
+static inline int noriSmLayout(const DScene &sc) { return sc.ordered ? (sc.wide && sc.nodes4 ? 2 : sc.nodes2 ? 1 : 0) : 0; }
 void noriLaunchShadeMis(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);

@@ -159,6 +159,16 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 #ifndef NORI_REFILL_MIN
 #define NORI_REFILL_MIN 8
 #endif
+// resident CTAs per SM asked of the compiler (register cap = 65536 / (128 * blocks)); LAY: 0 reference nodes,
+// 1 child-box pairs, 2 4-wide records
+#ifndef NORI_EXT_SM_BLOCKS4
+#define NORI_EXT_SM_BLOCKS4 8
+#endif
+#ifndef NORI_SHADOW_SM_BLOCKS4
+#define NORI_SHADOW_SM_BLOCKS4 10
+#endif
+#define NORI_EXT_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_EXT_SM_BLOCKS4 : 8)
+#define NORI_SHADOW_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_SHADOW_SM_BLOCKS4 : 10)
 enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
 struct LaneTrav {
@@ -196,9 +206,12 @@ struct LaneStack {
 #ifndef NORI_SM_STACK2
 #define NORI_SM_STACK2 16
 #endif
+// deepest stack: child-box pairs push one entry per level (<= 64 levels, checked at upload); the 4-wide layout
+// pushes up to three per level of a tree half as deep
+#define NORI_STACK2_MAX 96
 struct LaneStack2 {
     uint2 *sh;                          // &s_stack2[0][tid]; entry e at sh[e * 128]
-    uint2 ovf[64 - NORI_SM_STACK2];
+    uint2 ovf[NORI_STACK2_MAX - NORI_SM_STACK2];
     __device__ __forceinline__ void push(uint32_t sp, uint32_t ref, float nearT) {
         const uint2 v = make_uint2(ref, __float_as_uint(nearT));
         if (sp < NORI_SM_STACK2) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK2] = v;
@@ -254,6 +267,45 @@ __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack
     smPop2(L, stack);
 }
 
+// 4-wide layout (DScene::nodes4; built at upload from the reference's nodes, see nori_gpu.cu): every inner node
+// is merged with its inner children, one 128-byte record holds the boxes and references of the (up to four)
+// grandchildren -- half the dependent fetches of the child-box pairs again.  The boxes are the reference's own
+// and nested boxes give nested slab intervals (round-to-nearest is monotonic), so skipping the merged node's box
+// test does not change the set of primitives a ray can reach.
+//   record: slot k = quads 2k (min.xyz, reference of the child) and 2k+1 (max.xyz, -); slots 0,1 = the left
+//           child's children (or the left child itself, if a leaf, in slot 0), slots 2,3 = the right child's;
+//           an unused slot holds the empty-leaf reference 0x80000000 and is skipped
+//   child reference: bit 31 = leaf (as above); inner: record index in bits 30..6, split axes of the merged
+//           node, its left and its right child in bits 1..0, 3..2, 5..4
+// Visiting order: the near side of every split first (the sign rule of descend(), traverse.cuh, applied to the
+// three merged splits); slot p of the order is loaded straight from its place in the record, so the registers
+// are already in visiting order.
+template <bool COUNT>
+__device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    const uint4 *rec = &sc.nodes4[8 * (size_t) (L.cur >> 6)];
+    const uint32_t s0 = (L.neg >> (L.cur & 3u)) & 1u, sL = (L.neg >> ((L.cur >> 2) & 3u)) & 1u, sR = (L.neg >> ((L.cur >> 4) & 3u)) & 1u;
+    const uint32_t wA = s0 ? sR : sL, wB = s0 ? sL : sR;           // groups in visiting order: A = s0, B = s0 ^ 1
+    const uint4 *gA = rec + 4u * s0, *gB = rec + 4u * (s0 ^ 1u);
+    const uint4 *p0 = gA + 2u * wA, *p1 = gA + 2u * (wA ^ 1u), *p2 = gB + 2u * wB, *p3 = gB + 2u * (wB ^ 1u);
+    const uint4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
+    const uint4 a2 = __ldg(p2), b2 = __ldg(p2 + 1), a3 = __ldg(p3), b3 = __ldg(p3 + 1);
+    if (COUNT) cnt.nodes += 4;
+#define NORI_BOX4(a, b, n) (boxTest(r, make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), \
+                                   make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), n) && a.w != 0x80000000u)
+    float n0, n1, n2, n3;
+    const bool h0 = NORI_BOX4(a0, b0, n0), h1 = NORI_BOX4(a1, b1, n1), h2 = NORI_BOX4(a2, b2, n2), h3 = NORI_BOX4(a3, b3, n3);
+#undef NORI_BOX4
+    // the nearest hit slot is entered, the others wait on the stack, farthest lowest
+    uint32_t ref = 0; float nt = 0.f; bool any = false;
+    if (h3) { ref = a3.w; nt = n3; any = true; }
+    if (h2) { if (any) stack.push(r.sp++, ref, nt); ref = a2.w; nt = n2; any = true; }
+    if (h1) { if (any) stack.push(r.sp++, ref, nt); ref = a1.w; nt = n1; any = true; }
+    if (h0) { if (any) stack.push(r.sp++, ref, nt); ref = a0.w; any = true; }
+    if (any && smEnter(L, ref)) return;
+    smPop2(L, stack);
+}
+
 template <bool SHADOW, bool COUNT>
 __device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
@@ -277,7 +329,7 @@ __device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack
     smPop2(L, stack);
 }
 
-template <bool SHADOW, bool COUNT>
+template <bool SHADOW, bool COUNT, bool WIDE>
 __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt, bool canRefill) {
     while (true) {
         const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
@@ -293,18 +345,18 @@ __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2
                     if (L.st == ST_LEAF && L.leafEnd == leafEnd && L.leafI > 0) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
             }
         } else {
-            if (L.st == ST_NODE) smNode2<COUNT>(sc, L, stack, cnt);
+            if (L.st == ST_NODE) { if (WIDE) smNode4<COUNT>(sc, L, stack, cnt); else smNode2<COUNT>(sc, L, stack, cnt); }
         }
     }
 }
 
-template <bool L2>
+template <int LAY>
 __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 d, float mint, float maxt) {
     L.neg = sc.ordered ? ((d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u)) : 0u;
     if (!travInit(sc, L.r, o, d, mint, maxt)) { L.r.found = false; L.st = ST_DONE; return; }   // decided before the first node: a miss
     L.st = ST_NODE;
-    if (L2) {                                                    // the root's own box (bvh.cpp:421-423 on node 0)
-        L.cur = sc.root_ref;
+    if (LAY) {                                                   // the root's own box (bvh.cpp:421-423 on node 0)
+        L.cur = LAY == 2 ? sc.root_ref4 : sc.root_ref;
         float nearT;
         if (!boxTest(L.r, make_float3(sc.root_min[0], sc.root_min[1], sc.root_min[2]), make_float3(sc.root_max[0], sc.root_max[1], sc.root_max[2]), nearT)) L.st = ST_DONE;
     }
@@ -392,8 +444,8 @@ __device__ __forceinline__ bool smNextChunk(uint32_t *work, uint32_t P, uint32_t
     return base < P;
 }
 
-template <bool COUNT, bool VOL, bool L2>
-__global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+template <bool COUNT, bool VOL, int LAY>
+__global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -405,7 +457,7 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
     }
     const unsigned long long total = ctr->total_samples;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    __shared__ uint2 s_stack_mem[(L2 ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
+    __shared__ uint2 s_stack_mem[(LAY ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
     LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
     LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
     LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0; L.cur = 0;
@@ -476,14 +528,14 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
                 if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
                     const float4 ro = pool.rayO[s], rd = pool.rayD[s];
                     L.slot = s; ++nRays;
-                    smStart<L2>(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
+                    smStart<LAY>(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
                 }
             }
             idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        if (L2) smRun2<false, COUNT>(sc, L, stack2, cnt, canRefill); else smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
+        if (LAY) smRun2<false, COUNT, LAY == 2>(sc, L, stack2, cnt, canRefill); else smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
@@ -493,12 +545,12 @@ __global__ void __launch_bounds__(128, 8) k_extend_sm(DScene sc, Pool pool, Batc
 // Any-hit traversal (bvh.cpp:441-442) of the NEE rays k_shade<.., DEFER> left in the pool, same warp
 // state machine as k_extend_sm.  Adds the pending contribution when the ray is unoccluded
 // (path_mis.cpp:48-61) and finalises the paths the roulette ended.
-template <bool COUNT, bool L2>
-__global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+template <bool COUNT, int LAY>
+__global__ void __launch_bounds__(128, NORI_SHADOW_SM_BLOCKS(LAY)) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     const uint32_t lane = threadIdx.x & 31, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    __shared__ uint2 s_stack_mem[(L2 ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
+    __shared__ uint2 s_stack_mem[(LAY ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
     LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
     LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
     LaneTrav L; L.st = ST_IDLE; L.slot = 0; L.leafI = L.leafEnd = 0; L.neg = 0; L.cur = 0;
@@ -533,7 +585,7 @@ __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Bat
                     if (f & PF_SHADOW) {
                         const float4 so = pool.rayO[s], sd = pool.shD[s];
                         L.slot = s; flags = f; ++nRays;
-                        smStart<L2>(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
+                        smStart<LAY>(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
                     }
                 }
             }
@@ -541,29 +593,37 @@ __global__ void __launch_bounds__(128, 10) k_shadow_sm(DScene sc, Pool pool, Bat
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        if (L2) smRun2<true, COUNT>(sc, L, stack2, cnt, canRefill); else smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
+        if (LAY) smRun2<true, COUNT, LAY == 2>(sc, L, stack2, cnt, canRefill); else smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
     if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
 }
 
-template <bool COUNT, bool L2> static void launchShadowSm(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    k_shadow_sm<COUNT, L2><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+template <bool COUNT, int LAY> static void launchShadowSm(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    k_shadow_sm<COUNT, LAY><<<grid, 128, 0, st>>>(sc, pool, bt, ctr, it);
+}
+template <bool COUNT> static void launchShadowSmLay(int lay, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
+    if (lay == 2) launchShadowSm<COUNT, 2>(grid, st, sc, pool, bt, ctr, it);
+    else if (lay == 1) launchShadowSm<COUNT, 1>(grid, st, sc, pool, bt, ctr, it);
+    else launchShadowSm<COUNT, 0>(grid, st, sc, pool, bt, ctr, it);
 }
 void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {
-    const bool l2 = sc.ordered && sc.nodes2;
-    if (count) { if (l2) launchShadowSm<true, true>(grid, st, sc, pool, bt, ctr, it); else launchShadowSm<true, false>(grid, st, sc, pool, bt, ctr, it); }
-    else { if (l2) launchShadowSm<false, true>(grid, st, sc, pool, bt, ctr, it); else launchShadowSm<false, false>(grid, st, sc, pool, bt, ctr, it); }
+    if (count) launchShadowSmLay<true>(noriSmLayout(sc), grid, st, sc, pool, bt, ctr, it);
+    else launchShadowSmLay<false>(noriSmLayout(sc), grid, st, sc, pool, bt, ctr, it);
 }
-int noriShadowSmOccupancy(bool count, bool l2) {
+template <bool COUNT> static int shadowSmOcc(int lay) {
     int occ = 8;
-    if (count) { if (l2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true, true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<true, false>, 128, 0); }
-    else { if (l2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false, true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<false, false>, 128, 0); }
+    if (lay == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<COUNT, 2>, 128, 0);
+    else if (lay == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<COUNT, 1>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow_sm<COUNT, 0>, 128, 0);
     return occ;
 }
+int noriShadowSmOccupancy(bool count, int lay) { return count ? shadowSmOcc<true>(lay) : shadowSmOcc<false>(lay); }
 
-ExtendKernel noriPickExtend(bool sm, bool count, bool vol, bool l2) {
-    if (sm && l2) return count ? (vol ? k_extend_sm<true, true, true> : k_extend_sm<true, false, true>) : (vol ? k_extend_sm<false, true, true> : k_extend_sm<false, false, true>);
-    if (sm) return count ? (vol ? k_extend_sm<true, true, false> : k_extend_sm<true, false, false>) : (vol ? k_extend_sm<false, true, false> : k_extend_sm<false, false, false>);
+template <bool COUNT, bool VOL> static ExtendKernel pickExtendSm(int lay) {
+    return lay == 2 ? k_extend_sm<COUNT, VOL, 2> : lay == 1 ? k_extend_sm<COUNT, VOL, 1> : k_extend_sm<COUNT, VOL, 0>;
+}
+ExtendKernel noriPickExtend(bool sm, bool count, bool vol, int lay) {
+    if (sm) return count ? (vol ? pickExtendSm<true, true>(lay) : pickExtendSm<true, false>(lay)) : (vol ? pickExtendSm<false, true>(lay) : pickExtendSm<false, false>(lay));
     return count ? (vol ? k_extend<true, true> : k_extend<true, false>) : (vol ? k_extend<false, true> : k_extend<false, false>);
 }
