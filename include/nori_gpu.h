@@ -230,6 +230,8 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
  * reference's; 1: the child on the ray's side of the node's split axis first -- same hits, same
  * primitive ids incl. the reference's tie rule, fewer node visits; 2 (default): 1 when rendering
  * scenes with more than 4096 primitives, 0 otherwise and always for nori_gpu_trace),
+ * "wide" (1: with the near-first order, the large-scene kernels walk a 4-wide layout -- every inner
+ * node merged with its inner children, the reference's boxes unchanged -- instead of child-box pairs),
  * "area_only" (default 1: scenes whose emitters are all
  * area lights are shaded by kernels compiled without the point / spot / environment-map code),
  * "emitter_sort" (path_mis, emitters of several types: shade from

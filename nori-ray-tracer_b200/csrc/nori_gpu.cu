@@ -51,6 +51,7 @@ struct nori_gpu_ctx {
     // 0 reference child order (counters equal the reference's), 1 near child first, 2 auto: near child first when
     // rendering scenes with deep trees, reference order for small scenes and for the nori_gpu_trace test hook
     int64_t opt_order = 2;
+    int64_t opt_wide = 1;              // 1: large-scene kernels walk the 4-wide layout (with the near-first order)
     int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
 
     nori_gpu_stats stats{};
@@ -110,7 +111,7 @@ static size_t sceneArenaBytes(const nori_gpu_scene *s) {
         const size_t R = e.env_rows > 0 ? e.env_rows : 0, C = e.env_cols > 0 ? e.env_cols : 0;
         add(R * C * 12); add(R * C * 4); add(R * (C + 1) * 4); add(R * 4); add((R + 1) * 4);
     }
-    add(32 * (size_t) s->n_nodes); add(64 * (size_t) s->n_nodes); add(48 * (size_t) s->n_indices);
+    add(32 * (size_t) s->n_nodes); add(64 * (size_t) s->n_nodes); add(128 * (((size_t) s->n_nodes + 1) / 2)); add(48 * (size_t) s->n_indices);
     add(sizeof(DShape) * (size_t) s->n_shapes); add(sizeof(nori_gpu_bsdf) * (size_t) s->n_bsdfs);
     add(sizeof(DEmitter) * (size_t) s->n_emitters); add(sizeof(DImage) * (size_t) s->n_images);
     return total + 256 * arrays;
@@ -189,6 +190,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         }
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
+    else if (k == "wide") { REQUIRE(value == 0 || value == 1, "wide must be 0 or 1"); ctx->opt_wide = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
     else if (k == "area_only") ctx->opt_area_only = value != 0;
     else if (k == "emitter_sort") { REQUIRE(value >= 0 && value <= 2, "emitter_sort must be 0 (off), 1 (auto) or 2 (always)"); ctx->opt_emitter_sort = value; }
@@ -390,7 +392,54 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             }
         }
     }
+    // ---- 4-wide layout (wave_extend.cu: smNode4): every inner node merged with its inner children.  Records are
+    // numbered in depth-first order of the merged tree; empty leaves (bvh.cpp:437) become unused slots.
+    std::vector<uint4> nodes4;
+    if (!nodes2.empty()) {
+        const uint32_t *w = (const uint32_t *) s->nodes;
+        auto isLeaf = [&](uint32_t i) { return (w[8 * (size_t) i] & 1u) != 0; };
+        auto axis = [&](uint32_t i) { return isLeaf(i) ? 0u : ((w[8 * (size_t) i] >> 1) & 3u); };
+        auto right = [&](uint32_t i) { return w[8 * (size_t) i + 1]; };
+        std::vector<uint32_t> rec(s->n_nodes, 0xffffffffu), st; st.reserve(256);
+        uint32_t n = 0;
+        st.push_back(0);
+        while (!st.empty()) {                                    // slots of node i: children of its inner children, else the child
+            const uint32_t i = st.back(); st.pop_back();
+            rec[i] = n++;
+            const uint32_t c[2] = { i + 1, right(i) };
+            for (int g = 1; g >= 0; --g) {
+                if (isLeaf(c[g])) continue;
+                const uint32_t gc[2] = { c[g] + 1, right(c[g]) };
+                for (int k = 1; k >= 0; --k) if (!isLeaf(gc[k])) st.push_back(gc[k]);
+            }
+        }
+        if (n < (1u << 25)) {
+            nodes4.assign(8 * (size_t) n, make_uint4(0u, 0u, 0u, 0x80000000u));
+            auto ref = [&](uint32_t j) -> uint32_t {
+                const uint32_t w0 = w[8 * (size_t) j], w1 = w[8 * (size_t) j + 1];
+                if (isLeaf(j)) return 0x80000000u | ((w0 >> 1) << 25) | ((w0 >> 1) ? w1 : 0u);
+                return (rec[j] << 6) | axis(j) | (axis(j + 1) << 2) | (axis(w1) << 4);
+            };
+            for (uint32_t i = 0; i < s->n_nodes; ++i) {
+                if (rec[i] == 0xffffffffu) continue;
+                uint4 *o = &nodes4[8 * (size_t) rec[i]];
+                const uint32_t c[2] = { i + 1, right(i) };
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t slot[2] = { c[g], 0xffffffffu };
+                    if (!isLeaf(c[g])) { slot[0] = c[g] + 1; slot[1] = right(c[g]); }
+                    for (int k = 0; k < 2; ++k) {
+                        if (slot[k] == 0xffffffffu) continue;
+                        const uint32_t *b = &w[8 * (size_t) slot[k]];
+                        o[2 * (2 * g + k)] = make_uint4(b[2], b[3], b[4], ref(slot[k]));
+                        o[2 * (2 * g + k) + 1] = make_uint4(b[5], b[6], b[7], 0u);
+                    }
+                }
+            }
+            ds.root_ref4 = ref(0);
+        }
+    }
     if (devUpload(ctx, ctx->scene_allocs, nodes2.data(), nodes2.size(), &ds.nodes2)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, nodes4.data(), nodes4.size(), &ds.nodes4)) return 1;
     static_assert(sizeof(nori_gpu_bvh_node) == 2 * sizeof(uint4), "node layout");
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) s->nodes, 2 * (size_t) s->n_nodes, &ds.nodes)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, prims.data(), prims.size(), &ds.prims)) return 1;
@@ -456,6 +505,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const bool count = ctx->opt_stats != 0;
     const int integ = ctx->ds.integrator;
     ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
+    ctx->ds.wide = ctx->opt_wide ? 1 : 0;
     // scenes with a Perlin-noise sphere are rendered by the one-thread-per-sample kernel (traverse.cuh: NORI_WITH_PERLIN)
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
                       && !ctx->opt_megakernel && !ctx->has_perlin;
@@ -483,11 +533,11 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL, sm && ctx->ds.ordered && ctx->ds.nodes2);
+    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL, noriSmLayout(ctx->ds));
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
-    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count, ctx->ds.ordered && ctx->ds.nodes2)) : 0;
+    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count, noriSmLayout(ctx->ds))) : 0;
     ctx->last_wave = true; ctx->last_defer = defer;
     uint32_t it = 0;
     while (true) {

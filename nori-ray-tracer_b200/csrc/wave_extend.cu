@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 //   * each warp step runs EITHER the node code for all NODE lanes OR the primitive code for all LEAF
 //     lanes -- the primitive phase is entered once NORI_LEAF_MIN lanes wait in a leaf (or nothing else
 //     is runnable), so both code paths execute with many lanes active;
-//     (measured on the 10M-triangle scene: thresholds 4..8 are best, 16 costs 20 %, 24 costs 80 %);
+//     (measured on the 10M-triangle scene with the 4-wide layout: 12 is best, 8 and 16 cost 1-2 %, 4 costs 15 %);
 //   * the stepping loop (smRun) costs two ballots per step; publishing answers and refilling lanes from
 //     the warp's slot chunk happens only once NORI_REFILL_MIN lanes are out of work, so short rays do
 //     not wait for the longest ray of the warp and long rays do not pay for the bookkeeping.
@@ -154,21 +154,27 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 #define NORI_LEAF_BURST 4
 #endif
 #ifndef NORI_LEAF_MIN
-#define NORI_LEAF_MIN 8
+#define NORI_LEAF_MIN 12
 #endif
 #ifndef NORI_REFILL_MIN
-#define NORI_REFILL_MIN 8
+#define NORI_REFILL_MIN 12
 #endif
 // resident CTAs per SM asked of the compiler (register cap = 65536 / (128 * blocks)); LAY: 0 reference nodes,
 // 1 child-box pairs, 2 4-wide records
 #ifndef NORI_EXT_SM_BLOCKS4
-#define NORI_EXT_SM_BLOCKS4 8
+#define NORI_EXT_SM_BLOCKS4 6          // 80 registers: the eight loads of a 4-wide record stay in flight without spills
 #endif
 #ifndef NORI_SHADOW_SM_BLOCKS4
-#define NORI_SHADOW_SM_BLOCKS4 10
+#define NORI_SHADOW_SM_BLOCKS4 8
 #endif
-#define NORI_EXT_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_EXT_SM_BLOCKS4 : 8)
-#define NORI_SHADOW_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_SHADOW_SM_BLOCKS4 : 10)
+#ifndef NORI_EXT_SM_BLOCKS2
+#define NORI_EXT_SM_BLOCKS2 8
+#endif
+#ifndef NORI_SHADOW_SM_BLOCKS2
+#define NORI_SHADOW_SM_BLOCKS2 10
+#endif
+#define NORI_EXT_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_EXT_SM_BLOCKS4 : (LAY) == 1 ? NORI_EXT_SM_BLOCKS2 : 8)
+#define NORI_SHADOW_SM_BLOCKS(LAY) ((LAY) == 2 ? NORI_SHADOW_SM_BLOCKS4 : (LAY) == 1 ? NORI_SHADOW_SM_BLOCKS2 : 10)
 enum { ST_IDLE = 0, ST_NODE = 1, ST_LEAF = 2, ST_DONE = 3 };
 
 struct LaneTrav {
@@ -220,7 +226,9 @@ struct LaneStack2 {
 };
 
 // bbox.h:336-363 on one child box, plus the interval test of bvh.cpp:423
+template <bool PLAIN = false>
 __device__ __forceinline__ bool boxTest(const RayTrav &r, float3 mn, float3 mx, float &nearT) {
+    if (PLAIN) return boxPlain(r.o, r.rcp, r.mint, r.maxt, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, nearT);
     nearT = __int_as_float(0xff800000); float farT = __int_as_float(0x7f800000);
     return slab(r.o.x, r.d.x, r.rcp.x, mn.x, mx.x, nearT, farT) && slab(r.o.y, r.d.y, r.rcp.y, mn.y, mx.y, nearT, farT)
         && slab(r.o.z, r.d.z, r.rcp.z, mn.z, mx.z, nearT, farT) && (r.mint <= farT && nearT <= r.maxt);
@@ -252,10 +260,11 @@ __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack
     const uint4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2), d = __ldg(rec + 3);
     if (COUNT) cnt.nodes += 2;
     float nearL, nearR;
-    const bool hitL = boxTest(r, make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)),
-                              make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), nearL);
-    const bool hitR = boxTest(r, make_float3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)),
-                              make_float3(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z)), nearR);
+    bool hitL, hitR;
+#define NORI_BOX(P, a, b, n) boxTest<P>(r, make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), \
+                                        make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), n)
+    if (r.plain) { hitL = NORI_BOX(true, a, b, nearL); hitR = NORI_BOX(true, c, d, nearR); }
+    else { hitL = NORI_BOX(false, a, b, nearL); hitR = NORI_BOX(false, c, d, nearR); }
     const bool swap = (L.neg >> (L.cur & 3u)) & 1u;                  // the right child is the near one
     const uint32_t refN = swap ? b.w : a.w, refF = swap ? a.w : b.w;
     const bool hitN = swap ? hitR : hitL, hitF = swap ? hitL : hitR;
@@ -291,11 +300,11 @@ __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack
     const uint4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
     const uint4 a2 = __ldg(p2), b2 = __ldg(p2 + 1), a3 = __ldg(p3), b3 = __ldg(p3 + 1);
     if (COUNT) cnt.nodes += 4;
-#define NORI_BOX4(a, b, n) (boxTest(r, make_float3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)), \
-                                   make_float3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)), n) && a.w != 0x80000000u)
     float n0, n1, n2, n3;
-    const bool h0 = NORI_BOX4(a0, b0, n0), h1 = NORI_BOX4(a1, b1, n1), h2 = NORI_BOX4(a2, b2, n2), h3 = NORI_BOX4(a3, b3, n3);
-#undef NORI_BOX4
+    bool h0, h1, h2, h3;
+    if (r.plain) { h0 = NORI_BOX(true, a0, b0, n0); h1 = NORI_BOX(true, a1, b1, n1); h2 = NORI_BOX(true, a2, b2, n2); h3 = NORI_BOX(true, a3, b3, n3); }
+    else { h0 = NORI_BOX(false, a0, b0, n0); h1 = NORI_BOX(false, a1, b1, n1); h2 = NORI_BOX(false, a2, b2, n2); h3 = NORI_BOX(false, a3, b3, n3); }
+    h0 = h0 && a0.w != 0x80000000u; h1 = h1 && a1.w != 0x80000000u; h2 = h2 && a2.w != 0x80000000u; h3 = h3 && a3.w != 0x80000000u;
     // the nearest hit slot is entered, the others wait on the stack, farthest lowest
     uint32_t ref = 0; float nt = 0.f; bool any = false;
     if (h3) { ref = a3.w; nt = n3; any = true; }
@@ -369,12 +378,7 @@ __device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack 
     const uint4 n0 = __ldg(&sc.nodes[2 * r.node]);
     const uint4 n1 = __ldg(&sc.nodes[2 * r.node + 1]);
     if (COUNT) ++cnt.nodes;
-    float nearT = __int_as_float(0xff800000), farT = __int_as_float(0x7f800000);
-    const bool in = slab(r.o.x, r.d.x, r.rcp.x, __uint_as_float(n0.z), __uint_as_float(n1.y), nearT, farT)
-                 && slab(r.o.y, r.d.y, r.rcp.y, __uint_as_float(n0.w), __uint_as_float(n1.z), nearT, farT)
-                 && slab(r.o.z, r.d.z, r.rcp.z, __uint_as_float(n1.x), __uint_as_float(n1.w), nearT, farT)
-                 && (r.mint <= farT && nearT <= r.maxt);
-    if (in) {
+    if (nodeBox(r.plain, r.o, r.d, r.rcp, r.mint, r.maxt, n0, n1)) {
         if (!(n0.x & 1u)) {                                      // inner: descend() of traverse.cuh with the sign mask
             const bool swap = (L.neg >> (n0.x >> 1)) & 1u;
             const uint32_t farC = swap ? r.node + 1 : n0.y;

