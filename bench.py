@@ -65,7 +65,7 @@ def large_scene_probe(g, host_scene, peak):
     out = {"workload": "10M-triangle height field (9,999,392 triangles, reference-identical SAH tree) path_mis 3840x2160 @8spp",
            "msamples_per_s": st.samples / st.render_ms / 1e3, "mrays_per_s": st.rays / st.render_ms / 1e3,
            "ms": st.render_ms, "scene_build_s": build_s, "kernel_ms": {k: v["ms"] for k, v in ks.items() if v["ms"]},
-           "traversal": "near-child-first order on the child-box node layout (option order=2 auto)"}
+           "traversal": "near-child-first order on the 4-wide node layout (options order=2 auto, wide=1)"}
     for k in ("extend", "shadow"):
         c, t = kc[k], ks[k]
         if c["rays"] and t["ms"]:

@@ -392,50 +392,55 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
             }
         }
     }
-    // ---- 4-wide layout (wave_extend.cu: smNode4): every inner node merged with its inner children.  Records are
-    // numbered in depth-first order of the merged tree; empty leaves (bvh.cpp:437) become unused slots.
+    // ---- 4-wide layout (wave_extend.cu: smNode4): a record holds up to four descendants of a binary inner node,
+    // chosen greedily -- starting from the node's two children, the inner slot with the largest box surface is
+    // replaced by its own two children until four slots are filled -- so records are full wherever the tree allows
+    // (fewer record visits than merging exactly two levels).  Records are numbered in depth-first order; empty
+    // leaves (bvh.cpp:437) are dropped.  Not built when a ray's stack (3 entries per record level) could overflow.
     std::vector<uint4> nodes4;
     if (!nodes2.empty()) {
         const uint32_t *w = (const uint32_t *) s->nodes;
         auto isLeaf = [&](uint32_t i) { return (w[8 * (size_t) i] & 1u) != 0; };
-        auto axis = [&](uint32_t i) { return isLeaf(i) ? 0u : ((w[8 * (size_t) i] >> 1) & 3u); };
+        auto isEmpty = [&](uint32_t i) { return isLeaf(i) && (w[8 * (size_t) i] >> 1) == 0u; };
         auto right = [&](uint32_t i) { return w[8 * (size_t) i + 1]; };
-        std::vector<uint32_t> rec(s->n_nodes, 0xffffffffu), st; st.reserve(256);
-        uint32_t n = 0;
-        st.push_back(0);
-        while (!st.empty()) {                                    // slots of node i: children of its inner children, else the child
-            const uint32_t i = st.back(); st.pop_back();
-            rec[i] = n++;
-            const uint32_t c[2] = { i + 1, right(i) };
-            for (int g = 1; g >= 0; --g) {
-                if (isLeaf(c[g])) continue;
-                const uint32_t gc[2] = { c[g] + 1, right(c[g]) };
-                for (int k = 1; k >= 0; --k) if (!isLeaf(gc[k])) st.push_back(gc[k]);
+        auto area = [&](uint32_t i) {
+            const float *b = (const float *) &w[8 * (size_t) i + 2];
+            const double dx = (double) b[3] - b[0], dy = (double) b[4] - b[1], dz = (double) b[5] - b[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        std::vector<uint32_t> slots;                             // 4 per record: node index or 0xffffffff
+        std::vector<std::pair<uint32_t, uint32_t>> st; st.reserve(256);   // (binary node that roots a record, record depth)
+        std::vector<uint32_t> recOf(s->n_nodes, 0xffffffffu);
+        uint32_t n = 0, maxDepth = 0;
+        st.push_back({0u, 1u});
+        while (!st.empty()) {
+            const uint32_t i = st.back().first, depth = st.back().second; st.pop_back();
+            recOf[i] = n++; maxDepth = std::max(maxDepth, depth);
+            uint32_t sl[4]; int cnt = 0;
+            for (uint32_t c : { i + 1, right(i) }) if (!isEmpty(c)) sl[cnt++] = c;
+            while (cnt < 4) {
+                int best = -1; double bestA = -1.0;
+                for (int k = 0; k < cnt; ++k) if (!isLeaf(sl[k]) && area(sl[k]) > bestA) { bestA = area(sl[k]); best = k; }
+                if (best < 0) break;
+                const uint32_t c = sl[best];
+                sl[best] = sl[--cnt];
+                for (uint32_t gc : { c + 1, right(c) }) if (!isEmpty(gc)) sl[cnt++] = gc;
             }
+            for (int k = 0; k < 4; ++k) slots.push_back(k < cnt ? sl[k] : 0xffffffffu);
+            for (int k = cnt - 1; k >= 0; --k) if (!isLeaf(sl[k])) st.push_back({sl[k], depth + 1});
         }
-        if (n < (1u << 25)) {
+        if (n < (1u << 31) && 3u * maxDepth <= NORI_STACK2_MAX) {
             nodes4.assign(8 * (size_t) n, make_uint4(0u, 0u, 0u, 0x80000000u));
-            auto ref = [&](uint32_t j) -> uint32_t {
-                const uint32_t w0 = w[8 * (size_t) j], w1 = w[8 * (size_t) j + 1];
-                if (isLeaf(j)) return 0x80000000u | ((w0 >> 1) << 25) | ((w0 >> 1) ? w1 : 0u);
-                return (rec[j] << 6) | axis(j) | (axis(j + 1) << 2) | (axis(w1) << 4);
-            };
-            for (uint32_t i = 0; i < s->n_nodes; ++i) {
-                if (rec[i] == 0xffffffffu) continue;
-                uint4 *o = &nodes4[8 * (size_t) rec[i]];
-                const uint32_t c[2] = { i + 1, right(i) };
-                for (int g = 0; g < 2; ++g) {
-                    uint32_t slot[2] = { c[g], 0xffffffffu };
-                    if (!isLeaf(c[g])) { slot[0] = c[g] + 1; slot[1] = right(c[g]); }
-                    for (int k = 0; k < 2; ++k) {
-                        if (slot[k] == 0xffffffffu) continue;
-                        const uint32_t *b = &w[8 * (size_t) slot[k]];
-                        o[2 * (2 * g + k)] = make_uint4(b[2], b[3], b[4], ref(slot[k]));
-                        o[2 * (2 * g + k) + 1] = make_uint4(b[5], b[6], b[7], 0u);
-                    }
+            for (uint32_t r = 0; r < n; ++r)
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t j = slots[4 * (size_t) r + k];
+                    if (j == 0xffffffffu) continue;
+                    const uint32_t *b = &w[8 * (size_t) j];
+                    const uint32_t ref = isLeaf(j) ? (0x80000000u | ((b[0] >> 1) << 25) | b[1]) : recOf[j];
+                    nodes4[8 * (size_t) r + 2 * k] = make_uint4(b[2], b[3], b[4], ref);
+                    nodes4[8 * (size_t) r + 2 * k + 1] = make_uint4(b[5], b[6], b[7], 0u);
                 }
-            }
-            ds.root_ref4 = ref(0);
+            ds.root_ref4 = 0u;
         }
     }
     if (devUpload(ctx, ctx->scene_allocs, nodes2.data(), nodes2.size(), &ds.nodes2)) return 1;

@@ -212,9 +212,8 @@ struct LaneStack {
 #ifndef NORI_SM_STACK2
 #define NORI_SM_STACK2 16
 #endif
-// deepest stack: child-box pairs push one entry per level (<= 64 levels, checked at upload); the 4-wide layout
-// pushes up to three per level of a tree half as deep
-#define NORI_STACK2_MAX 96
+// deepest stack (NORI_STACK2_MAX, kernels.cuh): child-box pairs push one entry per level (<= 64 levels, checked
+// at upload); the 4-wide layout pushes up to three per record level (checked when the records are built)
 struct LaneStack2 {
     uint2 *sh;                          // &s_stack2[0][tid]; entry e at sh[e * 128]
     uint2 ovf[NORI_STACK2_MAX - NORI_SM_STACK2];
@@ -276,42 +275,52 @@ __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack
     smPop2(L, stack);
 }
 
-// 4-wide layout (DScene::nodes4; built at upload from the reference's nodes, see nori_gpu.cu): every inner node
-// is merged with its inner children, one 128-byte record holds the boxes and references of the (up to four)
-// grandchildren -- half the dependent fetches of the child-box pairs again.  The boxes are the reference's own
-// and nested boxes give nested slab intervals (round-to-nearest is monotonic), so skipping the merged node's box
-// test does not change the set of primitives a ray can reach.
-//   record: slot k = quads 2k (min.xyz, reference of the child) and 2k+1 (max.xyz, -); slots 0,1 = the left
-//           child's children (or the left child itself, if a leaf, in slot 0), slots 2,3 = the right child's;
-//           an unused slot holds the empty-leaf reference 0x80000000 and is skipped
-//   child reference: bit 31 = leaf (as above); inner: record index in bits 30..6, split axes of the merged
-//           node, its left and its right child in bits 1..0, 3..2, 5..4
-// Visiting order: the near side of every split first (the sign rule of descend(), traverse.cuh, applied to the
-// three merged splits); slot p of the order is loaded straight from its place in the record, so the registers
-// are already in visiting order.
-template <bool COUNT>
+// 4-wide layout (DScene::nodes4; built at upload from the reference's nodes, see nori_gpu.cu): one 128-byte
+// record (one cache line) holds the boxes and references of up to four descendants of a binary inner node, so a
+// visit answers four box tests and the chain of dependent fetches is less than half as long as with pairs.  The
+// boxes are the reference's own and nested boxes give nested slab intervals (round-to-nearest is monotonic), so
+// skipping the merged nodes' own box tests does not change the set of primitives a ray can reach.
+//   record: slot k = quads 2k (min.xyz, reference of the descendant) and 2k+1 (max.xyz, -); an unused slot holds
+//           the empty-leaf reference 0x80000000 and is skipped
+//   child reference: bit 31 = leaf (as above); inner: record index
+// Visiting order (closest-hit): hit slots by entry distance (a 5-exchange sorting network on (distance,
+// reference)); the nearest is entered, the others wait on the stack, farthest lowest, and are culled at pop time
+// as above.  Any-hit queries take the slots as they come.
+template <bool SHADOW, bool COUNT>
 __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
-    const uint4 *rec = &sc.nodes4[8 * (size_t) (L.cur >> 6)];
-    const uint32_t s0 = (L.neg >> (L.cur & 3u)) & 1u, sL = (L.neg >> ((L.cur >> 2) & 3u)) & 1u, sR = (L.neg >> ((L.cur >> 4) & 3u)) & 1u;
-    const uint32_t wA = s0 ? sR : sL, wB = s0 ? sL : sR;           // groups in visiting order: A = s0, B = s0 ^ 1
-    const uint4 *gA = rec + 4u * s0, *gB = rec + 4u * (s0 ^ 1u);
-    const uint4 *p0 = gA + 2u * wA, *p1 = gA + 2u * (wA ^ 1u), *p2 = gB + 2u * wB, *p3 = gB + 2u * (wB ^ 1u);
-    const uint4 a0 = __ldg(p0), b0 = __ldg(p0 + 1), a1 = __ldg(p1), b1 = __ldg(p1 + 1);
-    const uint4 a2 = __ldg(p2), b2 = __ldg(p2 + 1), a3 = __ldg(p3), b3 = __ldg(p3 + 1);
-    if (COUNT) cnt.nodes += 4;
+    const uint4 *rec = &sc.nodes4[8 * (size_t) L.cur];
+    const uint4 a0 = __ldg(rec), b0 = __ldg(rec + 1), a1 = __ldg(rec + 2), b1 = __ldg(rec + 3);
+    const uint4 a2 = __ldg(rec + 4), b2 = __ldg(rec + 5), a3 = __ldg(rec + 6), b3 = __ldg(rec + 7);
+    if (COUNT) cnt.nodes += (a0.w != 0x80000000u) + (a1.w != 0x80000000u) + (a2.w != 0x80000000u) + (a3.w != 0x80000000u);   // boxes tested
     float n0, n1, n2, n3;
     bool h0, h1, h2, h3;
     if (r.plain) { h0 = NORI_BOX(true, a0, b0, n0); h1 = NORI_BOX(true, a1, b1, n1); h2 = NORI_BOX(true, a2, b2, n2); h3 = NORI_BOX(true, a3, b3, n3); }
     else { h0 = NORI_BOX(false, a0, b0, n0); h1 = NORI_BOX(false, a1, b1, n1); h2 = NORI_BOX(false, a2, b2, n2); h3 = NORI_BOX(false, a3, b3, n3); }
-    h0 = h0 && a0.w != 0x80000000u; h1 = h1 && a1.w != 0x80000000u; h2 = h2 && a2.w != 0x80000000u; h3 = h3 && a3.w != 0x80000000u;
-    // the nearest hit slot is entered, the others wait on the stack, farthest lowest
-    uint32_t ref = 0; float nt = 0.f; bool any = false;
-    if (h3) { ref = a3.w; nt = n3; any = true; }
-    if (h2) { if (any) stack.push(r.sp++, ref, nt); ref = a2.w; nt = n2; any = true; }
-    if (h1) { if (any) stack.push(r.sp++, ref, nt); ref = a1.w; nt = n1; any = true; }
-    if (h0) { if (any) stack.push(r.sp++, ref, nt); ref = a0.w; any = true; }
-    if (any && smEnter(L, ref)) return;
+    if (SHADOW) {                                                // any-hit: the order does not matter, nothing to cull by
+        h0 = h0 && a0.w != 0x80000000u; h1 = h1 && a1.w != 0x80000000u; h2 = h2 && a2.w != 0x80000000u; h3 = h3 && a3.w != 0x80000000u;
+        uint32_t ref = 0; bool any = false;
+        if (h3) { ref = a3.w; any = true; }
+        if (h2) { if (any) stack.push(r.sp++, ref, 0.f); ref = a2.w; any = true; }
+        if (h1) { if (any) stack.push(r.sp++, ref, 0.f); ref = a1.w; any = true; }
+        if (h0) { if (any) stack.push(r.sp++, ref, 0.f); ref = a0.w; any = true; }
+        if (any && smEnter(L, ref)) return;
+        smPop2(L, stack);
+        return;
+    }
+    // sort key: the entry distance (capped below the "missed" key +inf; a pushed distance is only used to cull)
+    const float inf = __int_as_float(0x7f800000), big = __int_as_float(0x7f7fffff);
+    float k0 = (h0 && a0.w != 0x80000000u) ? fminf(n0, big) : inf, k1 = (h1 && a1.w != 0x80000000u) ? fminf(n1, big) : inf;
+    float k2 = (h2 && a2.w != 0x80000000u) ? fminf(n2, big) : inf, k3 = (h3 && a3.w != 0x80000000u) ? fminf(n3, big) : inf;
+    uint32_t r0 = a0.w, r1 = a1.w, r2 = a2.w, r3 = a3.w;
+#define NORI_CSWAP(ka, ra, kb, rb) { const bool s_ = kb < ka; const float kt = s_ ? kb : ka; kb = s_ ? ka : kb; ka = kt; \
+                                      const uint32_t rt = s_ ? rb : ra; rb = s_ ? ra : rb; ra = rt; }
+    NORI_CSWAP(k0, r0, k1, r1) NORI_CSWAP(k2, r2, k3, r3) NORI_CSWAP(k0, r0, k2, r2) NORI_CSWAP(k1, r1, k3, r3) NORI_CSWAP(k1, r1, k2, r2)
+#undef NORI_CSWAP
+    if (k3 < inf) stack.push(r.sp++, r3, k3);
+    if (k2 < inf) stack.push(r.sp++, r2, k2);
+    if (k1 < inf) stack.push(r.sp++, r1, k1);
+    if (k0 < inf && smEnter(L, r0)) return;
     smPop2(L, stack);
 }
 
@@ -354,7 +363,7 @@ __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2
                     if (L.st == ST_LEAF && L.leafEnd == leafEnd && L.leafI > 0) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
             }
         } else {
-            if (L.st == ST_NODE) { if (WIDE) smNode4<COUNT>(sc, L, stack, cnt); else smNode2<COUNT>(sc, L, stack, cnt); }
+            if (L.st == ST_NODE) { if (WIDE) smNode4<SHADOW, COUNT>(sc, L, stack, cnt); else smNode2<COUNT>(sc, L, stack, cnt); }
         }
     }
 }
@@ -365,7 +374,7 @@ __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 
     if (!travInit(sc, L.r, o, d, mint, maxt)) { L.r.found = false; L.st = ST_DONE; return; }   // decided before the first node: a miss
     L.st = ST_NODE;
     if (LAY) {                                                   // the root's own box (bvh.cpp:421-423 on node 0)
-        L.cur = LAY == 2 ? sc.root_ref4 : sc.root_ref;
+        L.cur = LAY == 2 ? sc.root_ref4 : sc.root_ref;                // (the root record's index, 0 / the root's index and axis)
         float nearT;
         if (!boxTest(L.r, make_float3(sc.root_min[0], sc.root_min[1], sc.root_min[2]), make_float3(sc.root_max[0], sc.root_max[1], sc.root_max[2]), nearT)) L.st = ST_DONE;
     }
