@@ -162,10 +162,10 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 // resident CTAs per SM asked of the compiler (register cap = 65536 / (128 * blocks)); LAY: 0 reference nodes,
 // 1 child-box pairs, 2 4-wide records
 #ifndef NORI_EXT_SM_BLOCKS4
-#define NORI_EXT_SM_BLOCKS4 6          // 80 registers: the eight loads of a 4-wide record stay in flight without spills
+#define NORI_EXT_SM_BLOCKS4 8          // 64 registers, no spills (the 4-wide node code has no slow path)
 #endif
 #ifndef NORI_SHADOW_SM_BLOCKS4
-#define NORI_SHADOW_SM_BLOCKS4 8
+#define NORI_SHADOW_SM_BLOCKS4 9
 #endif
 #ifndef NORI_EXT_SM_BLOCKS2
 #define NORI_EXT_SM_BLOCKS2 8
@@ -279,7 +279,8 @@ __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack
 // record (one cache line) holds the boxes and references of up to four descendants of a binary inner node, so a
 // visit answers four box tests and the chain of dependent fetches is less than half as long as with pairs.  The
 // boxes are the reference's own and nested boxes give nested slab intervals (round-to-nearest is monotonic), so
-// skipping the merged nodes' own box tests does not change the set of primitives a ray can reach.
+// skipping the merged nodes' own box tests does not change the set of primitives a ray can reach -- for rays
+// that cannot meet a NaN in the slab test (rayPlain(), traverse.cuh); the others never enter this layout (smStart).
 //   record: slot k = quads 2k (min.xyz, reference of the descendant) and 2k+1 (max.xyz, -); an unused slot holds
 //           the empty-leaf reference 0x80000000 and is skipped
 //   child reference: bit 31 = leaf (as above); inner: record index
@@ -295,8 +296,7 @@ __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack
     if (COUNT) cnt.nodes += (a0.w != 0x80000000u) + (a1.w != 0x80000000u) + (a2.w != 0x80000000u) + (a3.w != 0x80000000u);   // boxes tested
     float n0, n1, n2, n3;
     bool h0, h1, h2, h3;
-    if (r.plain) { h0 = NORI_BOX(true, a0, b0, n0); h1 = NORI_BOX(true, a1, b1, n1); h2 = NORI_BOX(true, a2, b2, n2); h3 = NORI_BOX(true, a3, b3, n3); }
-    else { h0 = NORI_BOX(false, a0, b0, n0); h1 = NORI_BOX(false, a1, b1, n1); h2 = NORI_BOX(false, a2, b2, n2); h3 = NORI_BOX(false, a3, b3, n3); }
+    h0 = NORI_BOX(true, a0, b0, n0); h1 = NORI_BOX(true, a1, b1, n1); h2 = NORI_BOX(true, a2, b2, n2); h3 = NORI_BOX(true, a3, b3, n3);   // only rayPlain() rays get here (smStart)
     if (SHADOW) {                                                // any-hit: the order does not matter, nothing to cull by
         h0 = h0 && a0.w != 0x80000000u; h1 = h1 && a1.w != 0x80000000u; h2 = h2 && a2.w != 0x80000000u; h3 = h3 && a3.w != 0x80000000u;
         uint32_t ref = 0; bool any = false;
@@ -368,11 +368,19 @@ __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2
     }
 }
 
-template <int LAY>
-__device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 d, float mint, float maxt) {
+template <int LAY, bool SHADOW, bool COUNT>
+__device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 d, float mint, float maxt, TraceCounters &cnt) {
     L.neg = sc.ordered ? ((d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u)) : 0u;
     if (!travInit(sc, L.r, o, d, mint, maxt)) { L.r.found = false; L.st = ST_DONE; return; }   // decided before the first node: a miss
     L.st = ST_NODE;
+    if (LAY == 2 && !L.r.plain) {
+        // The 4-wide records skip the box tests of the merged nodes, which is only equivalent while nested boxes give
+        // nested slab intervals.  A ray outside rayPlain() can meet a NaN there (origin on a bounding plane, 1/d
+        // infinite: bbox.h:347-348 then rejects THAT box), so it walks the reference's own nodes, here and now.
+        L.r.found = traverse<SHADOW, COUNT>(sc, o, d, mint, maxt, L.r.hit, cnt);
+        L.st = ST_DONE;
+        return;
+    }
     if (LAY) {                                                   // the root's own box (bvh.cpp:421-423 on node 0)
         L.cur = LAY == 2 ? sc.root_ref4 : sc.root_ref;                // (the root record's index, 0 / the root's index and axis)
         float nearT;
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
                 if (s < pool.P && (pool.flags[s] & PF_ALIVE)) {
                     const float4 ro = pool.rayO[s], rd = pool.rayD[s];
                     L.slot = s; ++nRays;
-                    smStart<LAY>(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w);
+                    smStart<LAY, false, COUNT>(sc, L, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, cnt);
                 }
             }
             idle = __ballot_sync(0xffffffffu, L.st == ST_IDLE);
@@ -598,7 +606,7 @@ __global__ void __launch_bounds__(128, NORI_SHADOW_SM_BLOCKS(LAY)) k_shadow_sm(D
                     if (f & PF_SHADOW) {
                         const float4 so = pool.rayO[s], sd = pool.shD[s];
                         L.slot = s; flags = f; ++nRays;
-                        smStart<LAY>(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w);
+                        smStart<LAY, true, COUNT>(sc, L, mk(so.x, so.y, so.z), mk(sd.x, sd.y, sd.z), NORI_EPS, sd.w, cnt);
                     }
                 }
             }
