@@ -308,6 +308,15 @@ int nori_gpu_build_bvh_device(int device, const nori_gpu_shape *shapes, uint32_t
 int nori_gpu_mesh_area_cdf(const float *V, const uint32_t *F, uint32_t n_triangles, float *cdf_out,
                            float *normalization_out);
 
+/* Test hook: the 4-wide node records nori_gpu_upload_scene derives from a reference-format tree for its
+ * large-scene kernels (option "wide").  records_out: 32 words per record -- slot k = words 8k..8k+7 =
+ * {bmin[3], ref}{bmax[3], 0}; ref: bit 31 = leaf (size in bits 30..25, first primitive in 24..0; 0x80000000 =
+ * unused slot), else the index of the child record; record 0 is the root.  capacity in records (n_nodes / 2 + 1
+ * always suffices).  *n_records_out = 0 when the layout is not built for this tree (root is a leaf, a leaf with
+ * more than 63 primitives, more than 2^25 primitives, or a ray's stack could exceed its 96 entries). */
+int nori_gpu_wide_layout(const nori_gpu_bvh_node *nodes, uint32_t n_nodes, uint32_t n_indices, uint32_t *records_out,
+                         uint32_t capacity, uint32_t *n_records_out);
+
 /* sizeof() of every ABI struct as compiled into the library (binding self-check); returns the count. */
 int nori_gpu_abi_sizes(uint32_t *out, int n);
 

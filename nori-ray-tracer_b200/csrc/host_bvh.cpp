@@ -14,6 +14,7 @@
 // i+2*nL), so large subtrees are built on separate threads without changing the result.
 // Float arithmetic follows the reference build (no FMA contraction: plain x86-64 SSE2).
 #include "nori_gpu.h"
+#include "host_layout.h"
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -152,6 +153,96 @@ struct Builder {
 
 } // namespace
 
+// ---------------------------------------------------------------------------------------------
+// traversal layouts for the large-scene kernels (host_layout.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NodeWords {
+    const uint32_t *w;
+    bool leaf(uint32_t i) const { return (w[8 * (size_t) i] & 1u) != 0; }
+    uint32_t size(uint32_t i) const { return w[8 * (size_t) i] >> 1; }            // leaf: primitive count; inner: split axis
+    uint32_t second(uint32_t i) const { return w[8 * (size_t) i + 1]; }           // leaf: first primitive; inner: right child
+    bool empty(uint32_t i) const { return leaf(i) && size(i) == 0u; }
+    const uint32_t *box(uint32_t i) const { return &w[8 * (size_t) i + 2]; }
+    uint32_t leafRef(uint32_t i) const { return 0x80000000u | (size(i) << 25) | second(i); }
+    double area(uint32_t i) const {
+        const float *b = (const float *) box(i);
+        const double dx = (double) b[3] - b[0], dy = (double) b[4] - b[1], dz = (double) b[5] - b[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+bool layoutEncodable(const NodeWords &t, uint32_t n_nodes, uint32_t n_indices) {
+    if (n_nodes == 0 || t.leaf(0) || n_indices >= (1u << 25) || n_nodes >= (1u << 29)) return false;
+    for (uint32_t i = 0; i < n_nodes; ++i) if (t.leaf(i) && t.size(i) > 63u) return false;
+    return true;
+}
+} // namespace
+
+bool noriBuildPairLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices, std::vector<uint32_t> &out, uint32_t &rootRef) {
+    out.clear();
+    const NodeWords t{w};
+    if (!layoutEncodable(t, n_nodes, n_indices)) return false;
+    std::vector<uint32_t> innerIdx(n_nodes, 0);
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_nodes; ++i) if (!t.leaf(i)) innerIdx[i] = n++;
+    auto ref = [&](uint32_t c) { return t.leaf(c) ? t.leafRef(c) : ((innerIdx[c] << 2) | (t.size(c) & 3u)); };
+    out.assign(16 * (size_t) n, 0u);
+    for (uint32_t i = 0; i < n_nodes; ++i) {
+        if (t.leaf(i)) continue;
+        const uint32_t l = i + 1, r = t.second(i);
+        if (l >= n_nodes || r >= n_nodes) { out.clear(); return false; }
+        const uint32_t *a = t.box(l), *b = t.box(r);
+        uint32_t *o = &out[16 * (size_t) innerIdx[i]];
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = ref(l);
+        o[4] = a[3]; o[5] = a[4]; o[6] = a[5]; o[7] = ref(r);
+        o[8] = b[0]; o[9] = b[1]; o[10] = b[2];
+        o[12] = b[3]; o[13] = b[4]; o[14] = b[5];
+    }
+    rootRef = t.size(0) & 3u;
+    return true;
+}
+
+bool noriBuildWideLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices, uint32_t maxStack, std::vector<uint32_t> &out) {
+    out.clear();
+    const NodeWords t{w};
+    if (!layoutEncodable(t, n_nodes, n_indices)) return false;
+    std::vector<uint32_t> slots;                                 // 4 per record: node index or 0xffffffff
+    std::vector<std::pair<uint32_t, uint32_t>> st; st.reserve(256);   // (binary node that roots a record, record depth)
+    std::vector<uint32_t> recOf(n_nodes, 0xffffffffu);
+    uint32_t n = 0, maxDepth = 0;
+    st.push_back({0u, 1u});
+    while (!st.empty()) {
+        const uint32_t i = st.back().first, depth = st.back().second; st.pop_back();
+        if (n >= n_nodes || i + 1 >= n_nodes || t.second(i) >= n_nodes) return false;     // not a tree
+        recOf[i] = n++; maxDepth = std::max(maxDepth, depth);
+        uint32_t sl[4]; int cnt = 0;
+        for (uint32_t c : { i + 1, t.second(i) }) if (!t.empty(c)) sl[cnt++] = c;
+        while (cnt < 4) {
+            int best = -1; double bestA = -1.0;
+            for (int k = 0; k < cnt; ++k) if (!t.leaf(sl[k]) && t.area(sl[k]) > bestA) { bestA = t.area(sl[k]); best = k; }
+            if (best < 0) break;
+            const uint32_t c = sl[best];
+            if (c + 1 >= n_nodes || t.second(c) >= n_nodes) return false;
+            sl[best] = sl[--cnt];
+            for (uint32_t gc : { c + 1, t.second(c) }) if (!t.empty(gc)) sl[cnt++] = gc;
+        }
+        for (int k = 0; k < 4; ++k) slots.push_back(k < cnt ? sl[k] : 0xffffffffu);
+        for (int k = cnt - 1; k >= 0; --k) if (!t.leaf(sl[k])) st.push_back({sl[k], depth + 1});
+    }
+    if (3u * maxDepth > maxStack) return false;
+    out.assign(32 * (size_t) n, 0u);
+    for (uint32_t r = 0; r < n; ++r)
+        for (int k = 0; k < 4; ++k) {
+            uint32_t *o = &out[32 * (size_t) r + 8 * k];
+            const uint32_t j = slots[4 * (size_t) r + k];
+            if (j == 0xffffffffu) { o[3] = 0x80000000u; continue; }
+            const uint32_t *b = t.box(j);
+            o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = t.leaf(j) ? t.leafRef(j) : recOf[j];
+            o[4] = b[3]; o[5] = b[4]; o[6] = b[5];
+        }
+    return true;
+}
+
 extern "C" {
 
 // Build the reference's SAH BVH over `shapes` (bvh.cpp:329-382).  Outputs: nodes_out (capacity
@@ -235,6 +326,20 @@ int nori_gpu_mesh_area_cdf(const float *V, const uint32_t *F, uint32_t n_triangl
         cdf_out[n_triangles] = 1.0f;
         *normalization_out = norm;
     } else *normalization_out = 0.0f;
+    return 0;
+}
+
+// Test hook for the 4-wide layout (host_layout.h).  records_out: 32 words per record, capacity in records
+// (n_nodes / 2 + 1 always suffices); *n_records_out = 0 when the layout is not built for this tree.
+int nori_gpu_wide_layout(const nori_gpu_bvh_node *nodes, uint32_t n_nodes, uint32_t n_indices, uint32_t *records_out,
+                         uint32_t capacity, uint32_t *n_records_out) {
+    if (!nodes || !records_out || !n_records_out) return 1;
+    std::vector<uint32_t> out;
+    *n_records_out = 0;
+    if (!noriBuildWideLayout((const uint32_t *) nodes, n_nodes, n_indices, NORI_STACK2_MAX, out)) return 0;
+    if (out.size() / 32 > capacity) return 1;
+    memcpy(records_out, out.data(), out.size() * sizeof(uint32_t));
+    *n_records_out = (uint32_t) (out.size() / 32);
     return 0;
 }
 

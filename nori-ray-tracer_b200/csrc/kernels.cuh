@@ -17,6 +17,7 @@
 //   k_trace / k_pcg32*   the ABI's test hooks
 #pragma once
 #include "integrators.cuh"
+#include "host_layout.h"        // NORI_STACK2_MAX
 
 #define NORI_FREE_SLOT 0xffffffffu
 
@@ -122,8 +123,6 @@ void noriLaunchShadeMats(bool count, int grid, cudaStream_t st, const DScene &sc
 void noriLaunchShadeMisDeferred(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadowSm(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 int noriShadowSmOccupancy(bool count, int layout);
-// deepest per-ray stack of the large-scene kernels' child-box layouts (wave_extend.cu: LaneStack2)
-#define NORI_STACK2_MAX 96
 static inline int noriSmLayout(const DScene &sc) { return sc.ordered ? (sc.wide && sc.nodes4 ? 2 : sc.nodes2 ? 1 : 0) : 0; }
 void noriLaunchShadeMis(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);

@@ -357,94 +357,16 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
         }
         REQUIRE(maxDepth <= 64, "upload_scene: BVH deeper than the 64-entry traversal stack (bvh.cpp:405)");
     }
-    // ---- child-box layout for the large-scene kernels (wave_extend.cu): one 64-byte record per inner node
-    // with both children's boxes and references.  Built only when every leaf fits the reference encoding.
-    std::vector<uint4> nodes2;
-    {
-        const uint32_t *w = (const uint32_t *) s->nodes;         // 8 words per node: flag|size-or-axis, start-or-right, bmin[3], bmax[3]
-        auto isLeaf = [&](uint32_t i) { return (w[8 * (size_t) i] & 1u) != 0; };
-        bool ok = s->n_nodes > 0 && !isLeaf(0) && s->n_indices < (1u << 25) && s->n_nodes < (1u << 29);
-        std::vector<uint32_t> innerIdx;
-        if (ok) {
-            innerIdx.assign(s->n_nodes, 0);
-            uint32_t n = 0;
-            for (uint32_t i = 0; i < s->n_nodes && ok; ++i) {
-                if (isLeaf(i)) { if ((w[8 * (size_t) i] >> 1) > 63u) ok = false; }
-                else innerIdx[i] = n++;
-            }
-            if (ok) {
-                nodes2.resize(4 * (size_t) n);
-                auto ref = [&](uint32_t c) -> uint32_t {
-                    const uint32_t w0 = w[8 * (size_t) c], w1 = w[8 * (size_t) c + 1];
-                    return isLeaf(c) ? (0x80000000u | ((w0 >> 1) << 25) | w1) : ((innerIdx[c] << 2) | ((w0 >> 1) & 3u));
-                };
-                for (uint32_t i = 0; i < s->n_nodes; ++i) {
-                    if (isLeaf(i)) continue;
-                    const uint32_t l = i + 1, r = w[8 * (size_t) i + 1];
-                    REQUIRE(r < s->n_nodes && l < s->n_nodes, "upload_scene: BVH child index out of range");
-                    const uint32_t *a = &w[8 * (size_t) l], *b = &w[8 * (size_t) r];
-                    uint4 *o = &nodes2[4 * (size_t) innerIdx[i]];
-                    o[0] = make_uint4(a[2], a[3], a[4], ref(l)); o[1] = make_uint4(a[5], a[6], a[7], ref(r));
-                    o[2] = make_uint4(b[2], b[3], b[4], 0u);     o[3] = make_uint4(b[5], b[6], b[7], 0u);
-                }
-                ds.root_ref = (w[0] >> 1) & 3u;
-                memcpy(ds.root_min, &w[2], 12); memcpy(ds.root_max, &w[5], 12);
-            }
-        }
-    }
-    // ---- 4-wide layout (wave_extend.cu: smNode4): a record holds up to four descendants of a binary inner node,
-    // chosen greedily -- starting from the node's two children, the inner slot with the largest box surface is
-    // replaced by its own two children until four slots are filled -- so records are full wherever the tree allows
-    // (fewer record visits than merging exactly two levels).  Records are numbered in depth-first order; empty
-    // leaves (bvh.cpp:437) are dropped.  Not built when a ray's stack (3 entries per record level) could overflow.
-    std::vector<uint4> nodes4;
-    if (!nodes2.empty()) {
+    // ---- layouts for the large-scene kernels (wave_extend.cu), derived from the reference nodes on the host
+    // (host_layout.h): child-box pairs and 4-wide records.  Built only when every leaf fits the reference encoding.
+    std::vector<uint32_t> nodes2, nodes4;
+    if (noriBuildPairLayout((const uint32_t *) s->nodes, s->n_nodes, s->n_indices, nodes2, ds.root_ref)) {
         const uint32_t *w = (const uint32_t *) s->nodes;
-        auto isLeaf = [&](uint32_t i) { return (w[8 * (size_t) i] & 1u) != 0; };
-        auto isEmpty = [&](uint32_t i) { return isLeaf(i) && (w[8 * (size_t) i] >> 1) == 0u; };
-        auto right = [&](uint32_t i) { return w[8 * (size_t) i + 1]; };
-        auto area = [&](uint32_t i) {
-            const float *b = (const float *) &w[8 * (size_t) i + 2];
-            const double dx = (double) b[3] - b[0], dy = (double) b[4] - b[1], dz = (double) b[5] - b[2];
-            return dx * dy + dy * dz + dz * dx;
-        };
-        std::vector<uint32_t> slots;                             // 4 per record: node index or 0xffffffff
-        std::vector<std::pair<uint32_t, uint32_t>> st; st.reserve(256);   // (binary node that roots a record, record depth)
-        std::vector<uint32_t> recOf(s->n_nodes, 0xffffffffu);
-        uint32_t n = 0, maxDepth = 0;
-        st.push_back({0u, 1u});
-        while (!st.empty()) {
-            const uint32_t i = st.back().first, depth = st.back().second; st.pop_back();
-            recOf[i] = n++; maxDepth = std::max(maxDepth, depth);
-            uint32_t sl[4]; int cnt = 0;
-            for (uint32_t c : { i + 1, right(i) }) if (!isEmpty(c)) sl[cnt++] = c;
-            while (cnt < 4) {
-                int best = -1; double bestA = -1.0;
-                for (int k = 0; k < cnt; ++k) if (!isLeaf(sl[k]) && area(sl[k]) > bestA) { bestA = area(sl[k]); best = k; }
-                if (best < 0) break;
-                const uint32_t c = sl[best];
-                sl[best] = sl[--cnt];
-                for (uint32_t gc : { c + 1, right(c) }) if (!isEmpty(gc)) sl[cnt++] = gc;
-            }
-            for (int k = 0; k < 4; ++k) slots.push_back(k < cnt ? sl[k] : 0xffffffffu);
-            for (int k = cnt - 1; k >= 0; --k) if (!isLeaf(sl[k])) st.push_back({sl[k], depth + 1});
-        }
-        if (n < (1u << 31) && 3u * maxDepth <= NORI_STACK2_MAX) {
-            nodes4.assign(8 * (size_t) n, make_uint4(0u, 0u, 0u, 0x80000000u));
-            for (uint32_t r = 0; r < n; ++r)
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t j = slots[4 * (size_t) r + k];
-                    if (j == 0xffffffffu) continue;
-                    const uint32_t *b = &w[8 * (size_t) j];
-                    const uint32_t ref = isLeaf(j) ? (0x80000000u | ((b[0] >> 1) << 25) | b[1]) : recOf[j];
-                    nodes4[8 * (size_t) r + 2 * k] = make_uint4(b[2], b[3], b[4], ref);
-                    nodes4[8 * (size_t) r + 2 * k + 1] = make_uint4(b[5], b[6], b[7], 0u);
-                }
-            ds.root_ref4 = 0u;
-        }
+        memcpy(ds.root_min, &w[2], 12); memcpy(ds.root_max, &w[5], 12);
+        if (noriBuildWideLayout(w, s->n_nodes, s->n_indices, NORI_STACK2_MAX, nodes4)) ds.root_ref4 = 0u;   // record 0
     }
-    if (devUpload(ctx, ctx->scene_allocs, nodes2.data(), nodes2.size(), &ds.nodes2)) return 1;
-    if (devUpload(ctx, ctx->scene_allocs, nodes4.data(), nodes4.size(), &ds.nodes4)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) nodes2.data(), nodes2.size() / 4, &ds.nodes2)) return 1;
+    if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) nodes4.data(), nodes4.size() / 4, &ds.nodes4)) return 1;
     static_assert(sizeof(nori_gpu_bvh_node) == 2 * sizeof(uint4), "node layout");
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) s->nodes, 2 * (size_t) s->n_nodes, &ds.nodes)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, prims.data(), prims.size(), &ds.prims)) return 1;

@@ -51,6 +51,7 @@ def load_library():
         "nori_gpu_build_bvh": (C.c_int, [C.POINTER(abi.Shape), u32, vp, vp, vp, C.POINTER(u32), C.c_int]),
         "nori_gpu_build_bvh_device": (C.c_int, [C.c_int, C.POINTER(abi.Shape), u32, vp, vp, vp, C.POINTER(u32), u32, C.POINTER(C.c_float)]),
         "nori_gpu_mesh_area_cdf": (C.c_int, [vp, vp, u32, vp, C.POINTER(C.c_float)]),
+        "nori_gpu_wide_layout": (C.c_int, [vp, u32, u32, vp, u32, C.POINTER(u32)]),
         "nori_gpu_get_stats": (C.c_int, [vp, C.POINTER(abi.Stats)]),
         "nori_gpu_get_kernel_stats": (C.c_int, [vp, C.POINTER(abi.KernelStats)]),
         "nori_gpu_reset_stats": (C.c_int, [vp]),
