@@ -195,11 +195,12 @@ static Replay replay(const BVH *bvh, const Ray3f &_ray, bool shadowRay) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 3) { cerr << "usage: nori_export scene.xml out.nscene [--rays N] [--seed S] [--seq N] [--probe N]" << endl; return 1; }
+    if (argc < 3) { cerr << "usage: nori_export scene.xml out.nscene [--rays N] [--special K] [--seed S] [--seq N] [--probe N]" << endl; return 1; }
     std::string xml = argv[1], out = argv[2];
-    size_t nRays = 0, nSeq = 0, nProbe = 0; uint64_t seed = 1;
+    size_t nRays = 0, nSeq = 0, nProbe = 0, special = 0; uint64_t seed = 1;
     for (int i = 3; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--rays")) nRays = (size_t) atoll(argv[i + 1]);
+        if (!strcmp(argv[i], "--special")) special = (size_t) atoll(argv[i + 1]);
         if (!strcmp(argv[i], "--seed")) seed = (uint64_t) atoll(argv[i + 1]);
         if (!strcmp(argv[i], "--seq")) nSeq = (size_t) atoll(argv[i + 1]);
         if (!strcmp(argv[i], "--probe")) nProbe = (size_t) atoll(argv[i + 1]);
@@ -435,6 +436,21 @@ int main(int argc, char **argv) {
                 }
             }
             rays.resize(nRays); shadowFlag.resize(nRays);
+            /* --special K: every K-th ray is turned into one of the special cases of the slab test (bbox.h:343-357):
+               a zero (+0 / -0) or subnormal direction component (1/d infinite), for half of them with the origin
+               exactly on a bounding plane of the scene or of a leaf, where (bound - o) * (1/d) is 0 * inf */
+            if (special > 0) {
+                const float comps[5] = { 0.0f, -0.0f, 1e-41f, -1e-41f, 1e-39f };
+                for (size_t i = 0; i < nRays; i += special) {
+                    const int a = (int) (rng.nextUInt() % 3u);
+                    rays[i].d[a] = comps[rng.nextUInt() % 5u];
+                    const uint32_t pick = rng.nextUInt() % 4u;
+                    if (pick < 2u) {
+                        const BVH::BVHNode &nd = bvh->m_nodes[pick == 0u ? 0u : rng.nextUInt() % (uint32_t) bvh->m_nodes.size()];
+                        rays[i].o[a] = (rng.nextUInt() & 1u) ? nd.bbox.min[a] : nd.bbox.max[a];
+                    }
+                }
+            }
             std::vector<nori_gpu_hit> hits(nRays);
             std::vector<float> hp(nRays * 3, 0.f), huv(nRays * 2, 0.f), hn(nRays * 3, 0.f), hg(nRays * 3, 0.f);
             size_t mismatches = 0;

@@ -52,6 +52,28 @@ def test_ray_batches_bit_exact(name, golden_scene, make_oracle):
             assert np.allclose(uv[hit], rb["uv"][m][hit], rtol=0, atol=2e-7)
 
 
+@pytest.mark.parametrize("name", ["cbox_path_mis", "sphere_mesh_normals", "veach_mis", "odyssey_mis"])
+def test_special_case_rays_bit_exact(name, golden_scene, make_oracle):
+    """The special cases of the slab test (bbox.h:343-357) -- a zero (+0 / -0) or subnormal direction component,
+    the origin exactly on a bounding plane ((bound - o) * (1/d) = 0 * inf = NaN rejects that box) -- answered by the
+    reference's BVH::rayIntersect (tests/golden/make_special_rays.py) on the tree of that export."""
+    from nori_ray_tracer_b200 import abi, nscene
+    fx = np.load(os.path.join(GOLDEN, f"special_rays_{name}.npz"))
+    entries = dict(golden_scene(name).entries)
+    entries["bvh.nodes"], entries["bvh.indices"] = fx["nodes"], fx["indices"]      # same geometry, the export's own tree
+    o = make_oracle(nscene.SceneData(entries))
+    rays = np.ascontiguousarray(fx["rays"]).view(abi.RAY_DTYPE).reshape(-1)
+    ref = np.ascontiguousarray(fx["hits"]).view(abi.HIT_DTYPE).reshape(-1)
+    d = rays["d"]
+    special = ((d == 0) | (np.abs(d) < np.float32(1.1754944e-38))).any(axis=1)
+    assert special.sum() > len(rays) // 3
+    for shadow in (0, 1):
+        m = fx["shadow"] == shadow
+        hits = o.trace(rays[m], shadow)
+        for f in ("t", "u", "v", "shape", "prim", "nodes_visited", "prims_tested"):
+            assert np.array_equal(hits[f], ref[m][f]), (name, shadow, f, int((hits[f] != ref[m][f]).sum()))
+
+
 @pytest.mark.parametrize("name", SCENE_NAMES)
 def test_plugin_probes_bit_exact(name, golden_scene, make_oracle):
     """BSDF::eval/pdf/sample and Emitter::sample/pdf/eval of every plugin instance in the scene."""
