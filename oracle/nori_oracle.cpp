@@ -411,6 +411,60 @@ done_shadow:
 }
 inline bool occluded(Scene &sc, const Ray &r) { Its tmp; return rayIntersect(sc, r, tmp, true); }   /* scene.h:112-115 */
 
+/* NOT the reference's algorithm: the same closest-hit query with the children of every inner node taken in
+ * another order -- what the GPU kernels do on large scenes (near child first) and two adversarial orders -- to
+ * test on the CPU, at scale, that the answer does not depend on the visiting order once exact ties are resolved
+ * the way the reference's order resolves them (equal t: the higher leaf position wins).
+ * order 1: the child on the ray's side of the node's recorded split axis first (traverse.cuh: descend());
+ * order 2: that child LAST; order 3: always the right child first. */
+bool rayIntersectOrdered(Scene &sc, const Ray &_ray, Its &its, int order) {
+    uint32_t node_idx = 0, stack_idx = 0, stack[64];
+    its.t = kInf; its.shape = -1; its.nodes = its.prims = 0;
+    Ray ray(_ray);
+    if (ray.mint == kEps)
+        ray.mint = std::max(ray.mint, ray.mint * std::max(std::abs(ray.o.x), std::max(std::abs(ray.o.y), std::abs(ray.o.z))));
+    if (sc.nodes.empty() || ray.maxt < ray.mint) return false;
+    bool found = false; uint32_t bestPos = 0;
+    while (true) {
+        const nori_gpu_bvh_node &node = sc.nodes[node_idx];
+        ++its.nodes;
+        bool descend = false;
+        if (boxHit(node, ray)) {
+            if (!(node.data[0] & 1u)) {
+                const uint32_t axis = (node.data[0] >> 1) & 3u, left = node_idx + 1, right = node.data[1];
+                const float da = axis == 0 ? ray.d.x : axis == 1 ? ray.d.y : ray.d.z;
+                bool rightFirst = order == 3 ? true : (da < 0.0f);
+                if (order == 2) rightFirst = !rightFirst;
+                stack[stack_idx++] = rightFirst ? left : right;
+                node_idx = rightFirst ? right : left;
+                descend = true;
+            } else {
+                uint32_t start = node.data[1], end = start + (node.data[0] >> 1);
+                for (uint32_t i = start; i < end; ++i) {
+                    uint32_t idx = sc.indices[i];
+                    uint32_t s = findShape(sc, idx);
+                    float u = 0, v = 0, t = 0;
+                    ++its.prims;
+                    const Shape &shp = sc.shapes[s];
+                    bool hit = shp.pod.type == NORI_SHAPE_MESH ? triHit(shp, idx, ray, u, v, t)
+                             : shp.pod.type == NORI_SHAPE_PERLIN ? perlinHit(shp, ray, t) : sphereHit(shp, ray, t);
+                    if (hit && (!found || t < ray.maxt || i > bestPos)) {      /* the kernels' tie rule */
+                        found = true; bestPos = i;
+                        ray.maxt = its.t = t;
+                        its.baryU = shp.pod.type == NORI_SHAPE_MESH ? u : 0.f;
+                        its.baryV = shp.pod.type == NORI_SHAPE_MESH ? v : 0.f;
+                        its.shape = (int) s; its.prim = idx;
+                    }
+                }
+            }
+        }
+        if (descend) continue;
+        if (stack_idx == 0) break;
+        node_idx = stack[--stack_idx];
+    }
+    return found;
+}
+
 /* ------------------------------------------------------------------ warps (src/warp.cpp) ------- */
 inline V3 squareToUniformSphere(P2 s) {                       /* warp.cpp:86-91 */
     float theta = std::acos(1 - 2 * (1 - s.x));
@@ -1211,6 +1265,18 @@ void nori_oracle_trace(void *h, const nori_gpu_ray *rays, uint64_t n, int shadow
             if (nsh) { nsh[3 * i] = its.sh.n.x; nsh[3 * i + 1] = its.sh.n.y; nsh[3 * i + 2] = its.sh.n.z; }
             if (ngeo) { ngeo[3 * i] = its.geo.n.x; ngeo[3 * i + 1] = its.geo.n.y; ngeo[3 * i + 2] = its.geo.n.z; }
         }
+    });
+}
+
+/* test-only: closest hits in another visiting order (rayIntersectOrdered); fills t,u,v,shape,prim */
+void nori_oracle_trace_ordered(void *h, const nori_gpu_ray *rays, uint64_t n, int order, nori_gpu_hit *out) {
+    Scene *sc = (Scene *) h;
+    parallelFor((int64_t) n, 1024, [&](int64_t i) {
+        Ray r(load3(rays[i].o), load3(rays[i].d), rays[i].mint, rays[i].maxt);
+        Its its; bool hit = rayIntersectOrdered(*sc, r, its, order);
+        nori_gpu_hit &o = out[i]; memset(&o, 0, sizeof(o));
+        o.t = its.t; o.u = its.baryU; o.v = its.baryV; o.shape = hit ? (uint32_t) its.shape : 0xffffffffu;
+        o.prim = hit ? its.prim : 0xffffffffu; o.nodes_visited = its.nodes; o.prims_tested = its.prims;
     });
 }
 

@@ -25,6 +25,7 @@ def _load(abi):
     lib.nori_oracle_destroy.argtypes = [C.c_void_p]
     lib.nori_oracle_film_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
     lib.nori_oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p] + [C.c_void_p] * 4
+    lib.nori_oracle_trace_ordered.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.nori_oracle_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.nori_oracle_pcg32_uint.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.nori_oracle_render_samples.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
@@ -66,6 +67,13 @@ class Oracle:
         self.lib.nori_oracle_trace(self.h, rays.ctypes.data, n, int(shadow), hits.ctypes.data,
                                    p.ctypes.data, uv.ctypes.data, ns.ctypes.data, ng.ctypes.data)
         return hits, p, uv, ns, ng
+
+    def trace_ordered(self, rays, order):
+        """Closest hits with the children of every inner node visited in another order (test of order independence)."""
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(rays.shape[0], dtype=self.abi.HIT_DTYPE)
+        self.lib.nori_oracle_trace_ordered(self.h, rays.ctypes.data, rays.shape[0], int(order), hits.ctypes.data)
+        return hits
 
     def pcg32(self, initstate, initseq, n):
         out = np.zeros(n, np.float32)
