@@ -14,7 +14,7 @@
  *
  * Pinning (see tests/test_oracle_golden.py, tests/golden/):
  *   - traversal: bit-exact (t,u,v,shape,prim,#nodes,#prims) against ray batches answered by the real
- *     reference (oracle/_ref/nori_export);
+ *     reference (oracle/_ref/nori_export), incl. the special cases of the slab test (--special);
  *   - pcg32: ext/pcg32/pcg32-demo.out known answers;
  *   - whole renders: RNG mode 1 below replays the reference's block-sequential sampler mapping
  *     (one pcg32 per 32x32 block, seeded with the block offset, independent.cpp:48-53,
@@ -23,6 +23,11 @@
  *   - the reference's t-test known answers (scenes/pa4/tests/*.xml, scenes/pa3/tests/*.xml).
  * RNG mode 0 is the GPU path's mapping (one stream per camera path), which makes oracle and GPU
  * comparable SAMPLE BY SAMPLE.
+ *
+ * One function is NOT a restatement of the reference: rayIntersectOrdered (nori_oracle_trace_ordered) walks the
+ * same tree with the children of every inner node in other orders, to test on the CPU that the reference-order
+ * answer does not depend on the visiting order (what the GPU kernels rely on for large scenes).  Nothing else
+ * uses it; in particular no render and no pin above goes through it.
  */
 #include "nori_gpu.h"
 #include <algorithm>
