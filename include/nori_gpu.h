@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NORI_GPU_ABI_VERSION 2
+#define NORI_GPU_ABI_VERSION 3
 #define NORI_FILTER_RESOLUTION 32          /* include/nori/rfilter.h:25 */
 #define NORI_BLOCK_SIZE 32                 /* include/nori/block.h:30   */
 
@@ -194,6 +194,9 @@ typedef struct {
     uint64_t kernel_launches;   /* CUDA kernels launched by render / trace calls              */
     double   render_ms;         /* device time of the last nori_gpu_render (CUDA events)      */
     double   trace_ms;          /* device time of the last nori_gpu_trace kernel              */
+    uint64_t max_stack_depth;   /* with "stats" on: deepest per-ray traversal stack of the large-scene kernels (entries) */
+    uint64_t guard_retraces;    /* with "stats" on: near-child-first closest-hit queries in which a second candidate appeared
+                                   within 2^-11 of the best hit and that were answered again in the reference's child order */
 } nori_gpu_stats;
 
 /* per-kernel-class accounting of nori_gpu_render since the last reset (ms only with option
@@ -240,7 +243,12 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
  * thread per remaining path once at most this many paths are alive and none is left to start; default
  * 32768, 0 = never),
  * "shadow_pass" (path_mis NEE rays: 1 their own state-machine pass, 2 inside the shade kernel,
- * 0 (default) by scene size), "traversal" (1 plain per-lane loops, 2 warp state machine, 0 by size). */
+ * 0 (default) by scene size), "traversal" (1 plain per-lane loops, 2 warp state machine, 0 by size),
+ * "trace_kernel" (test hook routing of nori_gpu_trace: 0 (default) one thread per ray over the reference nodes in the
+ * order "order" selects; 2: the rays are loaded into path-pool slots and answered by the kernels that render large
+ * scenes -- the warp-state-machine closest-hit / any-hit kernels with the configured "order" / "wide" layout; per-ray
+ * counters are then 0, the totals are in nori_gpu_get_kernel_stats, and any-hit rays start at Epsilon like the NEE
+ * rays those kernels trace, arealight.cpp:56). */
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);
 
 /* Render sample indices [spp_begin, spp_begin+spp_count) for every pixel and ACCUMULATE them into

@@ -2,7 +2,7 @@
 must match the header exactly; tests/test_abi.py checks every sizeof against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FILTER_RESOLUTION = 32
 BLOCK_SIZE = 32
 
@@ -97,7 +97,7 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("shadow_rays", u64), ("nodes_visited", u64),
                 ("prims_tested", u64), ("invalid_samples", u64), ("iterations", u64), ("kernel_launches", u64),
-                ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("max_stack_depth", u64), ("guard_retraces", u64)]
 
 
 class KernelStats(C.Structure):

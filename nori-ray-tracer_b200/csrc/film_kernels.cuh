@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(128) k_trace(DScene sc, const nori_gpu_ray *ra
     const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const nori_gpu_ray r = rays[i];
-    Hit h; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-    bool found = traverse<SHADOW, true>(sc, mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, h, cnt);
+    Hit h; TraceCounters cnt;
+    bool found = traverse<SHADOW, true, true>(sc, mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, h, cnt, sc.ordered != 0);
     nori_gpu_hit o;
     o.t = h.t; o.u = h.u; o.v = h.v; o.shape = NORI_NO_HIT; o.prim = NORI_NO_HIT;
     o.nodes_visited = cnt.nodes; o.prims_tested = cnt.prims; o.reserved = 0;
@@ -232,6 +232,50 @@ __global__ void __launch_bounds__(128) k_trace(DScene sc, const nori_gpu_ray *ra
         o.shape = __float_as_uint(sc.prims[3 * h.leafpos + 1].w);
     }
     out[i] = o;
+}
+
+// nori_gpu_trace through the LARGE-SCENE RENDER KERNELS (option "trace_kernel" = 2): the caller's rays are loaded into
+// path-pool slots exactly as k_shade leaves them (closest-hit: an alive path with its next ray; any-hit: a deferred
+// NEE ray with a pending contribution of 1), k_extend_sm / k_shadow_sm run one iteration over the pool with the
+// configured child order and node layout, and the answers are read back from the slots.  The batch has no camera
+// samples (total_samples = 0), so the kernels regenerate nothing.
+template <bool SHADOW>
+__global__ void k_trace_load(Pool pool, const nori_gpu_ray *rays, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool.P) return;
+    if (i >= n) { pool.sid[i] = NORI_FREE_SLOT; pool.flags[i] = 0u; return; }
+    const nori_gpu_ray r = rays[i];
+    pool.rayO[i] = make_float4(r.o[0], r.o[1], r.o[2], r.mint);
+    pool.hit[i] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __uint_as_float(NORI_NO_HIT));
+    pool.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    pool.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pool.rng[i] = 0ull; pool.sid[i] = i;
+    if (SHADOW) {                                           // k_shadow_sm: origin = rayO, mint = Epsilon, direction / far end = shD
+        pool.shD[i] = make_float4(r.d[0], r.d[1], r.d[2], r.maxt);
+        pool.shC[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+        pool.flags[i] = PF_ALIVE | PF_SHADOW;
+    } else {
+        pool.rayD[i] = make_float4(r.d[0], r.d[1], r.d[2], r.maxt);
+        pool.flags[i] = PF_ALIVE | PF_FIRST;
+    }
+}
+template <bool SHADOW>
+__global__ void k_trace_store(DScene sc, Pool pool, uint32_t n, nori_gpu_hit *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nori_gpu_hit o;
+    o.t = __int_as_float(0x7f800000); o.u = 0.f; o.v = 0.f; o.shape = NORI_NO_HIT; o.prim = NORI_NO_HIT;
+    o.nodes_visited = 0; o.prims_tested = 0; o.reserved = 0;   // per-ray counters do not exist here: see get_kernel_stats
+    if (SHADOW) { if (pool.rad[i].x == 0.f) o.t = 0.f; }        // the pending contribution was added iff the ray is free
+    else if (pool.flags[i] & PF_ALIVE) {                        // a miss ended the path (missRule); a hit left its record
+        const float4 h = pool.hit[i];
+        const uint32_t leafpos = __float_as_uint(h.w);
+        o.t = h.x; o.u = h.y; o.v = h.z;
+        o.prim = __float_as_uint(sc.prims[3 * leafpos].w);
+        o.shape = __float_as_uint(sc.prims[3 * leafpos + 1].w);
+    }
+    out[i] = o;
+    pool.sid[i] = NORI_FREE_SLOT; pool.flags[i] = 0u;           // hand the pool back empty
 }
 
 __global__ void k_pcg32(uint64_t initstate, uint64_t initseq, unsigned long long n, float *outf, uint32_t *outu) {

@@ -239,6 +239,9 @@ bool noriBuildWideLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices
             const uint32_t *b = t.box(j);
             o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = t.leaf(j) ? t.leafRef(j) : recOf[j];
             o[4] = b[3]; o[5] = b[4]; o[6] = b[5];
+            // rank of this slot in the reference's depth-first order (node indices ARE that order: a left subtree precedes
+            // its sibling): visiting the hit slots by rank walks the leaves exactly as bvh.cpp:430-433 does
+            for (int q = 0; q < 4; ++q) { const uint32_t jq = slots[4 * (size_t) r + q]; if (jq != 0xffffffffu && jq < j) ++o[7]; }
         }
     return true;
 }

@@ -18,7 +18,8 @@
 bool noriBuildPairLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices, std::vector<uint32_t> &out, uint32_t &rootRef);
 
 // 4-wide records: one 128-byte record (32 words) per group of merged nodes, depth-first order, record 0 = root:
-//   slot k = words 8k..8k+7 = {bmin, ref}{bmax, 0}; unused slots hold the empty-leaf reference 0x80000000
+//   slot k = words 8k..8k+7 = {bmin, ref}{bmax, rank}; unused slots hold the empty-leaf reference 0x80000000;
+//   rank = position of the slot's subtree among the record's slots in the reference's depth-first (leaf) order
 //   child reference: bit 31 = leaf (as above); inner: record index
 // Starting from a binary inner node's two children, the inner slot with the largest box surface is replaced by its
 // own children until four slots are filled; empty leaves (bvh.cpp:437) are dropped.  Same preconditions as the

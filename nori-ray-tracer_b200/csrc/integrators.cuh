@@ -95,11 +95,11 @@ struct RayStats { uint32_t rays, shadow; TraceCounters cnt; };
 
 template <bool COUNT>
 __device__ __forceinline__ bool closestHit(const DScene &sc, const Ray &r, Hit &h, RayStats &rs) {
-    ++rs.rays; return traverse<false, COUNT>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt);
+    ++rs.rays; return traverse<false, COUNT, true>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt, sc.ordered != 0);
 }
 template <bool COUNT>
 __device__ __forceinline__ bool anyHit(const DScene &sc, const Ray &r, RayStats &rs) {
-    Hit h; ++rs.rays; ++rs.shadow; return traverse<true, COUNT>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt);
+    Hit h; ++rs.rays; ++rs.shadow; return traverse<true, COUNT, true>(sc, r.o, r.d, r.mint, r.maxt, h, rs.cnt, sc.ordered != 0);
 }
 
 template <bool COUNT, bool MIS>

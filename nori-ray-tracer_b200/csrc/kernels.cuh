@@ -40,12 +40,14 @@ struct Pool {
 struct Counters {
     unsigned long long next_sample, total_samples, done;
     unsigned long long rays_ext, rays_sh, nodes_ext, prims_ext, nodes_sh, prims_sh, invalid;
+    unsigned long long guard_redo;           // with counters on: near-first queries answered again in reference order (traverse.cuh: order guard)
     unsigned long long rays_sh_closest;      // volumetric.cpp:63: the medium vertex's NEE query is a closest-hit one
     // per-iteration scheduling state, double-buffered by iteration parity: k_extend(it) uses [it & 1]
     // and zeroes [(it + 1) & 1], whose last readers (the kernels of iteration it - 1) have finished
     uint32_t qcount[2][NORI_NQ];
     uint32_t eqcount[2][NORI_NEQ];            // emitter-sorted mode: entries per (bsdf type, emitter type)
     uint32_t work_extend[2], work_shadow[2];
+    uint32_t max_stack;                      // with counters on: deepest per-ray stack of the large-scene kernels
 };
 
 struct Batch {
@@ -58,6 +60,11 @@ struct Batch {
 __device__ __forceinline__ void warpAdd(unsigned long long *dst, uint32_t v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long) v);
+}
+
+__device__ __forceinline__ void warpMax(uint32_t *dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(dst, v);
 }
 
 __device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uint32_t sid, V3 rad) {

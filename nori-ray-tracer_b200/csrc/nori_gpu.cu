@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#define NORI_DEFAULT_RESULTS_MB 8192
 static std::string g_init_error;
 
 struct nori_gpu_ctx {
@@ -39,9 +40,10 @@ struct nori_gpu_ctx {
     float4 *results = nullptr; size_t results_cap = 0;      // in float4 elements
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;      // device / pinned host
     float4 *flush_buf = nullptr; size_t flush_n = 0;
+    void *scratch = nullptr; size_t scratch_cap = 0;       // staging for resolve / variance / trace / probes / pcg32
 
     // options
-    int64_t opt_pool = 1 << 20, opt_results_mb = 8192, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
+    int64_t opt_pool = 1 << 20, opt_results_mb = NORI_DEFAULT_RESULTS_MB, opt_stats = 0, opt_megakernel = 0, opt_poll = 8;
     int64_t opt_emitter_sort = 1;      // path_mis with emitters of several types: (material, emitter type)-sorted shading queues
     uint32_t n_emitter_types = 0, emitter_type_mask = 0; bool has_envmap = false;
     int64_t opt_area_only = 1;         // scenes lit by area lights only: shade kernels compiled without the other emitter types
@@ -53,6 +55,7 @@ struct nori_gpu_ctx {
     int64_t opt_order = 2;
     int64_t opt_wide = 1;              // 1: large-scene kernels walk the 4-wide layout (with the near-first order)
     int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
+    int64_t opt_trace_kernel = 0;      // nori_gpu_trace: 0 k_trace (per-lane loops over the reference nodes), 2 the large-scene render kernels
 
     nori_gpu_stats stats{};
     nori_gpu_kernel_stats kstats[NORI_K_COUNT]{};
@@ -151,7 +154,7 @@ void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     freeAll(ctx->scene_allocs); freeAll(ctx->pool_allocs);
     cudaFree(ctx->arena);
-    cudaFree(ctx->film); cudaFree(ctx->vsum); cudaFree(ctx->vsum2); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf);
+    cudaFree(ctx->film); cudaFree(ctx->vsum); cudaFree(ctx->vsum2); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf); cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_ctr);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -174,6 +177,13 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     REQUIRE(ctx && name, "set_option: null argument");
     std::string k(name);
     if (k == "pool") { REQUIRE(value >= 1024 && value <= (1ll << 26), "pool must be in [1024, 2^26]"); ctx->opt_pool = value; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
+    else if (k == "reset_options") {
+        // every scheduling option back to its default (tests: a finalizer calls this so that no test leaks its settings)
+        if (ctx->opt_pool != (1 << 20)) { ctx->opt_pool = 1 << 20; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
+        ctx->opt_results_mb = NORI_DEFAULT_RESULTS_MB; ctx->opt_stats = 0; ctx->opt_megakernel = 0; ctx->opt_poll = 8; ctx->opt_emitter_sort = 1;
+        ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
+        ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0;
+    }
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
     else if (k == "stats") ctx->opt_stats = value != 0;
     else if (k == "megakernel") ctx->opt_megakernel = value != 0;
@@ -190,6 +200,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         }
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
+    else if (k == "trace_kernel") { REQUIRE(value == 0 || value == 2, "trace_kernel must be 0 (k_trace) or 2 (k_extend_sm / k_shadow_sm)"); ctx->opt_trace_kernel = value; }
     else if (k == "wide") { REQUIRE(value == 0 || value == 1, "wide must be 0 or 1"); ctx->opt_wide = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
     else if (k == "area_only") ctx->opt_area_only = value != 0;
@@ -503,6 +514,8 @@ static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     ctx->stats.rays += c.rays_ext + c.rays_sh + c.rays_sh_closest; ctx->stats.shadow_rays += c.rays_sh;
     ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
     ctx->stats.invalid_samples += c.invalid;
+    ctx->stats.max_stack_depth = std::max<uint64_t>(ctx->stats.max_stack_depth, c.max_stack);
+    ctx->stats.guard_retraces += c.guard_redo;
     if (ctx->last_wave) {
         // shadow rays are traced inside k_shade unless the deferred pass ran
         nori_gpu_kernel_stats &e = ctx->kstats[NORI_K_EXTEND], &s = ctx->kstats[ctx->last_defer ? NORI_K_SHADOW : NORI_K_SHADE];
@@ -579,6 +592,65 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
     return 0;
 }
 
+// Reusable device scratch for the calls that stage a host buffer (resolve, variance, trace, probes, pcg32): grown on
+// demand, never shrunk, freed with the context -- no cudaMalloc / cudaFree on any per-call path.
+static int scratch(nori_gpu_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_cap) {
+        cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_cap = 0;
+        CK(cudaMalloc(&ctx->scratch, bytes));
+        ctx->scratch_cap = bytes;
+    }
+    *out = ctx->scratch;
+    return 0;
+}
+
+// nori_gpu_trace with option "trace_kernel" = 2: the rays go through the kernels that render large scenes
+// (k_extend_sm / k_shadow_sm of wave_extend.cu, with the configured child order, node layout and counter variant),
+// one pool-sized chunk at a time.  See k_trace_load / k_trace_store (film_kernels.cuh).
+static int traceThroughRenderKernels(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int shadow, nori_gpu_hit *out) {
+    const bool count = ctx->opt_stats != 0;
+    ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
+    ctx->ds.wide = ctx->opt_wide ? 1 : 0;
+    if (ensurePool(ctx, true, false)) return 1;
+    const uint32_t P = ctx->pool.P;
+    if (ensureResults(ctx, P)) return 1;
+    nori_gpu_ray *dr = nullptr;
+    if (scratch(ctx, (size_t) P * (sizeof(nori_gpu_ray) + sizeof(nori_gpu_hit)), (void **) &dr)) return 1;
+    nori_gpu_hit *dh = (nori_gpu_hit *) (dr + P);
+    DScene ds = ctx->ds;
+    ds.camera.type = NORI_CAMERA_PERSPECTIVE;              // a miss ends the path here: no per-channel restarts (kernels.cuh: endOfPath)
+    const int lay = noriSmLayout(ds);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const ExtendKernel kext = noriPickExtend(true, count, false, lay);
+    int occE = 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
+    const int gridE = sms * std::max(1, occE), gridShadow = sms * std::max(1, noriShadowSmOccupancy(count, lay));
+    Batch bt{}; bt.results = ctx->results; bt.seed = 0; bt.spp_first = 0; bt.wh = P;
+    float msTotal = 0.f;
+    ctx->last_wave = true; ctx->last_defer = true;
+    for (uint64_t done = 0; done < n; done += P) {
+        const uint32_t nb = (uint32_t) std::min<uint64_t>(P, n - done);
+        CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream));      // total_samples = 0: nothing is regenerated
+        CK(cudaMemcpyAsync(dr, rays + done, (size_t) nb * sizeof(nori_gpu_ray), cudaMemcpyHostToDevice, ctx->stream));
+        const unsigned gridP = (P + 255) / 256;
+        if (shadow) k_trace_load<true><<<gridP, 256, 0, ctx->stream>>>(ctx->pool, dr, nb);
+        else k_trace_load<false><<<gridP, 256, 0, ctx->stream>>>(ctx->pool, dr, nb);
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (shadow) LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ds, ctx->pool, bt, ctx->ctr, 0));
+        else LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ds, ctx->pool, bt, ctx->ctr, 0)));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (shadow) k_trace_store<true><<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ds, ctx->pool, nb, dh);
+        else k_trace_store<false><<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ds, ctx->pool, nb, dh);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + done, dh, (size_t) nb * sizeof(nori_gpu_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); msTotal += ms;
+        if (foldStats(ctx, 0)) return 1;                   // rays / boxes / primitive tests into the kernel classes' counters
+    }
+    ctx->stats.trace_ms = msTotal;
+    return 0;
+}
+
 extern "C" {
 
 int nori_gpu_render(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed) {
@@ -605,12 +677,11 @@ int nori_gpu_download_variance(nori_gpu_ctx *ctx, float *rgb) {
     REQUIRE(ctx->vsum && ctx->var_passes > 0, "download_variance: enable option \"variance\" before rendering");
     CK(cudaSetDevice(ctx->device));
     float *d = nullptr; size_t n = (size_t) ctx->W * ctx->H * 3;
-    CK(cudaMalloc((void **) &d, n * sizeof(float)));
+    if (scratch(ctx, n * sizeof(float), (void **) &d)) return 1;
     dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
     k_variance<<<grid, blk, 0, ctx->stream>>>(ctx->vsum, ctx->vsum2, d, ctx->W, ctx->H, ctx->border, (float) ctx->var_passes);
     cudaError_t e = cudaMemcpyAsync(rgb, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
     if (e != cudaSuccess) { ctx->err = std::string("download_variance: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
@@ -650,12 +721,11 @@ int nori_gpu_resolve(nori_gpu_ctx *ctx, float *rgb) {
     REQUIRE(ctx && ctx->has_scene && rgb, "resolve: no scene / null buffer");
     CK(cudaSetDevice(ctx->device));
     float *d = nullptr; size_t n = (size_t) ctx->W * ctx->H * 3;
-    CK(cudaMalloc((void **) &d, n * sizeof(float)));
+    if (scratch(ctx, n * sizeof(float), (void **) &d)) return 1;
     dim3 blk(32, 8), grid((ctx->W + 31) / 32, (ctx->H + 7) / 8);
     k_resolve<<<grid, blk, 0, ctx->stream>>>(ctx->film, d, ctx->W, ctx->H, ctx->border);
     cudaError_t e = cudaMemcpyAsync(rgb, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
     if (e != cudaSuccess) { ctx->err = std::string("resolve: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
@@ -665,9 +735,10 @@ int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int 
     if (n == 0) return 0;                                  // empty batch is a no-op
     REQUIRE(rays && out, "trace: null buffer");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->opt_trace_kernel == 2) return traceThroughRenderKernels(ctx, rays, n, shadow, out);
     nori_gpu_ray *dr = nullptr; nori_gpu_hit *dh = nullptr;
-    CK(cudaMalloc((void **) &dr, n * sizeof(nori_gpu_ray)));
-    if (cudaMalloc((void **) &dh, n * sizeof(nori_gpu_hit)) != cudaSuccess) { cudaFree(dr); ctx->err = "trace: out of device memory"; return 1; }
+    if (scratch(ctx, n * (sizeof(nori_gpu_ray) + sizeof(nori_gpu_hit)), (void **) &dr)) return 1;
+    dh = (nori_gpu_hit *) (dr + n);
     cudaError_t e = cudaMemcpyAsync(dr, rays, n * sizeof(nori_gpu_ray), cudaMemcpyHostToDevice, ctx->stream);
     cudaEventRecord(ctx->ev0, ctx->stream);
     const unsigned grid = (unsigned) ((n + 127) / 128);
@@ -681,7 +752,6 @@ int nori_gpu_trace(nori_gpu_ctx *ctx, const nori_gpu_ray *rays, uint64_t n, int 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     float ms = 0.f; if (e == cudaSuccess) cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.trace_ms = ms;
-    cudaFree(dr); cudaFree(dh);
     if (e != cudaSuccess) { ctx->err = std::string("trace: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
@@ -696,8 +766,8 @@ static int probeImpl(nori_gpu_ctx *ctx, bool bsdf, uint32_t index, uint64_t n, c
     CK(cudaSetDevice(ctx->device));
     const size_t ni = (bsdf ? 10 : 5) * n, no = (bsdf ? 12 : 15) * n;
     float *di = nullptr, *dout = nullptr;
-    CK(cudaMalloc((void **) &di, ni * 4));
-    if (cudaMalloc((void **) &dout, no * 4) != cudaSuccess) { cudaFree(di); ctx->err = "probe: out of device memory"; return 1; }
+    if (scratch(ctx, (ni + no) * 4, (void **) &di)) return 1;
+    dout = di + ni;
     cudaError_t e = cudaMemcpyAsync(di, in, ni * 4, cudaMemcpyHostToDevice, ctx->stream);
     const unsigned grid = (unsigned) ((n + 127) / 128);
     if (bsdf) k_probe_bsdf<<<grid, 128, 0, ctx->stream>>>(ctx->ds, index, n, di, dout);
@@ -705,7 +775,6 @@ static int probeImpl(nori_gpu_ctx *ctx, bool bsdf, uint32_t index, uint64_t n, c
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, no * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(di); cudaFree(dout);
     if (e != cudaSuccess) { ctx->err = std::string("probe: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
@@ -716,11 +785,10 @@ static int pcgImpl(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint
     REQUIRE(outf || outu, "pcg32: null buffer");
     CK(cudaSetDevice(ctx->device));
     void *d = nullptr;
-    CK(cudaMalloc(&d, n * 4));
+    if (scratch(ctx, n * 4, &d)) return 1;
     k_pcg32<<<1, 1, 0, ctx->stream>>>(initstate, initseq, n, outf ? (float *) d : nullptr, outf ? nullptr : (uint32_t *) d);
     cudaError_t e = cudaMemcpyAsync(outf ? (void *) outf : (void *) outu, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
     if (e != cudaSuccess) { ctx->err = std::string("pcg32: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }

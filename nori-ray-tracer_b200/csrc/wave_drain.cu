@@ -10,7 +10,7 @@
 // code (bit-identical results), including the per-channel restarts of chromatic aberration.
 template <bool MIS, bool COUNT>
 __global__ void __launch_bounds__(128) k_drain(DScene sc, Pool pool, Batch bt, Counters *ctr) {
-    uint32_t nRays = 0, nShadow = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t nRays = 0, nShadow = 0, nDone = 0; TraceCounters cnt;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.P; slot += stride) {
         while (pool.flags[slot] & PF_ALIVE) {                       // one pass per colour channel (one pass normally)

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
         ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
-    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt;
     while (true) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&ctr->work_extend[par], NORI_FETCH);
@@ -227,10 +227,41 @@ struct LaneStack2 {
 // bbox.h:336-363 on one child box, plus the interval test of bvh.cpp:423
 template <bool PLAIN = false>
 __device__ __forceinline__ bool boxTest(const RayTrav &r, float3 mn, float3 mx, float &nearT) {
-    if (PLAIN) return boxPlain(r.o, r.rcp, r.mint, r.maxt, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, nearT);
+    if (PLAIN) return boxPlain(r.o, r.rcp, r.mint, r.cull, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, nearT);
     nearT = __int_as_float(0xff800000); float farT = __int_as_float(0x7f800000);
     return slab(r.o.x, r.d.x, r.rcp.x, mn.x, mx.x, nearT, farT) && slab(r.o.y, r.d.y, r.rcp.y, mn.y, mx.y, nearT, farT)
-        && slab(r.o.z, r.d.z, r.rcp.z, mn.z, mx.z, nearT, farT) && (r.mint <= farT && nearT <= r.maxt);
+        && slab(r.o.z, r.d.z, r.rcp.z, mn.z, mx.z, nearT, farT) && (r.mint <= farT && nearT <= r.cull);
+}
+
+// The order guard of traverse.cuh for one lane.  A second hit candidate within the margin of the current best ends the
+// near-first query and the lane starts over in REFERENCE MODE (bit NORI_REFMODE of LaneTrav::neg): left child first --
+// in the 4-wide records: hit slots in slot order, which host_bvh.cpp keeps depth-first -- with the exact distance
+// cull and the reference's `t <= maxt` acceptance, i.e. bvh.cpp:404-462 step for step (the merged nodes' own box
+// tests are implied by their children's: nested boxes, nested intervals).  Still inside the state machine: the other
+// lanes of the warp do not wait for it.
+#define NORI_REFMODE 0x80000000u
+template <int LAY, bool COUNT>
+__device__ __forceinline__ void smCandidate(const DScene &sc, const float4 *rayD, LaneTrav &L, const float4 &r1, const float4 &r2, float t, float u, float v,
+                                            uint32_t i, TraceCounters &cnt) {
+    RayTrav &r = L.r;
+    float m = 0.f;
+#if NORI_ORDER_GUARD
+    if (sc.ordered && !(L.neg & NORI_REFMODE)) {
+        m = guardMargin(r1, r2, r.d);
+        if (r.found && (t >= 2.0f * r.hit.t - r.cull || t >= __fmul_rn(r.hit.t, 1.0f - m))) {      // a second candidate: start over in reference mode
+            if (COUNT) ++cnt.redo;
+            L.neg = NORI_REFMODE; L.st = ST_NODE;
+            L.cur = LAY == 2 ? sc.root_ref4 : sc.root_ref; r.node = 0; r.sp = 0;  // the root's own box was passed at the start
+            r.found = false; r.cull = rayD[L.slot].w;                              // the query's own far end (not kept in a register)
+            r.hit.t = __int_as_float(0x7f800000); r.hit.u = 0.f; r.hit.v = 0.f; r.hit.leafpos = NORI_NO_HIT;
+            return;
+        }
+    }
+#else                                                        // experiment: the leaf-position tie rule alone
+    if (!(!r.found || t < r.hit.t || i > r.hit.leafpos)) return;
+#endif
+    r.found = true; r.cull = __fmaf_rn(t, m, t);            // reference mode / reference order: m = 0, the exact cull
+    r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
 }
 
 // continue with child `ref`: an inner child becomes the current node, a leaf child the current primitive range
@@ -247,7 +278,7 @@ __device__ __forceinline__ void smPop2(LaneTrav &L, const LaneStack2 &stack) {
     RayTrav &r = L.r;
     while (r.sp) {
         const uint2 e = stack.pop(--r.sp);
-        if (__uint_as_float(e.y) <= r.maxt && smEnter(L, e.x)) return;
+        if (__uint_as_float(e.y) <= r.cull && smEnter(L, e.x)) return;
     }
     L.st = ST_DONE;
 }
@@ -269,7 +300,7 @@ __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack
     const bool hitN = swap ? hitR : hitL, hitF = swap ? hitL : hitR;
     const float nearF = swap ? nearL : nearR;
     if (hitN) {
-        if (hitF) stack.push(r.sp++, refF, nearF);
+        if (hitF) { stack.push(r.sp++, refF, nearF); if (COUNT) cnt.maxsp = max(cnt.maxsp, r.sp); }
         if (smEnter(L, refN)) return;
     } else if (hitF && smEnter(L, refF)) return;
     smPop2(L, stack);
@@ -304,10 +335,27 @@ __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack
         if (h2) { if (any) stack.push(r.sp++, ref, 0.f); ref = a2.w; any = true; }
         if (h1) { if (any) stack.push(r.sp++, ref, 0.f); ref = a1.w; any = true; }
         if (h0) { if (any) stack.push(r.sp++, ref, 0.f); ref = a0.w; any = true; }
+        if (COUNT) cnt.maxsp = max(cnt.maxsp, r.sp);
         if (any && smEnter(L, ref)) return;
         smPop2(L, stack);
         return;
     }
+#if NORI_ORDER_GUARD
+    if (L.neg & NORI_REFMODE) {
+        // reference mode (rare): the hit slots in the reference's depth-first order -- their rank is the spare word of
+        // each slot -- pushed last to first with their entry distances, so that the pops walk them first to last
+#pragma unroll
+        for (uint32_t rank = 4; rank-- > 0;) {
+            if (h0 && a0.w != 0x80000000u && b0.w == rank) stack.push(r.sp++, a0.w, n0);
+            if (h1 && a1.w != 0x80000000u && b1.w == rank) stack.push(r.sp++, a1.w, n1);
+            if (h2 && a2.w != 0x80000000u && b2.w == rank) stack.push(r.sp++, a2.w, n2);
+            if (h3 && a3.w != 0x80000000u && b3.w == rank) stack.push(r.sp++, a3.w, n3);
+        }
+        if (COUNT) cnt.maxsp = max(cnt.maxsp, r.sp);
+        smPop2(L, stack);
+        return;
+    }
+#endif
     // sort key: the entry distance (capped below the "missed" key +inf; a pushed distance is only used to cull)
     const float inf = __int_as_float(0x7f800000), big = __int_as_float(0x7f7fffff);
     float k0 = (h0 && a0.w != 0x80000000u) ? fminf(n0, big) : inf, k1 = (h1 && a1.w != 0x80000000u) ? fminf(n1, big) : inf;
@@ -320,12 +368,13 @@ __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack
     if (k3 < inf) stack.push(r.sp++, r3, k3);
     if (k2 < inf) stack.push(r.sp++, r2, k2);
     if (k1 < inf) stack.push(r.sp++, r1, k1);
+    if (COUNT) cnt.maxsp = max(cnt.maxsp, r.sp);
     if (k0 < inf && smEnter(L, r0)) return;
     smPop2(L, stack);
 }
 
-template <bool SHADOW, bool COUNT>
-__device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
+template <int LAY, bool SHADOW, bool COUNT>
+__device__ __forceinline__ void smPrim2(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint32_t i = L.leafI;
     const float4 r0 = __ldg(&sc.prims[3 * i]);
@@ -335,20 +384,20 @@ __device__ __forceinline__ void smPrim2(const DScene &sc, LaneTrav &L, LaneStack
     float u = 0.f, v = 0.f, t;
     bool h;
     if (__float_as_uint(r2.w) == 0u)
-        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
+        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.cull, u, v, t);
     else
-        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.maxt, t);
-    if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
-        r.found = true;
-        if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }
-        r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
+        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.cull, t);
+    if (h) {
+        if (SHADOW) { r.found = true; r.hit.t = 0.f; L.st = ST_DONE; return; }
+        smCandidate<LAY, COUNT>(sc, rayD, L, r1, r2, t, u, v, i, cnt);
+        if (L.st != ST_LEAF) return;                        // the order guard restarted the lane
     }
     if (++L.leafI < L.leafEnd) return;
     smPop2(L, stack);
 }
 
 template <bool SHADOW, bool COUNT, bool WIDE>
-__device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt, bool canRefill) {
+__device__ __forceinline__ void smRun2(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt, bool canRefill) {
     while (true) {
         const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
         const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
@@ -357,10 +406,10 @@ __device__ __forceinline__ void smRun2(const DScene &sc, LaneTrav &L, LaneStack2
         if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
             if (L.st == ST_LEAF) {
                 const uint32_t leafEnd = L.leafEnd;                  // up to NORI_LEAF_BURST primitives of THIS leaf per step
-                smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+                smPrim2<WIDE ? 2 : 1, SHADOW, COUNT>(sc, rayD, L, stack, cnt);
 #pragma unroll 1
                 for (int k = 1; k < NORI_LEAF_BURST; ++k)
-                    if (L.st == ST_LEAF && L.leafEnd == leafEnd && L.leafI > 0) smPrim2<SHADOW, COUNT>(sc, L, stack, cnt);
+                    if (L.st == ST_LEAF && L.leafEnd == leafEnd && L.leafI > 0) smPrim2<WIDE ? 2 : 1, SHADOW, COUNT>(sc, rayD, L, stack, cnt);
             }
         } else {
             if (L.st == ST_NODE) { if (WIDE) smNode4<SHADOW, COUNT>(sc, L, stack, cnt); else smNode2<COUNT>(sc, L, stack, cnt); }
@@ -376,7 +425,8 @@ __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 
     if (LAY == 2 && !L.r.plain) {
         // The 4-wide records skip the box tests of the merged nodes, which is only equivalent while nested boxes give
         // nested slab intervals.  A ray outside rayPlain() can meet a NaN there (origin on a bounding plane, 1/d
-        // infinite: bbox.h:347-348 then rejects THAT box), so it walks the reference's own nodes, here and now.
+        // infinite: bbox.h:347-348 then rejects THAT box), so it walks the reference's own nodes in the reference's
+        // order, here and now.
         L.r.found = traverse<SHADOW, COUNT>(sc, o, d, mint, maxt, L.r.hit, cnt);
         L.st = ST_DONE;
         return;
@@ -395,11 +445,12 @@ __device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack 
     const uint4 n0 = __ldg(&sc.nodes[2 * r.node]);
     const uint4 n1 = __ldg(&sc.nodes[2 * r.node + 1]);
     if (COUNT) ++cnt.nodes;
-    if (nodeBox(r.plain, r.o, r.d, r.rcp, r.mint, r.maxt, n0, n1)) {
+    if (nodeBox(r.plain, r.o, r.d, r.rcp, r.mint, r.cull, n0, n1)) {
         if (!(n0.x & 1u)) {                                      // inner: descend() of traverse.cuh with the sign mask
             const bool swap = (L.neg >> (n0.x >> 1)) & 1u;
             const uint32_t farC = swap ? r.node + 1 : n0.y;
             stack.push(r.sp++, farC);
+            if (COUNT) cnt.maxsp = max(cnt.maxsp, r.sp);
             r.node = swap ? n0.y : r.node + 1;
             return;
         }
@@ -415,7 +466,7 @@ __device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack 
 
 // primitive phase for one lane: one primitive test
 template <bool SHADOW, bool COUNT>
-__device__ __forceinline__ void smPrim(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
+__device__ __forceinline__ void smPrim(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint32_t i = L.leafI;
     const float4 r0 = __ldg(&sc.prims[3 * i]);
@@ -425,13 +476,13 @@ __device__ __forceinline__ void smPrim(const DScene &sc, LaneTrav &L, LaneStack 
     float u = 0.f, v = 0.f, t;
     bool h;
     if (__float_as_uint(r2.w) == 0u)
-        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.maxt, u, v, t);
+        h = triTest(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), r.o, r.d, r.mint, r.cull, u, v, t);
     else
-        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.maxt, t);
-    if (h && (SHADOW || !r.found || t < r.maxt || i > r.hit.leafpos)) {
-        r.found = true;
-        if (SHADOW) { r.hit.t = 0.f; L.st = ST_DONE; return; }
-        r.maxt = t; r.hit.t = t; r.hit.u = u; r.hit.v = v; r.hit.leafpos = i;
+        h = roundTest(r0, r1, r2, r.o, r.d, r.mint, r.cull, t);
+    if (h) {
+        if (SHADOW) { r.found = true; r.hit.t = 0.f; L.st = ST_DONE; return; }
+        smCandidate<0, COUNT>(sc, rayD, L, r1, r2, t, u, v, i, cnt);
+        if (L.st != ST_LEAF) return;                        // the order guard restarted the lane
     }
     if (++L.leafI < L.leafEnd) return;
     if (r.sp == 0) { L.st = ST_DONE; return; }
@@ -442,14 +493,14 @@ __device__ __forceinline__ void smPrim(const DScene &sc, LaneTrav &L, LaneStack 
 // Step the warp until NORI_REFILL_MIN lanes are out of work (and `canRefill` says new rays exist) or no
 // lane has work left.
 template <bool SHADOW, bool COUNT>
-__device__ __forceinline__ void smRun(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt, bool canRefill) {
+__device__ __forceinline__ void smRun(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack &stack, TraceCounters &cnt, bool canRefill) {
     while (true) {
         const uint32_t mNode = __ballot_sync(0xffffffffu, L.st == ST_NODE);
         const uint32_t mLeaf = __ballot_sync(0xffffffffu, L.st == ST_LEAF);
         const uint32_t mWork = mNode | mLeaf;
         if (!mWork || (canRefill && __popc(mWork) <= 32 - NORI_REFILL_MIN)) return;
         if (mLeaf && (__popc(mLeaf) >= NORI_LEAF_MIN || !mNode)) {
-            if (L.st == ST_LEAF) smPrim<SHADOW, COUNT>(sc, L, stack, cnt);
+            if (L.st == ST_LEAF) smPrim<SHADOW, COUNT>(sc, rayD, L, stack, cnt);
         } else {
             if (L.st == ST_NODE) smNode<COUNT>(sc, L, stack, cnt);
         }
@@ -477,7 +528,7 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
         ctr->work_extend[par ^ 1u] = 0; ctr->work_shadow[par ^ 1u] = 0;
     }
     const unsigned long long total = ctr->total_samples;
-    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt;
     __shared__ uint2 s_stack_mem[(LAY ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
     LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
     LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
@@ -556,10 +607,10 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        if (LAY) smRun2<false, COUNT, LAY == 2>(sc, L, stack2, cnt, canRefill); else smRun<false, COUNT>(sc, L, stack, cnt, canRefill);
+        if (LAY) smRun2<false, COUNT, LAY == 2>(sc, pool.rayD, L, stack2, cnt, canRefill); else smRun<false, COUNT>(sc, pool.rayD, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_ext, nRays); warpAdd(&ctr->done, nDone);
-    if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); }
+    if (COUNT) { warpAdd(&ctr->nodes_ext, cnt.nodes); warpAdd(&ctr->prims_ext, cnt.prims); warpMax(&ctr->max_stack, cnt.maxsp); warpAdd(&ctr->guard_redo, cnt.redo); }
 }
 
 // ------------------------------------------------------------------------------ deferred shadow rays
@@ -570,7 +621,7 @@ template <bool COUNT, int LAY>
 __global__ void __launch_bounds__(128, NORI_SHADOW_SM_BLOCKS(LAY)) k_shadow_sm(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     const uint32_t lane = threadIdx.x & 31, par = it & 1u;
     const uint32_t ltMask = (1u << lane) - 1u;
-    uint32_t nRays = 0, nDone = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t nRays = 0, nDone = 0; TraceCounters cnt;
     __shared__ uint2 s_stack_mem[(LAY ? NORI_SM_STACK2 * 2 : NORI_SM_STACK) * 128 / 2];
     LaneStack stack; stack.sh = (uint32_t *) s_stack_mem + threadIdx.x;
     LaneStack2 stack2; stack2.sh = s_stack_mem + threadIdx.x;
@@ -614,10 +665,10 @@ __global__ void __launch_bounds__(128, NORI_SHADOW_SM_BLOCKS(LAY)) k_shadow_sm(D
         }
         const bool canRefill = moreChunks || chunkNext < NORI_FETCH;
         if (!canRefill && !__any_sync(0xffffffffu, L.st != ST_IDLE)) break;
-        if (LAY) smRun2<true, COUNT, LAY == 2>(sc, L, stack2, cnt, canRefill); else smRun<true, COUNT>(sc, L, stack, cnt, canRefill);
+        if (LAY) smRun2<true, COUNT, LAY == 2>(sc, nullptr, L, stack2, cnt, canRefill); else smRun<true, COUNT>(sc, nullptr, L, stack, cnt, canRefill);
     }
     warpAdd(&ctr->rays_sh, nRays); warpAdd(&ctr->done, nDone);
-    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); }
+    if (COUNT) { warpAdd(&ctr->nodes_sh, cnt.nodes); warpAdd(&ctr->prims_sh, cnt.prims); warpMax(&ctr->max_stack, cnt.maxsp); }
 }
 
 template <bool COUNT, int LAY> static void launchShadowSm(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it) {

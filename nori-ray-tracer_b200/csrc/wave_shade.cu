@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_sh
     for (int t = 0; t < NQ; ++t) off[t + 1] = off[t] + (ESORT ? ctr->eqcount[it & 1u][t] : ctr->qcount[it & 1u][t]);
     const uint32_t n = off[NQ];
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+    uint32_t nDone = 0, nShadow = 0, nClosest = 0; TraceCounters cnt;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 #if NORI_SHADE_TEMPLATED && NORI_SHADE_MODE != 2
         if constexpr (ESORT) {

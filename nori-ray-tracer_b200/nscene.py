@@ -68,7 +68,9 @@ class SceneData:
         self.entries = entries
         e = entries
         hdr = e["header"]
-        if int(hdr[0]) not in (1, abi.ABI_VERSION):           # version-1 containers lack images and the advanced camera fields
+        # containers written for ABI 2 are what ABI 3 reads (only nori_gpu_stats and the entry points grew);
+        # version-1 containers lack images and the advanced camera fields
+        if int(hdr[0]) not in (1, 2, abi.ABI_VERSION):
             raise ValueError("ABI version mismatch in .nscene")
         self.sample_count = int(hdr[2])
         self.nodes = np.ascontiguousarray(e["bvh.nodes"], dtype=np.uint32)

@@ -57,6 +57,15 @@ def gpu():
     g.close()
 
 
+@pytest.fixture(autouse=True)
+def _restore_gpu_options(request):
+    """Tests change scheduling options on the session-scoped context; whatever a test does (or wherever it
+    fails), the next one starts from the library's defaults."""
+    yield
+    if "gpu" in request.fixturenames:
+        request.getfixturevalue("gpu").set_option("reset_options", 0)
+
+
 SCENE_NAMES = sorted(json.load(open(os.path.join(GOLDEN, "meta.json")))["scenes"]) if os.path.exists(
     os.path.join(GOLDEN, "meta.json")) else []
 

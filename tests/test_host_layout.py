@@ -80,6 +80,24 @@ def test_wide_records_cover_the_tree(name, golden_scene):
             assert inner_slots == 0                                # greedy: an inner slot would have been opened
     assert seen_records == set(range(len(rec)))
     assert seen_leaves == set(by_start)                            # every non-empty leaf exactly once
+    # the spare word of every slot ranks the slots of its record in the reference's depth-first (= leaf) order
+    first_leaf = {}
+
+    def first(ref):                                                # first leaf position below a reference
+        if ref & EMPTY:
+            return ref & 0x1ffffff
+        if ref not in first_leaf:
+            first_leaf[ref] = min(first(int(x)) for x in rec[ref].reshape(4, 8)[:, 3] if x != EMPTY)
+        return first_leaf[ref]
+    import sys
+    sys.setrecursionlimit(10000)
+    for r in range(len(rec)):
+        slots = rec[r].reshape(4, 8)
+        used = [k for k in range(4) if slots[k, 3] != EMPTY]
+        ranks = [int(slots[k, 7]) for k in used]
+        assert sorted(ranks) == list(range(len(used)))
+        by_rank = [first(int(slots[k, 3])) for k in sorted(used, key=lambda k: slots[k, 7])]
+        assert by_rank == sorted(by_rank)
     assert 3 * max_depth <= 96                                     # the kernels' per-ray stack (NORI_STACK2_MAX)
 
 
