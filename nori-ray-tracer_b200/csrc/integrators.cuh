@@ -51,7 +51,7 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
         float w_mats = 1.0f;
         if (MIS && !(inFlags & (PF_FIRST | PF_DISCRETE))) {
             float pdf_em = emitterPdf<AO>(sc, em, e);
-            w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
+            w_mats = st.pdf_mat + pdf_em > 0.f ? fdiv(st.pdf_mat, st.pdf_mat + pdf_em) : st.pdf_mat;
         }
         V3 Le = emitterEval<AO>(sc, em, e);
         st.rad = st.rad + (MIS ? st.thr * w_mats * Le : st.thr * Le);
@@ -68,7 +68,7 @@ __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, Pat
         BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, its.uv); b.wo = woLocal;
         V3 f = evalT<BSDF>(bsdf, b);
         float pdf_mat = pdfT<BSDF>(bsdf, b);
-        float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+        float w_ems = (pdf_mat + pdf_em) > 0.0f ? fdiv(pdf_em, pdf_mat + pdf_em) : pdf_em;
         out.shadow = e.shadow;
         out.contrib = st.thr * w_ems * f * theta * Li;
         flags |= PF_SHADOW;
@@ -148,7 +148,7 @@ __device__ V3 liDirect(const DScene &sc, Pcg32 &rng, const Ray &ray, int kind, R
                 V3 f = bsdfEvalDyn(bsdf, b);
                 if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
                     float pdf_mat = bsdfPdfDyn(bsdf, b);
-                    float w_em = pdf_mat + pdf_em > 0.f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                    float w_em = pdf_mat + pdf_em > 0.f ? fdiv(pdf_em, pdf_mat + pdf_em) : pdf_em;
                     color = color + w_em * f * traced * wi.z;
                 } else color = color + f * wi.z * traced;
             }
@@ -169,7 +169,7 @@ __device__ V3 liDirect(const DScene &sc, Pcg32 &rng, const Ray &ray, int kind, R
                 V3 Le = emitterEval(sc, em, e);
                 if (kind == NORI_INTEGRATOR_DIRECT_MIS) {
                     float pdf_em = emitterPdf(sc, em, e);
-                    float w_mat = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : 0.0f;
+                    float w_mat = pdf_mat + pdf_em > 0.f ? fdiv(pdf_mat, pdf_mat + pdf_em) : 0.0f;
                     color = color + w_mat * w * Le;
                 } else color = color + w * Le;
             }
@@ -207,7 +207,7 @@ __device__ __forceinline__ bool boundsHit(const nori_gpu_medium &m, V3 o, V3 d, 
         float origin = comp(o, i), dd = comp(d, i), minVal = m.bounds_min[i], maxVal = m.bounds_max[i];
         if (dd == 0) { if (origin < minVal || origin > maxVal) return false; }
         else {
-            float rcp = 1.0f / dd;
+            float rcp = frcp(dd);
             float t1 = (minVal - origin) * rcp, t2 = (maxVal - origin) * rcp;
             if (t1 > t2) { float t = t1; t1 = t2; t2 = t; }
             nearT = std_max(t1, nearT); farT = std_min(t2, farT);
@@ -235,9 +235,9 @@ static __device__ V3 mediumSample(const nori_gpu_medium &m, const Ray &ray, Pcg3
     if (!boundsHit(m, ray.o, ray.d, nearT, farT)) { hitObject = true; return mk(1.0f); }
     V3 sp = boundsContain(m, ray.o) ? ray.o : ray.o + normalized(ray.d) * nearT;
     V3 ext = arr3(m.sigma_a) + arr3(m.sigma_s);
-    float invTr = -1.0f * logf(1 - rng.next1D()) / fmaxf(ext.x, fmaxf(ext.y, ext.z));     // medium.cpp:92-94
+    float invTr = fdiv(-1.0f * logf(1 - rng.next1D()), fmaxf(ext.x, fmaxf(ext.y, ext.z)));     // medium.cpp:92-94
     float distance = norm(sp - ray.o) + invTr;
-    V3 albedo = mk(m.sigma_s[0] / ext.x, m.sigma_s[1] / ext.y, m.sigma_s[2] / ext.z);
+    V3 albedo = mk(fdiv(m.sigma_s[0], ext.x), fdiv(m.sigma_s[1], ext.y), fdiv(m.sigma_s[2], ext.z));
     if (distance >= tMax) hitObject = true; else { p = ray.o + distance * ray.d; hitObject = false; }
     return albedo;
 }
@@ -279,7 +279,7 @@ __device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, Path
             float w_mats = 1.0f;
             if (!(inFlags & (PF_FIRST | PF_DISCRETE))) {
                 float pdf_em = emitterPdf(sc, em, l);
-                w_mats = st.pdf_mat + pdf_em > 0.f ? st.pdf_mat / (st.pdf_mat + pdf_em) : st.pdf_mat;
+                w_mats = st.pdf_mat + pdf_em > 0.f ? fdiv(st.pdf_mat, st.pdf_mat + pdf_em) : st.pdf_mat;
             }
             st.rad = st.rad + st.thr * w_mats * emitterEval(sc, em, l) * mediumTr(med, its.p, l.p);
         }
@@ -307,7 +307,7 @@ __device__ __forceinline__ void volVertex(const DScene &sc, const Hit &hit, Path
             BRec b = mkBRec(sc, *bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
             V3 f = bsdfEvalDyn(*bsdf, b);
             float pdf_mat = bsdfPdfDyn(*bsdf, b);
-            float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+            float w_ems = (pdf_mat + pdf_em) > 0.0f ? fdiv(pdf_em, pdf_mat + pdf_em) : pdf_em;
             st.rad = st.rad + st.thr * w_ems * f * theta * Li * Tr;
         }
     }
@@ -360,7 +360,7 @@ __device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) 
                 if (shp.emitter >= 0) {
                     ERec l = makeERec(cur.o, its.p, its.sh.n);
                     float pdf_em = emitterPdf(sc, sc.emitters[shp.emitter].pod, l);
-                    w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+                    w_mats = pdf_mat + pdf_em > 0.f ? fdiv(pdf_mat, pdf_mat + pdf_em) : pdf_mat;
                 }
             }
         } else if (intersection) {
@@ -382,7 +382,7 @@ __device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) 
             BRec b = mkBRec(sc, bsdf, wiLocal, M_SOLID_ANGLE, uv0); b.wo = woLocal;
                 V3 f = bsdfEvalDyn(bsdf, b);
                 float pdf_mat = bsdfPdfDyn(bsdf, b);
-                float w_ems = (pdf_mat + pdf_em) > 0.0f ? pdf_em / (pdf_mat + pdf_em) : pdf_em;
+                float w_ems = (pdf_mat + pdf_em) > 0.0f ? fdiv(pdf_em, pdf_mat + pdf_em) : pdf_em;
                 color = color + att * w_ems * f * theta * Li * mediumTr(med, its.p, e.p);
             }
             float p = fminf(att.x, 0.80f);
@@ -401,7 +401,7 @@ __device__ V3 liVolumetric(const DScene &sc, Pcg32 &rng, Ray cur, RayStats &rs) 
                 if (shp2.emitter >= 0) {
                     ERec l = makeERec(cur.o, its.p, its.sh.n);
                     float pdf_em = emitterPdf(sc, sc.emitters[shp2.emitter].pod, l);
-                    w_mats = pdf_mat + pdf_em > 0.f ? pdf_mat / (pdf_mat + pdf_em) : pdf_mat;
+                    w_mats = pdf_mat + pdf_em > 0.f ? fdiv(pdf_mat, pdf_mat + pdf_em) : pdf_mat;
                 }
                 if (b.measure == M_DISCRETE) w_mats = 1.0f;
             }

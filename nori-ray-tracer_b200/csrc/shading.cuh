@@ -17,17 +17,17 @@ __device__ __forceinline__ Frame makeFrame(V3 a) {
     Frame f; f.n = a;
     V3 c;
     if (fabsf(a.x) > fabsf(a.y)) {
-        float invLen = 1.0f / sqrtf(a.x * a.x + a.z * a.z);
+        float invLen = frsqrt(fma_(a.x, a.x, a.z * a.z));
         c = mk(a.z * invLen, 0.0f, -a.x * invLen);
     } else {
-        float invLen = 1.0f / sqrtf(a.y * a.y + a.z * a.z);
+        float invLen = frsqrt(fma_(a.y, a.y, a.z * a.z));
         c = mk(0.0f, a.z * invLen, -a.y * invLen);
     }
     f.s = cross(c, a); f.t = c;
     return f;
 }
 __device__ __forceinline__ V3 toLocal(const Frame &f, V3 v) { return mk(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }
-__device__ __forceinline__ V3 toWorld(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }
+__device__ __forceinline__ V3 toWorld(const Frame &f, V3 v) { return madd(madd(f.s * v.x, v.y, f.t), v.z, f.n); }
 
 // ImageTexture::getData / NormalMap::getData (imagetexture.cpp:98-116, normalmap.cpp:98-120): the texel at the
 // truncated coordinates, wrapped with C's % (repeat) or clamped.  A negative remainder reads in front of the
@@ -42,7 +42,7 @@ __device__ __forceinline__ V3 imageTexel(const DImage &im, float xf, float yf) {
         x = min(max((int) xf, 0), im.width - 1); y = min(max((int) yf, 0), im.height - 1);
     }
     const uint8_t *t = &im.rgb[((size_t) x + (size_t) im.width * y) * 3];
-    return mk((float) __ldg(t) / 255.f, (float) __ldg(t + 1) / 255.f, (float) __ldg(t + 2) / 255.f);
+    return mk(fdiv((float) __ldg(t), 255.f), fdiv((float) __ldg(t + 1), 255.f), fdiv((float) __ldg(t + 2), 255.f));
 }
 // ImageTexture::eval / NormalMap::eval (imagetexture.cpp:118-136, normalmap.cpp:122-139).  In the reference
 // `x` is the un-floored float uv.x * width, so dstdx = uv.x * width - x is exactly 0 and the "bilinear" blend
@@ -67,31 +67,36 @@ __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit 
         const float b1 = h.u, b2 = h.v, b0 = 1 - (b1 + b2);
         const uint32_t i0 = __ldg(&m.F[3 * prim]), i1 = __ldg(&m.F[3 * prim + 1]), i2 = __ldg(&m.F[3 * prim + 2]);
         const V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
-        its.p = (b0 * p0 + b1 * p1) + b2 * p2;
+        its.p = bary(b0, p0, b1, p1, b2, p2);
         its.uv.x = b1; its.uv.y = b2;
         if (m.has_uv) {
             its.uv.x = (b0 * __ldg(&m.UV[2 * i0]) + b1 * __ldg(&m.UV[2 * i1])) + b2 * __ldg(&m.UV[2 * i2]);
             its.uv.y = (b0 * __ldg(&m.UV[2 * i0 + 1]) + b1 * __ldg(&m.UV[2 * i1 + 1])) + b2 * __ldg(&m.UV[2 * i2 + 1]);
         }
         V3 n;
-        if (m.has_n) n = normalizedDyn((b0 * ld3(&m.N[3 * i0]) + b1 * ld3(&m.N[3 * i1])) + b2 * ld3(&m.N[3 * i2]));
+        if (m.has_n) n = normalizedDyn(bary(b0, ld3(&m.N[3 * i0]), b1, ld3(&m.N[3 * i1]), b2, ld3(&m.N[3 * i2])));
         else n = normalized(cross(p1 - p0, p2 - p0));
         its.sh = makeFrame(n);
         if (m.has_n && m.normal_map > 0)                          // mesh.cpp:149-154
             its.sh = makeFrame(toWorld(its.sh, normalized(imageEval<true>(sc.images[m.normal_map - 1], its.uv))));
     } else {
         const V3 c = mk(r0.x, r0.y, r0.z);
-        its.p = o + h.t * d;
+        its.p = madd(o, h.t, d);
         const V3 n = normalized(its.p - c);
         its.sh = makeFrame(n);
-        float th = acosf(n.z), ph = atan2f(n.y, n.x);            // common.cpp:264-272
-        if (ph < 0) ph += 2 * NORI_PI;
-        if (__float_as_uint(r2.w) == 1u) {                          // sphere.cpp:88-91
-            its.uv.x = (float) (0.5 + th / (2 * NORI_PI));
-            its.uv.y = ph / NORI_PI;
-        } else {                                                    // perlinnoise.cpp:71-74
-            its.uv.x = (float) (0.5 + (double) (th * 0.15915494309189533577f));
-            its.uv.y = ph * NORI_INV_PI;
+        its.uv.x = 0.f; its.uv.y = 0.f;
+        // its.uv is only ever read by a textured albedo (mkBRec; normal maps exist on meshes only): the spherical
+        // coordinates (acos + atan2) are computed for those shapes alone
+        if (sc.bsdfs[m.bsdf].albedo_texture != NORI_TEXTURE_CONSTANT) {
+            float th = acosf(n.z), ph = atan2f(n.y, n.x);            // common.cpp:264-272
+            if (ph < 0) ph += 2 * NORI_PI;
+            if (__float_as_uint(r2.w) == 1u) {                          // sphere.cpp:88-91
+                its.uv.x = (float) (0.5 + th / (2 * NORI_PI));
+                its.uv.y = ph / NORI_PI;
+            } else {                                                    // perlinnoise.cpp:71-74
+                its.uv.x = (float) (0.5 + (double) (th * 0.15915494309189533577f));
+                its.uv.y = ph * NORI_INV_PI;
+            }
         }
     }
 }
@@ -101,14 +106,38 @@ __device__ __forceinline__ V3 sphericalDir(float theta, float phi) {
     float st, ct, sp, cp; sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
     return mk(st * cp, st * sp, ct);
 }
+#if NORI_FAST_SHADING
+// The reference's warps compute theta = acos / atan(..) and then sin(theta), cos(theta) again.  Here the direction
+// is built from cos(theta) AND sin(theta), each derived directly from the warped sample (never sin from 1 - cos^2,
+// which loses everything near the pole), and the azimuth 2 pi y goes through the MUFU sine / cosine after an exact
+// shift into [-pi, pi) (absolute error < 4e-7): no acosf / atan, no sincosf range reduction.
+__device__ __forceinline__ V3 sphericalDirCS(float ct, float st, float y) {
+    float sp, cp; __sincosf(__fmul_rn(2.f * NORI_PI, __fsub_rn(y, 0.5f)), &sp, &cp);   // sin / cos(phi - pi) = -sin / -cos(phi)
+    return mk(-__fmul_rn(st, cp), -__fmul_rn(st, sp), ct);
+}
+__device__ __forceinline__ V3 squareToUniformSphere(P2 s) {                     // cos = 1 - 2 (1 - x), sin^2 = (1 - cos)(1 + cos)
+    const float ct = 1 - 2 * (1 - s.x);
+    return sphericalDirCS(ct, fsqrt(fmaxf(0.0f, (1.0f - ct) * (1.0f + ct))), s.y);
+}
+__device__ __forceinline__ V3 squareToCosineHemisphere(P2 s) {                  // cos^2 = 1 - (1 - x), sin^2 = 1 - cos^2
+    const float c2 = 1 - (1 - s.x);
+    return sphericalDirCS(fsqrt(c2), fsqrt(1.0f - c2), s.y);
+}
+__device__ __forceinline__ V3 squareToBeckmann(P2 s, float alpha) {            // tan^2 = -alpha^2 log(1 - x); cos = 1 / sqrt(1 + tan^2), sin = tan cos
+    const float t2 = -(alpha * alpha) * logf(1 - s.x);
+    const float ct = frsqrt(1.0f + t2);
+    return sphericalDirCS(ct, fsqrt(t2) * ct, s.y);
+}
+#else
 __device__ __forceinline__ V3 squareToUniformSphere(P2 s) { return sphericalDir(acosf(1 - 2 * (1 - s.x)), 2.f * NORI_PI * s.y); }   // :86-91
 __device__ __forceinline__ V3 squareToCosineHemisphere(P2 s) { return sphericalDir(acosf(sqrtf(1 - (1 - s.x))), 2.f * NORI_PI * s.y); }  // :110-115
 __device__ __forceinline__ V3 squareToBeckmann(P2 s, float alpha) {                                                      // :122-127
     float theta = (float) atan(sqrt(-((double) alpha * (double) alpha) * (double) logf(1 - s.x)));
     return sphericalDir(theta, 2 * NORI_PI * s.y);
 }
+#endif
 __device__ __forceinline__ V3 squareToUniformTriangle(P2 s) {                                                            // :135-140
-    float su1 = sqrtf(s.x); float u = 1.f - su1, v = s.y * su1;
+    float su1 = fsqrt(s.x); float u = 1.f - su1, v = s.y * su1;
     return mk(u, v, 1.f - u - v);
 }
 __device__ __forceinline__ P2 squareToConcentricDisk(P2 s) {                                                             // :143-162
@@ -119,6 +148,26 @@ __device__ __forceinline__ P2 squareToConcentricDisk(P2 s) {                    
     else { rad = oy; theta = NORI_PI * 0.5f - NORI_PI * 0.25f * (ox / oy); }
     r.x = rad * cosf(theta); r.y = rad * sinf(theta); return r;
 }
+#if NORI_FAST_SHADING
+__device__ __forceinline__ V3 squareToGTR2(P2 s, float alpha) {
+    // The reference's theta = acos(c), c = sqrt((1 - x) / (1 + (a2 - 1) x)) in float: for a glossy lobe c is within a few
+    // ulps of 1 and its LAST BITS decide theta (alpha = 1e-3: one ulp of c is 10 % of theta).  c is therefore computed
+    // with the reference's own roundings (IEEE division and square root), and sin(theta) = sin(acos(c)) from that c as
+    // sqrt((1 - c)(1 + c)) (1 - c is exact).
+    const float a2 = alpha * alpha;
+    const float c = __fsqrt_rn(__fdiv_rn(1.0f - s.x, __fadd_rn(1.0f, __fmul_rn(a2 - 1.0f, s.x))));
+    return sphericalDirCS(c, fsqrt(fmaxf(0.0f, (1.0f - c) * (1.0f + c))), s.y);
+}
+__device__ __forceinline__ float squareToGTR2Pdf(V3 m, float alpha) {
+    // the reference evaluates 1 + (double) (a2 - 1.0f) * c^2 in double, where the FLOAT a2 - 1.0f has already rounded a2
+    // to a2' = fl(a2 - 1) + 1 (for alpha = 1e-3 up to 3 % off a2); in float the same quantity without the cancellation
+    // is sin^2 + a2' cos^2 with sin^2 = (1 - c)(1 + c)
+    const float a2 = alpha * alpha, a2r = __fadd_rn(__fsub_rn(a2, 1.0f), 1.0f), c = m.z;
+    const float den = __fmaf_rn(a2r, c * c, (1.0f - c) * (1.0f + c));
+    const float pdf = fdiv(a2 * c * NORI_INV_PI, den * den);
+    return (c >= 0 && fabsf(sqnorm(m) - 1.0f) < 1.0f) ? pdf : 0.0f;
+}
+#else
 __device__ __forceinline__ V3 squareToGTR2(P2 s, float alpha) {                                                          // :180-185
     float a2 = (float) ((double) alpha * (double) alpha);
     return sphericalDir(acosf(sqrtf((1.0f - s.x) / (1.0f + (a2 - 1.0f) * s.x))), 2 * NORI_PI * s.y);
@@ -130,20 +179,21 @@ __device__ __forceinline__ float squareToGTR2Pdf(V3 m, float alpha) {           
     float pdf = (float) ((double) (a2 * c * NORI_INV_PI) / (den * den));
     return (c >= 0 && fabsf(sqnorm(m) - 1.0f) < 1.0f) ? pdf : 0.0f;
 }
+#endif
 
 // common.cpp:285-314
 __device__ __forceinline__ float fresnel(float cosThetaI, float extIOR, float intIOR) {
     float etaI = extIOR, etaT = intIOR;
     if (extIOR == intIOR) return 0.0f;
     if (cosThetaI < 0.0f) { float t = etaI; etaI = etaT; etaT = t; cosThetaI = -cosThetaI; }
-    float eta = etaI / etaT, sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
+    float eta = fdiv(etaI, etaT), sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
     if (sinThetaTSqr > 1.0f) return 1.0f;
-    float cosThetaT = sqrtf(1.0f - sinThetaTSqr);
-    float Rs = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
-    float Rp = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
-    return (Rs * Rs + Rp * Rp) / 2.0f;
+    float cosThetaT = fsqrt(1.0f - sinThetaTSqr);
+    float Rs = fdiv(etaI * cosThetaI - etaT * cosThetaT, etaI * cosThetaI + etaT * cosThetaT);
+    float Rp = fdiv(etaT * cosThetaI - etaI * cosThetaT, etaT * cosThetaI + etaI * cosThetaT);
+    return (Rs * Rs + Rp * Rp) * 0.5f;
 }
-__device__ __forceinline__ float tanTheta(V3 v) { float t = 1 - v.z * v.z; if (t <= 0.0f) return 0.0f; return sqrtf(t) / v.z; }   // frame.h:81-86
+__device__ __forceinline__ float tanTheta(V3 v) { float t = 1 - v.z * v.z; if (t <= 0.0f) return 0.0f; return fdiv(fsqrt(t), v.z); }   // frame.h:81-86
 
 // ------------------------------------------------------------------------------ BSDFs
 enum { M_UNKNOWN = 0, M_SOLID_ANGLE = 1, M_DISCRETE = 2 };
@@ -159,22 +209,27 @@ __device__ __forceinline__ V3 albedoAt(const DScene &sc, const nori_gpu_bsdf &b,
     return arr3(b.albedo);                                        // consttexture.cpp:30-32
 }
 __device__ __forceinline__ float evalBeckmann(float alpha, V3 m) {                                    // microfacet.cpp:52-58
-    float temp = tanTheta(m) / alpha, ct = m.z, ct2 = ct * ct;
-    return expf(-temp * temp) / (NORI_PI * alpha * alpha * ct2 * ct2);
+    float temp = fdiv(tanTheta(m), alpha), ct = m.z, ct2 = ct * ct;
+    return fdiv(expf(-temp * temp), NORI_PI * alpha * alpha * ct2 * ct2);
 }
 __device__ __forceinline__ float smithBeckmannG1(float alpha, V3 v, V3 m) {                            // microfacet.cpp:61-82
     float tt = tanTheta(v);
     if (tt == 0.0f) return 1.0f;
     if (dot(m, v) * v.z <= 0) return 0.0f;
-    float a = 1.0f / (alpha * tt);
+    float a = frcp(alpha * tt);
     if (a >= 1.6f) return 1.0f;
     float a2 = a * a;
-    return (3.535f * a + 2.181f * a2) / (1.0f + 2.276f * a + 2.577f * a2);
+    return fdiv(3.535f * a + 2.181f * a2, 1.0f + 2.276f * a + 2.577f * a2);
 }
 __device__ __forceinline__ float schlickFresnel(float u) {                                             // disney.cpp:26-30
-    float m = fminf(1.0f, fmaxf(0.0f, 1 - u)); double md = m; return (float) (md * md * md * md * md);
+    float m = fminf(1.0f, fmaxf(0.0f, 1 - u));
+#if NORI_FAST_SHADING
+    const float m2 = m * m; return m2 * m2 * m;
+#else
+    double md = m; return (float) (md * md * md * md * md);
+#endif
 }
-__device__ __forceinline__ float ggx(float NdotV, float alphaG) { float a = alphaG * alphaG, b = NdotV * NdotV; return 1 / (NdotV + sqrtf(a + b - a * b)); }   // disney.cpp:32-37
+__device__ __forceinline__ float ggx(float NdotV, float alphaG) { float a = alphaG * alphaG, b = NdotV * NdotV; return frcp(NdotV + fsqrt(a + b - a * b)); }   // disney.cpp:32-37
 __device__ __forceinline__ V3 lerp3(float t, V3 a, V3 b) { return (1.0f - t) * a + t * b; }                 // disney.cpp:40-43
 __device__ __forceinline__ float luminance(V3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }   // common.cpp:233-235
 
@@ -184,25 +239,30 @@ __device__ __forceinline__ V3 bsdfEval(const nori_gpu_bsdf &b, const BRec &r) {
         if (r.measure != M_SOLID_ANGLE || r.wi.z <= 0 || r.wo.z <= 0) return mk(0.f);
         return r.albedo * NORI_INV_PI;
     } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:84-94
-        V3 n = normalized(r.wi + r.wo);
+        V3 n = xnormalized(xadd(r.wi, r.wo));                     // exact: 1 - n.z^2 (tanTheta) cancels for glossy lobes
         float D = evalBeckmann(b.alpha, n);
         float F = fresnel(dot(n, r.wi), b.extIOR, b.intIOR);
         float G = smithBeckmannG1(b.alpha, r.wi, n) * smithBeckmannG1(b.alpha, r.wo, n);
         float denom = 4.0f * r.wi.z * r.wo.z;
-        float spec = b.ks * D * F * G / denom;
+        float spec = fdiv(b.ks * D * F * G, denom);
         V3 kd = arr3(b.kd) * NORI_INV_PI;
         return mk(kd.x + spec, kd.y + spec, kd.z + spec);
     } else if (TYPE == NORI_BSDF_DISNEY) {                        // disney.cpp:63-105
         float NdotV = r.wi.z, NdotL = r.wo.z;
         if (NdotV < 0 || NdotL < 0) return mk(0.f);
-        V3 wh = normalized(r.wi + r.wo);
+        V3 wh = xnormalized(xadd(r.wi, r.wo));
         float LdotH = dot(r.wo, wh), VdotH = dot(r.wi, wh);
         V3 base = arr3(b.baseColor), white = mk(1.f);
         float lum = luminance(base);
-        V3 Ctint = lum > 0.f ? mk(base.x / lum, base.y / lum, base.z / lum) : mk(1.0f);
+        V3 Ctint = lum > 0.f ? base / lum : mk(1.0f);
+#if NORI_FAST_SHADING
+        V3 CtintMix = (b.specular * 0.08f) * lerp3(b.specularTint, white, Ctint);
+        float fd90 = __fmaf_rn(2 * b.roughness, VdotH * VdotH, 0.5f);
+#else
         V3 CtintMix = (float) ((double) b.specular * 0.08) * lerp3(b.specularTint, white, Ctint);
-        V3 Cspec = lerp3(b.metallic, CtintMix, base);
         float fd90 = (float) (0.5 + (double) (2 * b.roughness) * ((double) VdotH * (double) VdotH));
+#endif
+        V3 Cspec = lerp3(b.metallic, CtintMix, base);
         float fl = schlickFresnel(NdotL), fv = schlickFresnel(NdotV);
         V3 diffuse = base * NORI_INV_PI * (1.f + (fd90 - 1.f) * fl) * (1.f + (fd90 - 1.f) * fv);
         float alpha = fmaxf(0.001f, b.roughness * b.roughness);
@@ -224,13 +284,13 @@ __device__ __forceinline__ float bsdfPdf(const nori_gpu_bsdf &b, const BRec &r) 
         return NORI_INV_PI * r.wo.z;
     } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:97-111
         float c = r.wo.z; if (c <= 0.0f) return 0.0f;
-        V3 n = normalized(r.wi + r.wo);
-        float metallicTerm = evalBeckmann(b.alpha, n) * n.z / (4.0f * fabsf(dot(n, r.wo)));
+        V3 n = xnormalized(xadd(r.wi, r.wo));
+        float metallicTerm = fdiv(evalBeckmann(b.alpha, n) * n.z, 4.0f * fabsf(dot(n, r.wo)));
         return b.ks * metallicTerm + (1 - b.ks) * (c * NORI_INV_PI);
     } else if (TYPE == NORI_BSDF_DISNEY) {                        // disney.cpp:108-121
         float c = r.wo.z; if (c <= 0.0f) return 0.0f;
-        V3 n = normalized(r.wi + r.wo);
-        float metallicTerm = squareToGTR2Pdf(n, b.alpha) * n.z / (4.0f * fabsf(dot(n, r.wo)));
+        V3 n = xnormalized(xadd(r.wi, r.wo));
+        float metallicTerm = fdiv(squareToGTR2Pdf(n, b.alpha) * n.z, 4.0f * fabsf(dot(n, r.wo)));
         return (1 - b.metallic) * (c * NORI_INV_PI) + b.metallic * metallicTerm;
     }
     return 0.0f;
@@ -261,12 +321,16 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
         float theta = r.wi.z; V3 nv = mk(0.f, 0.f, 1.0f);
         if (fresnel(theta, b.extIOR, b.intIOR) > s.x) r.wo = mk(-r.wi.x, -r.wi.y, r.wi.z);
         else {
-            float factor = b.extIOR / b.intIOR;
-            if (theta < 0.0f) { factor = 1 / factor; nv.z *= -1; }
+            float factor = fdiv(b.extIOR, b.intIOR);
+            if (theta < 0.0f) { factor = frcp(factor); nv.z *= -1; }
             float win = dot(r.wi, nv);
             V3 part1 = -factor * (r.wi - win * nv);
+#if NORI_FAST_SHADING
+            V3 part2 = -nv * fsqrt(__fmaf_rn(-(factor * factor), __fmaf_rn(-win, win, 1.0f), 1.0f));
+#else
             double f2 = (double) factor * (double) factor, w2 = (double) win * (double) win;
             V3 part2 = -nv * (float) sqrt(1 - f2 * (1 - w2));
+#endif
             r.wo = normalized(part1 + part2);
         }
         r.measure = M_DISCRETE;
@@ -274,11 +338,11 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
     } else if (TYPE == NORI_BSDF_MICROFACET) {                    // microfacet.cpp:114-137
         if (r.wi.z <= 0.0f) return mk(0.f);
         if (s.x < b.ks) {
-            P2 ns; ns.x = s.x / b.ks; ns.y = s.y;
+            P2 ns; ns.x = fdiv(s.x, b.ks); ns.y = s.y;
             V3 n = squareToBeckmann(ns, b.alpha);
             r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
         } else {
-            P2 ns; ns.x = (s.x - b.ks) / (1.f - b.ks); ns.y = s.y;
+            P2 ns; ns.x = fdiv(s.x - b.ks, 1.f - b.ks); ns.y = s.y;
             r.wo = squareToCosineHemisphere(ns);
         }
         float c = r.wo.z; if (c <= 0.f) return mk(0.f);
@@ -286,11 +350,11 @@ __device__ __forceinline__ V3 bsdfSample(const nori_gpu_bsdf &b, BRec &r, P2 s) 
     } else {                                                      // disney.cpp:124-145
         if (r.wi.z <= 0.0f) return mk(0.f);
         if (s.x <= b.metallic) {
-            P2 ns; ns.x = s.x / b.metallic; ns.y = s.y;
+            P2 ns; ns.x = fdiv(s.x, b.metallic); ns.y = s.y;
             V3 n = squareToGTR2(ns, b.alpha);
             r.wo = normalized((2.0f * dot(r.wi, n) * n) - r.wi);
         } else {
-            P2 ns; ns.x = (s.x - b.metallic) / (1 - b.metallic); ns.y = s.y;
+            P2 ns; ns.x = fdiv(s.x - b.metallic, 1 - b.metallic); ns.y = s.y;
             r.wo = squareToCosineHemisphere(ns);
         }
         float c = r.wo.z; if (c <= 0.0f) return mk(0.f);
@@ -356,7 +420,7 @@ __device__ __forceinline__ uint32_t cdfSampleReuse(const float *cdf, uint32_t nE
     int idx = (int) lo - 1; if (idx < 0) idx = 0;
     if ((uint32_t) idx > nEntries - 2) idx = (int) nEntries - 2;
     float c0 = __ldg(&cdf[idx]), c1 = __ldg(&cdf[idx + 1]);
-    s = (s - c0) / (c1 - c0);
+    s = fdiv(s - c0, c1 - c0);
     return (uint32_t) idx;
 }
 
@@ -367,8 +431,8 @@ __device__ __forceinline__ void sampleSurface(const DShape &m, P2 s, V3 &p, V3 &
         V3 bc = squareToUniformTriangle(s);
         uint32_t i0 = __ldg(&m.F[3 * idT]), i1 = __ldg(&m.F[3 * idT + 1]), i2 = __ldg(&m.F[3 * idT + 2]);
         V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
-        p = (bc.x * p0 + bc.y * p1) + bc.z * p2;
-        if (m.has_n) n = normalizedDyn((bc.x * ld3(&m.N[3 * i0]) + bc.y * ld3(&m.N[3 * i1])) + bc.z * ld3(&m.N[3 * i2]));
+        p = bary(bc.x, p0, bc.y, p1, bc.z, p2);
+        if (m.has_n) n = normalizedDyn(bary(bc.x, ld3(&m.N[3 * i0]), bc.y, ld3(&m.N[3 * i1]), bc.z, ld3(&m.N[3 * i2])));
         else n = normalized(cross(p1 - p0, p2 - p0));
         pdf = m.area_normalization;
 #if NORI_WITH_PERLIN
@@ -475,7 +539,7 @@ __device__ __forceinline__ V3 emitterSample(const DScene &sc, const nori_gpu_emi
         l.wi = normalized(l.p - l.ref);
         l.shadow = mkray(l.ref, l.wi, NORI_EPS, norm(l.p - l.ref) - NORI_EPS);
         l.pdf = emitterPdf<AO>(sc, e, l);
-        float att = dot(l.n, -l.wi) / sqnorm(l.p - l.ref);
+        float att = fdiv(dot(l.n, -l.wi), sqnorm(l.p - l.ref));
         return l.pdf > 0.0f ? emitterEval<AO>(sc, e, l) * att / l.pdf : mk(0.f);
     }
     case NORI_EMITTER_POINT: {                                    // pointlight.cpp:15-24
@@ -523,7 +587,7 @@ __device__ __forceinline__ V3 xfPoint(const float *m, V3 p) {                // 
     float r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = ((m[4 * i] * p.x + m[4 * i + 1] * p.y) + m[4 * i + 2] * p.z) + m[4 * i + 3] * 1.0f;
-    return mk(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
+    return xdivs(mk(r[0], r[1], r[2]), r[3]);
 }
 __device__ __forceinline__ V3 xfVector(const float *m, V3 v) {               // transform.h:68-70
     return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
@@ -535,11 +599,13 @@ __device__ __forceinline__ P2 squareToUniformDisk(P2 s) {                    // 
 __device__ __forceinline__ bool hasChromaticAberrations(const nori_gpu_camera &c) {   // advancedCamera.cpp:230-232
     return c.type == NORI_CAMERA_ADVANCED && !(c.chromatic[0] == 0.f && c.chromatic[1] == 0.f && c.chromatic[2] == 0.f);
 }
+// Camera rays are built in the EXACT arithmetic in every build (x* operations, IEEE division / square root): the first
+// vertex of every path -- hit primitive, hit point -- then equals the reference's for the same film sample.
 // perspective.cpp:90-112, thinlens.cpp:126-171, advancedCamera.cpp:133-228.  `weight` is the camera's importance
 // weight: Color3f(1), or the unit colour of `channel` when chromatic aberration is on (advancedCamera.cpp:176-183).
 __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as, int channel, V3 &weight) {
     V3 nearP = xfPoint(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
-    V3 d = normalized(nearP);
+    V3 d = xnormalized(nearP);
     weight = mk(1.f);
     Ray ray;
     if (c.type == NORI_CAMERA_ADVANCED) {
@@ -557,7 +623,7 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             }
             const float distortionFactor = r / y;
             nearP.x *= distortionFactor; nearP.y *= distortionFactor;
-            d = normalized(nearP);
+            d = xnormalized(nearP);
         }
         float w = 0.0f;
         if (chroma) { w = c.chromatic[channel]; weight = mk(channel == 0 ? 1.f : 0.f, channel == 1 ? 1.f : 0.f, channel == 2 ? 1.f : 0.f); }
@@ -566,15 +632,15 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             P2 disk = squareToUniformDisk(as);
             float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
             float ft = c.focalDistance / d.z;
-            V3 pFocus = mk(0.f) + ft * d;
+            V3 pFocus = xadd(mk(0.f), xscale(d, ft));
             float spx = ps.x - (0.5f * (float) c.width), spy = ps.y - (0.5f * (float) c.height);
             const float mx = (float) max(c.width, c.height);
             spx /= mx; spy /= mx;
             const float sq = spx * spx + spy * spy;
             const float dx = spx * sq * w, dy = spy * sq * w;
-            pFocus = pFocus + mk(-dx, dy, 0.0f);
+            pFocus = xadd(pFocus, mk(-dx, dy, 0.0f));
             V3 o = mk(lx, ly, 0.0f);
-            V3 dir = normalized(pFocus - o);
+            V3 dir = xnormalized(xsub(pFocus, o));
             ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
         } else {
             ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
@@ -587,9 +653,9 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
         P2 disk = squareToConcentricDisk(as);
         float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
         float ft = c.focalDistance / d.z;
-        V3 pFocus = mk(0.f) + ft * d;
+        V3 pFocus = xadd(mk(0.f), xscale(d, ft));
         V3 o = mk(lx, ly, 0.0f);
-        V3 dir = normalized(pFocus - o);
+        V3 dir = xnormalized(xsub(pFocus, o));
         ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
     } else {
         ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);

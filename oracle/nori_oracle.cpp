@@ -1313,8 +1313,8 @@ void nori_oracle_render_samples(void *h, uint32_t spp_begin, uint32_t spp_count,
  * mode 0: per-path streams (as above); mode 1: the reference's mapping -- one pcg32 per 32x32 block,
  * seeded (offset.x, offset.y) when spp_begin == 0 and carried across passes through `block_rng`
  * (2 x uint64 per block, caller-owned, may be NULL if a single call renders everything). */
-void nori_oracle_render_var(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
-                            float *film, uint64_t *block_rng, float *vsum, float *vsum2) {
+static void renderVarImpl(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
+                          float *film, uint64_t *block_rng, float *vsum, float *vsum2, const float *given) {
     Scene *sc = (Scene *) h; const int W = sc->pod.camera.width, H = sc->pod.camera.height, b = sc->border;
     const int fcols = W + 2 * b, BS = NORI_BLOCK_SIZE;
     const int nbx = (W + BS - 1) / BS, nby = (H + BS - 1) / BS;
@@ -1334,7 +1334,12 @@ void nori_oracle_render_var(void *h, uint32_t spp_begin, uint32_t spp_count, uin
             for (int y = 0; y < bh; ++y) for (int x = 0; x < bw; ++x) {
                 Pcg32 path; Pcg32 *rng = &rngs[bi];
                 if (mode == 0) { path.seed(seed + spp_begin + k, (uint64_t) (y + oy) * W + (x + ox)); rng = &path; }
-                P2 ps; V3 v = cameraSample(*sc, *rng, x + ox, y + oy, ps);
+                P2 ps; V3 v;
+                if (given) {                                    /* radiance supplied by the caller: only the film position is drawn */
+                    P2 a = rng->next2D(); ps.x = (float) (x + ox) + a.x; ps.y = (float) (y + oy) + a.y;
+                    const float *g = &given[(((size_t) k * H + (y + oy)) * W + (x + ox)) * 4];
+                    v = g[3] != 0.f ? V3(g[0], g[1], g[2]) : V3(-1.f);              /* dropped samples stay dropped (block.cpp:94-98) */
+                } else v = cameraSample(*sc, *rng, x + ox, y + oy, ps);
                 if (!validColor(v)) __atomic_fetch_add(&sc->invalid, 1, __ATOMIC_RELAXED);
                 blockPut(*sc, blk.data(), ox, oy, BS, BS, ps, v);
             }
@@ -1401,6 +1406,18 @@ void nori_oracle_emitter_probe(void *h, uint32_t emitter, uint64_t n, const floa
     }
 }
 
+void nori_oracle_render_var(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
+                            float *film, uint64_t *block_rng, float *vsum, float *vsum2) {
+    renderVarImpl(h, spp_begin, spp_count, seed, mode, film, block_rng, vsum, vsum2, nullptr);
+}
+/* ImageBlock::put / put(block) / the variance statistic applied to radiance values supplied by the caller
+ * (samples[(k*H + y)*W + x] = (r,g,b,valid), the layout of nori_oracle_render_samples) at the film positions of the
+ * per-path streams (RNG mode 0): the film semantics of block.cpp:93-133 and render.cpp:238-247 on their own, whatever
+ * produced the radiance.  vsum / vsum2 may be NULL. */
+void nori_oracle_splat(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, const float *samples,
+                       float *film, float *vsum, float *vsum2) {
+    renderVarImpl(h, spp_begin, spp_count, seed, 0, film, nullptr, vsum, vsum2, samples);
+}
 void nori_oracle_render(void *h, uint32_t spp_begin, uint32_t spp_count, uint64_t seed, int mode,
                         float *film, uint64_t *block_rng) {
     nori_oracle_render_var(h, spp_begin, spp_count, seed, mode, film, block_rng, nullptr, nullptr);

@@ -31,6 +31,7 @@ def _load(abi):
     lib.nori_oracle_render_samples.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     lib.nori_oracle_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     lib.nori_oracle_render_var.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nori_oracle_splat.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nori_oracle_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nori_oracle_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
     lib.nori_oracle_reset_stats.argtypes = [C.c_void_p]
@@ -102,6 +103,20 @@ class Oracle:
         vs = np.zeros((self.scene.height, self.scene.width, 3), np.float32); vs2 = np.zeros_like(vs)
         self.lib.nori_oracle_render_var(self.h, 0, spp, seed, mode, film.ctypes.data, None, vs.ctypes.data, vs2.ctypes.data)
         n = np.float32(spp)
+        return film, vs2 / n - (vs / n) ** 2
+
+    def splat(self, samples, spp_begin, seed=0, variance=False):
+        """Film (and optionally the variance image) of the given per-sample radiance values (the layout of
+        render_samples) at the film positions of the per-path streams: ImageBlock::put on its own."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        film = np.zeros(self.scene.film_shape, np.float32)
+        vs = np.zeros((self.scene.height, self.scene.width, 3), np.float32) if variance else None
+        vs2 = np.zeros_like(vs) if variance else None
+        self.lib.nori_oracle_splat(self.h, spp_begin, samples.shape[0], seed, samples.ctypes.data, film.ctypes.data,
+                                   vs.ctypes.data if variance else None, vs2.ctypes.data if variance else None)
+        if not variance:
+            return film
+        n = np.float32(samples.shape[0])
         return film, vs2 / n - (vs / n) ** 2
 
     def resolve(self, film):

@@ -1,7 +1,7 @@
 """Registers / spills / stack / shared memory per kernel from csrc/ptxas.log (nvcc -Xptxas -v).
 usage: python tools/ptxas_table.py [regex]"""
 import os, re, subprocess, sys
-log = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "nori-ray-tracer_b200", "csrc", "ptxas.log")).read()
+log = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "nori-ray-tracer_b200", "csrc", "obj", "ptxas.log")).read()
 pat = re.compile(sys.argv[1]) if len(sys.argv) > 1 else None
 cur = None
 for line in log.splitlines():
