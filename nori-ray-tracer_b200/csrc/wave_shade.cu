@@ -68,7 +68,7 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
 #define NORI_SHADE_THREADS 128
 #endif
 #ifndef NORI_SHADE_MINBLOCKS
-#define NORI_SHADE_MINBLOCKS 6
+#define NORI_SHADE_MINBLOCKS 8
 #endif
 template <int MODE, bool COUNT, bool DEFER, bool ESORT, bool AO>
 __global__ void __launch_bounds__(NORI_SHADE_THREADS, NORI_SHADE_MINBLOCKS) k_shade(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
