@@ -13,9 +13,18 @@ accumulation buffers are summed onto rank 0 by ONE NCCL reduce inside the timed 
 metric = Msamples/s (whole job).  `value` is timed on the device (CUDA events on the stream the
 kernels run on + the reduce on torch's stream, max over ranks) with the scene resident in HBM;
 `e2e` goes through the public host API with host buffers (scene upload + render + film download)
-and is timed on the host clock.  One extra profiled step brackets every kernel launch with CUDA
-events for the roofline line, and one extra step with traversal counters on measures the
-algorithmic bytes per ray (B_ray = 32 B/node + 48 B/primitive + 48 B ray/hit record).
+and is timed on the host clock.
+
+What else the line carries (all measured live in this run unless it says "profile"):
+  roofline      N = 1: the HBM roofline of k_extend_sm on BASELINE config 4 (10 M triangles, 0.7 GB >> L2) -- the
+                configuration SURVEY 8(d) names as the one where the HBM fraction is a real grade.
+  roofline_c2   the headline workload's dominant kernel.  Its scene is 14 primitives and L1-resident, so its bound
+                is the issue slot, not HBM: issue-slot utilisation and lanes per instruction come from the committed
+                ncu profile, times and the (nominal) algorithmic bytes from this run.
+  cpu_baseline  the reference binary on the host cores at 16 AND 64 spp (the two must agree within 5 %).
+  configs       N = 1: BASELINE configs 1, 3 and the per-GPU share of 5 with image checks against their fixtures.
+  strong, large_scene, c5   N > 1: the fixed 1024-spp job, the 10 M-triangle scene at 16 spp and (N = 8) config 5
+                at its stated size, each sharded over the N GPUs, with the single-GPU time of the same job.
 """
 import argparse
 import json
@@ -34,46 +43,21 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SCENE = os.path.join(GOLDEN, "cbox_path_mis.nscene")
 WIDTH, HEIGHT, SPP = 800, 600, 1024
 WORKLOAD = "cornell-box(pa4/cbox) path_mis 800x600 @1024spp per GPU"
+PROFILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json:
-    dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch at the bench's pool size)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        t = json.load(open(p)).get(kernel)
-        if t:
-            return float(t["dram_bytes_per_launch"])
+def shared_config(spp, world):
+    """`config` is the same object in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "spp_per_gpu": spp, "total_spp": spp * world,
+            "l2": "working set (path pool + 7.9 GB sample buffer) >> L2 and L2 flushed between timed steps"}
+
+
+def profile_entry(kernel):
+    """Numbers of the committed `ncu --set full` capture of `kernel` (profiles/r02_traffic.json): DRAM bytes per launch,
+    issue-slot utilisation, lanes per instruction."""
+    if os.path.exists(PROFILE):
+        return json.load(open(PROFILE)).get(kernel)
     return None
-
-
-def large_scene_probe(g, host_scene, peak):
-    """BASELINE config 4 (10M-triangle height field, path_mis, 3840x2160): a short supplementary measurement of
-    the large-scene kernels -- here the scene (0.7 GB) is far larger than L2, so the HBM fraction is a real one.
-    Untimed extra of rank 0; NOT part of `value`."""
-    import time as _t
-    t0 = _t.perf_counter()
-    sc = host_scene.heightfield_scene(n=2237)
-    build_s = _t.perf_counter() - t0
-    g.upload_scene(sc)
-    g.set_option("pool", 1 << 22)
-    g.render(0, 2, seed=1)
-    g.set_option("stats", 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); kc = g.kernel_stats(); g.set_option("stats", 0)
-    g.set_option("kernel_timing", 1); g.reset_stats(); g.clear_film(); g.render(0, 8, seed=1)
-    st, ks = g.stats(), g.kernel_stats()
-    g.set_option("kernel_timing", 0)
-    out = {"workload": "10M-triangle height field (9,999,392 triangles, reference-identical SAH tree) path_mis 3840x2160 @8spp",
-           "msamples_per_s": st.samples / st.render_ms / 1e3, "mrays_per_s": st.rays / st.render_ms / 1e3,
-           "ms": st.render_ms, "scene_build_s": build_s, "kernel_ms": {k: v["ms"] for k, v in ks.items() if v["ms"]},
-           "traversal": "near-child-first order on the 4-wide node layout (options order=2 auto, wide=1)"}
-    for k in ("extend", "shadow"):
-        c, t = kc[k], ks[k]
-        if c["rays"] and t["ms"]:
-            b = 32.0 * c["nodes"] / c["rays"] + 48.0 * c["prims"] / c["rays"] + 48.0
-            ach = t["rays"] * b / (t["ms"] * 1e-3) / 1e9
-            out[f"k_{k}_sm"] = {"boxes_per_ray": c["nodes"] / c["rays"], "prims_per_ray": c["prims"] / c["rays"], "bytes_per_ray": b,
-                                "grays_per_s": t["rays"] / t["ms"] / 1e6, "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak}
-    return out
 
 
 def measured_peak():
@@ -81,6 +65,89 @@ def measured_peak():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def rel_mse(a, b, f=16):
+    """mean((a-b)^2 / (b^2 + 1e-2)) on f x f box-downsampled images."""
+    import numpy as np
+
+    def ds(img):
+        h, w = (img.shape[0] // f) * f, (img.shape[1] // f) * f
+        return img[:h, :w].reshape(h // f, f, w // f, f, -1).mean((1, 3))
+    a, b = ds(a), ds(b)
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+# ------------------------------------------------------------------------------------------------
+# large scene (BASELINE config 4) and the other configs
+# ------------------------------------------------------------------------------------------------
+C4_WORKLOAD = "10M-triangle height field (9,999,392 triangles, reference-identical SAH tree) path_mis 3840x2160"
+
+
+def c4_roofline(g, host_scene, peak, peak_src):
+    """k_extend_sm / k_shadow_sm on the 10 M-triangle scene: boxes and primitives per ray from the device counters of
+    one render, Grays/s from CUDA events around every launch of another (8 spp), algorithmic bytes per ray
+    B_ray = 32 B/box + 48 B/primitive + 48 B (ray read + hit write)."""
+    t0 = time.perf_counter()
+    sc = host_scene.heightfield_scene(n=2237)
+    build_s = time.perf_counter() - t0
+    g.upload_scene(sc)
+    g.set_option("pool", 1 << 22)
+    g.render(0, 2, seed=1)
+    g.set_option("stats", 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); kc = g.kernel_stats(); g.set_option("stats", 0)
+    g.set_option("kernel_timing", 1); g.reset_stats(); g.clear_film(); g.render(0, 8, seed=1)
+    st, ks = g.stats(), g.kernel_stats()
+    g.set_option("kernel_timing", 0)
+    g.reset_stats(); g.clear_film(); g.render(0, 16, seed=1); s16 = g.stats()
+    out = {"workload": C4_WORKLOAD + " @8spp (kernel timing) / @16spp (throughput)",
+           "msamples_per_s": s16.samples / s16.render_ms / 1e3, "mrays_per_s": s16.rays / s16.render_ms / 1e3, "ms_16spp": s16.render_ms,
+           "scene_build_s": build_s, "kernel_ms_8spp": {k: v["ms"] for k, v in ks.items() if v["ms"]},
+           "traversal": "near-child-first order with the order guard on the 4-wide node layout (options order=2 auto, wide=1); "
+                        "bit-exact vs the oracle on this scene: tests/test_gpu_large_scene.py"}
+    roof = None
+    for k in ("extend", "shadow"):
+        c, t = kc[k], ks[k]
+        if c["rays"] and t["ms"]:
+            b = 32.0 * c["nodes"] / c["rays"] + 48.0 * c["prims"] / c["rays"] + 48.0
+            ach = t["rays"] * b / (t["ms"] * 1e-3) / 1e9
+            out[f"k_{k}_sm"] = {"boxes_per_ray": c["nodes"] / c["rays"], "prims_per_ray": c["prims"] / c["rays"], "bytes_per_ray": b,
+                                "grays_per_s": t["rays"] / t["ms"] / 1e6, "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak}
+            if k == "extend":
+                prof = profile_entry("k_extend_sm") or {}
+                roof = {"bound": "hbm", "kernel": "k_extend_sm", "workload": C4_WORKLOAD + " @8spp", "achieved": ach, "peak": peak,
+                        "unit": "GB/s", "frac": ach / peak, "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                        "bytes_per_ray": b, "rays_per_launch": t["rays"] / max(t["launches"], 1), "avg_launch_ms": t["ms"] / max(t["launches"], 1),
+                        "algorithmic_bytes_per_launch": b * t["rays"] / max(t["launches"], 1),
+                        "issue_active_pct": prof.get("issue_active_pct"), "lanes_per_inst": prof.get("lanes_per_inst"),
+                        "note": "the dominant kernel of BASELINE config 4, where the scene (0.7 GB) is far larger than L2 and the HBM fraction is a "
+                                "real one (SURVEY 8(d)); the headline workload's own kernels are in roofline_c2 (issue-bound: its scene is L1-resident)"}
+    return out, roof
+
+
+def other_configs(g, nscene, np):
+    """BASELINE configs 1, 3 and (the per-GPU share of) 5 on this GPU: throughput at the stated size, and the image at the
+    fixture's size and sample count against the reference binary's render of that fixture."""
+    rows = []
+
+    def run(label, name, film, spp, check_spp):
+        sc = nscene.load_scene(os.path.join(GOLDEN, f"{name}.nscene"))
+        ref_spp = json.load(open(os.path.join(GOLDEN, "meta.json")))["scenes"][name]["ref_spp"][-1]
+        ref = np.load(os.path.join(GOLDEN, f"{name}.ref{ref_spp}.npy"))
+        g.upload_scene(sc); g.set_option("pool", 1 << 18); g.clear_film(); g.render(0, check_spp, seed=77)
+        img = g.resolve()
+        err = rel_mse(img, ref)
+        sc.set_film(*film)
+        g.upload_scene(sc); g.set_option("pool", 1 << 22)
+        g.render(0, 2, seed=1); g.reset_stats(); g.clear_film(); g.render(0, spp, seed=1)
+        s = g.stats()
+        rows.append({"config": label, "res": f"{film[0]}x{film[1]}", "spp": spp, "ms": s.render_ms, "msamples_per_s": s.samples / s.render_ms / 1e3,
+                     "mrays_per_s": s.rays / s.render_ms / 1e3, "rays_per_sample": s.rays / s.samples,
+                     "image_check": {"fixture": name, "res": f"{ref.shape[1]}x{ref.shape[0]}", "spp": check_spp, "ref_spp": ref_spp,
+                                     "rel_mse_vs_reference_render": err, "ok": bool(err < 1e-3)}})
+    run("C1 sphere-mesh normals (5120 triangles, primary rays)", "sphere_mesh_normals", (768, 768), 32, 64)
+    run("C3 disney + microfacet + envmap + thin lens, path_mis", "c3_project", (800, 600), 2048, 256)
+    run("C5 volumetric + spot + envmap: per-GPU share of the 8-GPU job (4096 spp / 8 = 512 spp per GPU; 64 spp timed)", "c5_volumetric", (3840, 2160), 64, 2048)
+    return rows
 
 
 class ClockSampler(threading.Thread):
@@ -151,6 +218,17 @@ def run_reference_render(spp, width=WIDTH, height=HEIGHT):
     return time.perf_counter() - t, cores, "port"
 
 
+def reference_linearity():
+    """the per-pass cost of the reference is constant, so a 1024-spp render is extrapolated from a bounded
+    one -- provided two sample counts give the same rate.  Returns the 16- and 64-spp rates and whether they agree within 5 %."""
+    s16, cores, kind = run_reference_render(16)
+    s64, _, _ = run_reference_render(64)
+    r16, r64 = WIDTH * HEIGHT * 16 / s16 / 1e6, WIDTH * HEIGHT * 64 / s64 / 1e6
+    dev = abs(r16 - r64) / r64
+    return {"msamples_per_s_16spp": r16, "msamples_per_s_64spp": r64, "seconds_16spp": s16, "seconds_64spp": s64,
+            "relative_difference": dev, "agree_within_5pct": bool(dev <= 0.05)}, cores, kind
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -162,14 +240,16 @@ def reference_arm(args):
     for _ in range(args.steps):
         sec, cores, kind = run_reference_render(spp)
         t_total += sec
+    lin, _, _ = reference_linearity()
     samples = WIDTH * HEIGHT * spp
     value = samples * args.steps / t_total / 1e6
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{spp} of 1024 spp per step (per-pass cost is constant)"},
+            "config": shared_config(args.spp, max(args.gpus, 1)),
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind,
-                             "sample": f"cornell box 800x600 path_mis, {spp} spp per step, TBB on all host cores"},
+                             "sample": f"cornell box 800x600 path_mis, {spp} of 1024 spp per step (per-pass cost is constant: see linearity), "
+                                       "the reference's own render timer, TBB on all host cores", "linearity": lin},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -185,7 +265,8 @@ def main():
     ap.add_argument("--pool", type=int, default=1 << 22)
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one bounded reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-large-scene", action="store_true", help="skip the supplementary 10M-triangle measurement")
+    ap.add_argument("--no-large-scene", action="store_true", help="skip the 10M-triangle measurements (roofline falls back to roofline_c2's accounting)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs / the strong-scaling and C5 runs")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -219,21 +300,28 @@ def main():
         torch.cuda.synchronize()
         g.synchronize()
 
-    def step():
-        """render (device-timed by the library's events on its own stream) + the single reduce"""
+    def render_and_reduce(first, count, film):
+        """one job: render `count` sample indices from `first` (device-timed by the library's events on its own stream) +
+        the single reduce onto rank 0; returns this rank's device milliseconds"""
         g.clear_film()
-        g.render(begin, spp, seed=0)
-        ms = g.stats().render_ms
+        g.render(first, count, seed=0)
+        ms = g.stats().render_ms if count else 0.0
         if world > 1:
             ev0.record()
-            dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
             ev1.record()
             torch.cuda.synchronize()
             ms += ev0.elapsed_time(ev1)
         return ms
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
-        step()
+        render_and_reduce(begin, spp, film_t)
     clocks = ClockSampler(local)
     clocks.start()
     g.reset_stats()
@@ -241,16 +329,13 @@ def main():
     wall0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
-        dev_ms += step()
+        dev_ms += render_and_reduce(begin, spp, film_t)
         g.set_option("flush_l2", 256)                        # evict L2 between timed iterations (untimed)
     barrier()
     wall = time.perf_counter() - wall0
     clk = clocks.stop()
     st = g.stats()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = max_over_ranks(dev_ms) / args.steps
     value = world * samples_per_gpu / (ms_per_step * 1e-3) / 1e6
     rays_per_sample = st.rays / max(st.samples, 1)
 
@@ -277,14 +362,57 @@ def main():
             parts[k] += 1e3 * v / args.steps
     barrier()
     e2e_s = (time.perf_counter() - e0) / args.steps
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * samples_per_gpu / float(e2e_t.item()) / 1e6
+    e2e_value = world * samples_per_gpu / max_over_ranks(e2e_s) / 1e6
+
+    # ---- N > 1: the fixed-size jobs, sharded (every rank takes part; rank 0 reports)
+    extras = {}
+    if world > 1 and not args.no_extras:
+        film_t = torch.as_tensor(g.film_device_array(), device=f"cuda:{local}")
+        # strong scaling: ONE 1024-spp Cornell-box render over all GPUs, and the same render on one GPU (every rank
+        # times it on its own device at the same moment; the slowest is reported)
+        b0, cnt = render.shard_spp(SPP, rank, world)
+        for _ in range(2):
+            render_and_reduce(b0, cnt, film_t)
+        barrier()
+        tn = max_over_ranks(sum(render_and_reduce(b0, cnt, film_t) for _ in range(3)) / 3)
+        g.clear_film(); g.render(0, SPP, seed=0); g.clear_film(); g.render(0, SPP, seed=0)
+        t1 = max_over_ranks(g.stats().render_ms)
+        extras["strong"] = {"workload": "cornell box path_mis 800x600, ONE 1024-spp job sharded by sample index over the GPUs + one NCCL reduce",
+                            "n_gpus": world, "ms": tn, "msamples_per_s": WIDTH * HEIGHT * SPP / tn / 1e3, "single_gpu_ms": t1,
+                            "speedup": t1 / tn, "efficiency": t1 / tn / world, "spp_per_gpu": SPP // world}
+        if not args.no_large_scene:
+            hs = host_scene.heightfield_scene(n=2237)
+            g.upload_scene(hs); g.set_option("pool", 1 << 22)
+            film_c4 = torch.as_tensor(g.film_device_array(), device=f"cuda:{local}")
+            b0, cnt = render.shard_spp(16, rank, world)
+            g.render(0, 2, seed=1)
+            render_and_reduce(b0, cnt, film_c4)
+            barrier()
+            tn = max_over_ranks(render_and_reduce(b0, cnt, film_c4))
+            g.clear_film(); g.render(0, 16, seed=0)
+            t1 = max_over_ranks(g.stats().render_ms)
+            extras["large_scene"] = {"workload": C4_WORKLOAD + " @16spp sharded by sample index over the GPUs (133 MB film reduce)", "n_gpus": world, "ms": tn,
+                                     "msamples_per_s": 3840 * 2160 * 16 / tn / 1e3, "single_gpu_ms": t1, "speedup": t1 / tn,
+                                     "efficiency": t1 / tn / world}
+        if world == 8:
+            c5 = nscene.load_scene(os.path.join(GOLDEN, "c5_volumetric.nscene"))
+            c5.set_film(3840, 2160)
+            g.upload_scene(c5); g.set_option("pool", 1 << 22)
+            film_c5 = torch.as_tensor(g.film_device_array(), device=f"cuda:{local}")
+            b0, cnt = render.shard_spp(4096, rank, world)
+            g.render(0, 2, seed=1)
+            barrier()
+            tn = max_over_ranks(render_and_reduce(b0, cnt, film_c5))
+            extras["c5"] = {"workload": "BASELINE config 5: volumetric + spotlight + envmap, 3840x2160 @4096 spp sharded over 8 GPUs (512 spp each) + one reduce",
+                            "n_gpus": world, "ms": tn, "msamples_per_s": 3840 * 2160 * 4096 / tn / 1e3}
+            if rank == 0:
+                img = g.resolve()
+                extras["c5"]["image_mean"] = float(img.mean()); extras["c5"]["finite"] = bool(np.isfinite(img).all())
+        g.upload_scene(sc); g.set_option("pool", args.pool)
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: one profiled step (events around every launch) ...
+        # ---- the headline workload's kernels: one profiled step (events around every launch) ...
         g.set_option("kernel_timing", 1)
         g.reset_stats(); g.clear_film(); g.render(begin, spp, seed=0)
         ks = g.kernel_stats()
@@ -295,41 +423,54 @@ def main():
         kc = g.kernel_stats()
         g.set_option("stats", 0)
         kernel_ms = {k: v["ms"] for k, v in ks.items()}
-        # dominant trace kernel: k_extend (closest-hit + raygen) or k_shade (shading + the any-hit NEE rays)
         trace_dom = max(("extend", "shade"), key=lambda k: kernel_ms[k])
         c = kc[trace_dom]
         b_ray = 32.0 * c["nodes"] / max(c["rays"], 1) + 48.0 * c["prims"] / max(c["rays"], 1) + 48.0
         k = ks[trace_dom]
         peak, peak_src = measured_peak()
         achieved = k["rays"] * b_ray / max(k["ms"] * 1e-3, 1e-12) / 1e9
-        roofline = {"bound": "hbm", "kernel": f"k_{trace_dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": measured_traffic(f"k_{trace_dom}"), "peak_source": peak_src,
-                    "bytes_per_ray": b_ray, "rays_per_launch": k["rays"] / max(k["launches"], 1),
-                    "avg_launch_ms": k["ms"] / max(k["launches"], 1), "kernel_ms_per_step": kernel_ms,
-                    "note": "scene (14 primitives, <2 KB) is L1/L2-resident: HBM fraction is small by construction; "
-                            "see profiles/ for issue-slot and L1/L2 numbers"}
+        prof = profile_entry(f"k_{trace_dom}") or {}
+        roofline_c2 = {"bound": "issue", "kernel": f"k_{trace_dom}", "workload": WORKLOAD,
+                       "issue_active_pct": prof.get("issue_active_pct"), "lanes_per_inst": prof.get("lanes_per_inst"), "lanes_peak": 32,
+                       "issue_x_lanes_frac": (prof["issue_active_pct"] / 100.0 * prof["lanes_per_inst"] / 32.0) if prof else None,
+                       "traffic": prof.get("dram_bytes_per_launch"), "dram_gbs_profile": prof.get("dram_gbs"), "profile": "profiles/ (ncu --set full, this round)",
+                       "nominal_hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "bytes_per_ray": b_ray,
+                                       "note": "algorithmic bytes of a 14-primitive scene that never leaves L1: an accounting figure, not a bandwidth"},
+                       "rays_per_launch": k["rays"] / max(k["launches"], 1), "avg_launch_ms": k["ms"] / max(k["launches"], 1),
+                       "kernel_ms_per_step": kernel_ms}
         cpu = None
         if not args.no_cpu_baseline:
-            sec, cores, kind = run_reference_render(args.ref_spp)
-            cpu = {"value": WIDTH * HEIGHT * args.ref_spp / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
-                   "sample": f"cornell box 800x600 path_mis, {args.ref_spp} of 1024 spp, reference binary with TBB on all host cores, "
-                             f"its own render timer ({sec:.2f} s)"}
+            lin, cores, kind = reference_linearity()
+            cpu = {"value": lin["msamples_per_s_64spp"], "unit": "Msamples/s", "cores": cores, "kind": kind,
+                   "sample": f"cornell box 800x600 path_mis, 64 of 1024 spp (and 16 spp: linearity), reference binary with TBB on all host cores, "
+                             f"its own render timer ({lin['seconds_64spp']:.2f} s)", "linearity": lin}
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "spp_per_gpu": spp, "total_spp": spp * world, "pool_slots": args.pool,
-                           "l2": "working set (path pool + 7.9 GB sample buffer) >> L2 and L2 flushed between timed steps"},
+                "config": shared_config(spp, world), "tuning": {"pool_slots": args.pool},
                 "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes,
                         "d2h_bytes_per_step": int(host_film.nbytes), "ms_per_step": 1e3 * e2e_s,
                         "host_ms_breakdown": {k: round(v, 3) for k, v in parts.items()}},
-                "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
-        if world == 1 and not args.no_large_scene:
+                "gpu_launches": int(st.kernel_launches), "clocks": clk, "roofline_c2": roofline_c2, "cpu_baseline": cpu}
+        line.update(extras)
+        line["roofline"] = None
+        if not args.no_large_scene:                                      # rank 0's GPU (the other ranks wait at the barrier below)
             try:
-                line["large_scene"] = large_scene_probe(g, host_scene, peak)
-            except Exception as e:                                   # supplementary: never fail the headline line
-                line["large_scene"] = {"error": str(e)[:200]}
+                c4, line["roofline"] = c4_roofline(g, host_scene, peak, peak_src)
+                line["large_scene_1gpu" if world > 1 else "large_scene"] = c4
+            except Exception as e:                                       # supplementary: never fail the headline line
+                line["large_scene_1gpu" if world > 1 else "large_scene"] = {"error": str(e)[:200]}
+        if world == 1:
+            if not args.no_extras:
+                try:
+                    line["configs"] = other_configs(g, nscene, np)
+                except Exception as e:
+                    line["configs"] = {"error": str(e)[:200]}
+        if line["roofline"] is None:                                     # no large-scene run: the nominal accounting of the headline kernel
+            line["roofline"] = dict(roofline_c2["nominal_hbm"], bound="hbm", kernel=roofline_c2["kernel"], traffic=roofline_c2["traffic"],
+                                    note="NOT a bandwidth: see roofline_c2; run without --no-large-scene (N = 1) for the config-4 roofline")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -197,6 +197,8 @@ typedef struct {
     uint64_t max_stack_depth;   /* with "stats" on: deepest per-ray traversal stack of the large-scene kernels (entries) */
     uint64_t guard_retraces;    /* with "stats" on: near-child-first closest-hit queries in which a second candidate appeared
                                    within 2^-11 of the best hit and that were answered again in the reference's child order */
+    double   reduce_ms;         /* multi-device contexts: device time of the film sum of the last nori_gpu_render (part of render_ms) */
+    uint64_t devices;           /* devices the context renders on (nori_gpu_init_multi), 1 otherwise */
 } nori_gpu_stats;
 
 /* per-kernel-class accounting of nori_gpu_render since the last reset (ms only with option
@@ -217,6 +219,18 @@ typedef struct {
 
 /* Create a context on CUDA device `device`. Replaces nothing in the reference (there is no device). */
 int nori_gpu_init(int device, nori_gpu_ctx **out);
+/* One context over `n` devices of one node ("multi-GPU inside render").  The host keeps calling the same
+ * entry points: upload_scene / set_option / clear_film act on every device (the scene is replicated); nori_gpu_render
+ * shards the sample indices [spp_begin, spp_begin + spp_count) over the devices -- device g renders [g*count/n,
+ * (g+1)*count/n), disjoint pcg32 initstate ranges, one host thread per device -- and sums the accumulation buffers onto
+ * devices[0] with one kernel that reads the peers' buffers in place over NVLink (cudaDeviceEnablePeerAccess; staged
+ * with cudaMemcpyPeerAsync where peer access is unavailable).  Film / resolve / stats calls then answer for the whole
+ * render from devices[0].  render.cpp's block loop (render.cpp:173-284) has no counterpart: TBB shares one image among
+ * the cores of one host.  The variance statistic and the test hooks (trace, probes, render_samples) stay
+ * single-device: they run on devices[0]; set_option("variance", 1) is refused.
+ * With torch.distributed (one process per GPU) use nori_gpu_init per rank and reduce nori_gpu_film_device_ptr instead. */
+int nori_gpu_init_multi(const int *devices, int n, nori_gpu_ctx **out);
+int nori_gpu_device_count(const nori_gpu_ctx *ctx);
 void nori_gpu_destroy(nori_gpu_ctx *ctx);
 const char *nori_gpu_last_error(const nori_gpu_ctx *ctx);   /* ctx may be NULL: last init error */
 

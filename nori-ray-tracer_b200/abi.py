@@ -97,7 +97,8 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays", u64), ("shadow_rays", u64), ("nodes_visited", u64),
                 ("prims_tested", u64), ("invalid_samples", u64), ("iterations", u64), ("kernel_launches", u64),
-                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("max_stack_depth", u64), ("guard_retraces", u64)]
+                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("max_stack_depth", u64), ("guard_retraces", u64),
+                ("reduce_ms", C.c_double), ("devices", u64)]
 
 
 class KernelStats(C.Structure):
@@ -116,7 +117,7 @@ assert HIT_DTYPE.itemsize == C.sizeof(Hit) == 32 and RAY_DTYPE.itemsize == C.siz
 
 # every entry point include/nori_gpu.h declares (tests check the library exports all of them)
 ENTRY_POINTS = [
-    "nori_gpu_init", "nori_gpu_destroy", "nori_gpu_last_error", "nori_gpu_upload_scene",
+    "nori_gpu_init", "nori_gpu_init_multi", "nori_gpu_device_count", "nori_gpu_destroy", "nori_gpu_last_error", "nori_gpu_upload_scene",
     "nori_gpu_set_option", "nori_gpu_render", "nori_gpu_render_samples", "nori_gpu_clear_film",
     "nori_gpu_download_film", "nori_gpu_upload_film", "nori_gpu_film_device_ptr",
     "nori_gpu_film_dims", "nori_gpu_resolve", "nori_gpu_download_variance", "nori_gpu_trace", "nori_gpu_probe_bsdf", "nori_gpu_probe_emitter", "nori_gpu_pcg32",

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define NORI_DEFAULT_RESULTS_MB 8192
@@ -64,6 +65,13 @@ struct nori_gpu_ctx {
     int64_t opt_kernel_timing = 0;
     std::vector<cudaEvent_t> kev; std::vector<int> kev_kind; size_t kev_used = 0;
     bool last_wave = false, last_defer = false;
+
+    // multi-GPU context (nori_gpu_init_multi): this is the context of devices[0]; `peers` are complete contexts of
+    // the other devices (scene replicated, sample indices sharded in nori_gpu_render, films summed onto this one)
+    std::vector<nori_gpu_ctx *> peers;
+    std::vector<char> peer_direct;     // peers[i]'s film is readable from this device over NVLink (peer access enabled)
+    float4 *peer_stage = nullptr; size_t peer_stage_cap = 0;   // staging for peers without direct access
+    float multi_reduce_ms = 0.f;
 };
 
 // bracket one kernel launch: counts it and, with kernel_timing on, records a CUDA event pair on the stream
@@ -148,9 +156,41 @@ int nori_gpu_init(int device, nori_gpu_ctx **out) {
     return 0;
 }
 
+/* one context over several devices of one node.  The host calls the same entry points; upload_scene
+ * replicates the scene, render shards the sample indices and sums the films (k_film_reduce over peer memory). */
+int nori_gpu_init_multi(const int *devices, int n, nori_gpu_ctx **out) {
+    *out = nullptr;
+    if (!devices || n < 1) { g_init_error = "nori_gpu_init_multi: empty device list"; return 1; }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j)
+        if (devices[i] == devices[j]) { g_init_error = "nori_gpu_init_multi: device listed twice"; return 1; }
+    nori_gpu_ctx *root = nullptr;
+    if (nori_gpu_init(devices[0], &root)) return 1;
+    for (int i = 1; i < n; ++i) {
+        nori_gpu_ctx *p = nullptr;
+        if (nori_gpu_init(devices[i], &p)) { nori_gpu_destroy(root); return 1; }
+        root->peers.push_back(p);
+        int can = 0;
+        cudaSetDevice(root->device);
+        if (cudaDeviceCanAccessPeer(&can, root->device, devices[i]) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            can = e == cudaSuccess;
+            if (!can) cudaGetLastError();
+        }
+        root->peer_direct.push_back((char) can);
+    }
+    *out = root;
+    return 0;
+}
+
+int nori_gpu_device_count(const nori_gpu_ctx *ctx) { return ctx ? 1 + (int) ctx->peers.size() : 0; }
+
 void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     if (!ctx) return;
+    for (nori_gpu_ctx *p : ctx->peers) nori_gpu_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
+    cudaFree(ctx->peer_stage);
     cudaStreamSynchronize(ctx->stream);
     freeAll(ctx->scene_allocs); freeAll(ctx->pool_allocs);
     cudaFree(ctx->arena);
@@ -176,6 +216,12 @@ int nori_gpu_abi_sizes(uint32_t *out, int n) {
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     REQUIRE(ctx && name, "set_option: null argument");
     std::string k(name);
+    if (!ctx->peers.empty()) {
+        REQUIRE(!(k == "variance" && value), "set_option(variance): the running-mean statistic (render.cpp:238-247) depends on the order of "
+                                             "all passes and does not decompose over devices: use a single-device context");
+        for (nori_gpu_ctx *p : ctx->peers)
+            if (nori_gpu_set_option(p, name, value)) { ctx->err = p->err; return 1; }
+    }
     if (k == "pool") { REQUIRE(value >= 1024 && value <= (1ll << 26), "pool must be in [1024, 2^26]"); ctx->opt_pool = value; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
     else if (k == "reset_options") {
         // every scheduling option back to its default (tests: a finalizer calls this so that no test leaks its settings)
@@ -222,6 +268,8 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
 
 int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     REQUIRE(ctx && s, "upload_scene: null argument");
+    for (nori_gpu_ctx *p : ctx->peers)                       // the scene is replicated on every device
+        if (nori_gpu_upload_scene(p, s)) { ctx->err = p->err; return 1; }
     REQUIRE(s->abi_version == NORI_GPU_ABI_VERSION, "upload_scene: ABI version mismatch");
     REQUIRE(s->integrator >= 0 && s->integrator <= NORI_INTEGRATOR_VOLUMETRIC, "upload_scene: unknown integrator");
     REQUIRE(s->camera.width > 0 && s->camera.height > 0, "upload_scene: empty film");
@@ -651,9 +699,99 @@ static int traceThroughRenderKernels(nori_gpu_ctx *ctx, const nori_gpu_ray *rays
     return 0;
 }
 
+// ---- multi-GPU inside render: device g renders the sample indices [begin + g*count/G, begin +
+// (g+1)*count/G) -- disjoint pcg32 initstate ranges, scene replicated -- each from its own host thread (the wavefront
+// loop polls its device), and the films are summed onto devices[0] by ONE kernel that reads the peers' accumulation
+// buffers in place over NVLink (peer access) and hands them back zeroed, so that repeated render calls keep
+// accumulating.  Peers without direct access are staged with cudaMemcpyPeerAsync first.
+#define NORI_MAX_PEERS 15
+struct PeerFilms { float4 *src[NORI_MAX_PEERS]; int n; };
+__global__ void k_film_reduce(float4 *dst, PeerFilms peers, size_t n) {
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 a = dst[i];
+        for (int p = 0; p < peers.n; ++p) {                  // fixed order: the sum does not depend on scheduling
+            const float4 b = peers.src[p][i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            peers.src[p][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        dst[i] = a;
+    }
+}
+
+static int renderMulti(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed) {
+    REQUIRE(ctx->has_scene, "render: no scene uploaded");
+    const int G = 1 + (int) ctx->peers.size();
+    REQUIRE(G - 1 <= NORI_MAX_PEERS, "render: too many devices");
+    std::vector<int> rc(G, 0);
+    std::vector<std::thread> th;
+    auto share = [&](int g) { return (uint32_t) (((uint64_t) spp_count * g) / G); };
+    for (int g = 1; g < G; ++g)
+        th.emplace_back([&, g] { rc[g] = renderImpl(ctx->peers[g - 1], spp_begin + share(g), share(g + 1) - share(g), seed, nullptr); });
+    rc[0] = renderImpl(ctx, spp_begin + share(0), share(1) - share(0), seed, nullptr);
+    for (auto &t : th) t.join();
+    for (int g = 1; g < G; ++g) if (rc[g]) { ctx->err = "device " + std::to_string(ctx->peers[g - 1]->device) + ": " + ctx->peers[g - 1]->err; return 1; }
+    if (rc[0]) return 1;
+    // ---- the one exchange step of the path: sum of the accumulation buffers
+    CK(cudaSetDevice(ctx->device));
+    const size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
+    PeerFilms pf{}; pf.n = G - 1;
+    size_t staged = 0;
+    for (int g = 1; g < G; ++g) if (!ctx->peer_direct[g - 1]) ++staged;
+    if (staged * nf > ctx->peer_stage_cap) {
+        cudaFree(ctx->peer_stage); ctx->peer_stage = nullptr; ctx->peer_stage_cap = 0;
+        CK(cudaMalloc((void **) &ctx->peer_stage, staged * nf * sizeof(float4)));
+        ctx->peer_stage_cap = staged * nf;
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    staged = 0;
+    for (int g = 1; g < G; ++g) {
+        nori_gpu_ctx *p = ctx->peers[g - 1];
+        if (ctx->peer_direct[g - 1]) pf.src[g - 1] = p->film;
+        else {
+            float4 *st = ctx->peer_stage + (staged++) * nf;
+            CK(cudaMemcpyPeerAsync(st, ctx->device, p->film, p->device, nf * sizeof(float4), ctx->stream));
+            pf.src[g - 1] = st;
+        }
+    }
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    LAUNCH(NORI_K_FILM, (k_film_reduce<<<sms * 4, 256, 0, ctx->stream>>>(ctx->film, pf, nf)));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float red = 0.f; CK(cudaEventElapsedTime(&red, ctx->ev0, ctx->ev1));
+    ctx->multi_reduce_ms = red;
+    double worst = ctx->stats.render_ms;
+    for (int g = 1; g < G; ++g) {
+        nori_gpu_ctx *p = ctx->peers[g - 1];
+        if (!ctx->peer_direct[g - 1]) {                      // the staged copy was summed: clear the peer's own buffer
+            CK(cudaSetDevice(p->device));
+            CK(cudaMemsetAsync(p->film, 0, nf * sizeof(float4), p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+        }
+        const nori_gpu_stats &q = p->stats;
+        worst = std::max(worst, q.render_ms);
+        ctx->stats.samples += q.samples; ctx->stats.rays += q.rays; ctx->stats.shadow_rays += q.shadow_rays;
+        ctx->stats.nodes_visited += q.nodes_visited; ctx->stats.prims_tested += q.prims_tested;
+        ctx->stats.invalid_samples += q.invalid_samples; ctx->stats.kernel_launches += q.kernel_launches;
+        ctx->stats.iterations += q.iterations; ctx->stats.guard_retraces += q.guard_retraces;
+        ctx->stats.max_stack_depth = std::max(ctx->stats.max_stack_depth, q.max_stack_depth);
+        for (int i = 0; i < NORI_K_COUNT; ++i) {             // work counters add up; times stay those of devices[0]
+            ctx->kstats[i].rays += p->kstats[i].rays; ctx->kstats[i].nodes_visited += p->kstats[i].nodes_visited;
+            ctx->kstats[i].prims_tested += p->kstats[i].prims_tested;
+        }
+        nori_gpu_reset_stats(p);
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->stats.render_ms = worst + red;                      // the devices run side by side: slowest device + the reduce
+    ctx->stats.reduce_ms = red;
+    return 0;
+}
+
 extern "C" {
 
 int nori_gpu_render(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count, uint64_t seed) {
+    if (ctx && !ctx->peers.empty()) return renderMulti(ctx, spp_begin, spp_count, seed);
     return renderImpl(ctx, spp_begin, spp_count, seed, nullptr);
 }
 
@@ -664,6 +802,7 @@ int nori_gpu_render_samples(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_
 
 int nori_gpu_clear_film(nori_gpu_ctx *ctx) {
     REQUIRE(ctx && ctx->has_scene, "clear_film: no scene uploaded");
+    for (nori_gpu_ctx *p : ctx->peers) if (nori_gpu_clear_film(p)) { ctx->err = p->err; return 1; }
     CK(cudaSetDevice(ctx->device));
     size_t nf = (size_t) (ctx->W + 2 * ctx->border) * (ctx->H + 2 * ctx->border);
     CK(cudaMemsetAsync(ctx->film, 0, nf * sizeof(float4), ctx->stream));
@@ -799,7 +938,11 @@ int nori_gpu_probe_emitter(nori_gpu_ctx *ctx, uint32_t emitter, uint64_t n, cons
 int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out) { return pcgImpl(ctx, initstate, initseq, n, out, nullptr); }
 int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out) { return pcgImpl(ctx, initstate, initseq, n, nullptr, out); }
 
-int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out) { REQUIRE(ctx && out, "get_stats: null argument"); *out = ctx->stats; return 0; }
+int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out) {
+    REQUIRE(ctx && out, "get_stats: null argument");
+    *out = ctx->stats; out->devices = 1 + ctx->peers.size();
+    return 0;
+}
 int nori_gpu_get_kernel_stats(nori_gpu_ctx *ctx, nori_gpu_kernel_stats *out) {
     REQUIRE(ctx && out, "get_kernel_stats: null argument");
     for (int i = 0; i < NORI_K_COUNT; ++i) out[i] = ctx->kstats[i];
@@ -811,6 +954,11 @@ int nori_gpu_reset_stats(nori_gpu_ctx *ctx) {
     for (int i = 0; i < NORI_K_COUNT; ++i) ctx->kstats[i] = nori_gpu_kernel_stats{};
     return 0;
 }
-int nori_gpu_synchronize(nori_gpu_ctx *ctx) { REQUIRE(ctx, "synchronize: null context"); CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+int nori_gpu_synchronize(nori_gpu_ctx *ctx) {
+    REQUIRE(ctx, "synchronize: null context");
+    for (nori_gpu_ctx *p : ctx->peers) if (nori_gpu_synchronize(p)) { ctx->err = p->err; return 1; }
+    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 } // extern "C"

@@ -29,6 +29,8 @@ def load_library():
     vp, u32, u64, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
     sig = {
         "nori_gpu_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "nori_gpu_init_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "nori_gpu_device_count": (C.c_int, [vp]),
         "nori_gpu_destroy": (None, [vp]),
         "nori_gpu_last_error": (C.c_char_p, [vp]),
         "nori_gpu_upload_scene": (C.c_int, [vp, C.POINTER(abi.Scene)]),
@@ -76,12 +78,21 @@ class _CudaArray:
 class NoriGpu:
     """One rendering context on one CUDA device (mirrors what RenderThread owns, render.h:30-52)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """`devices` (a list of device indices): one context over several GPUs of the node (nori_gpu_init_multi:
+        the scene is replicated, render() shards the sample indices and sums the films onto devices[0])."""
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        if self.lib.nori_gpu_init(device, C.byref(self.ctx)) != 0:
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.nori_gpu_init_multi(arr, len(devices), C.byref(self.ctx))
+            device = devices[0] if len(devices) else 0
+        else:
+            rc = self.lib.nori_gpu_init(device, C.byref(self.ctx))
+        if rc != 0:
             raise NoriGpuError(self.lib.nori_gpu_last_error(None).decode())
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
         self.scene = None
 
     def close(self):

@@ -167,6 +167,29 @@ class SceneData:
         cam.invOutputSize[0] = np.float32(1.0) / np.float32(width)
         cam.invOutputSize[1] = np.float32(1.0) / np.float32(height)
 
+    def set_film(self, width, height):
+        """Output size with ANY aspect ratio: rebuilds sampleToCamera the way PerspectiveCamera's constructor does
+        (perspective.cpp:53-80: inverse of scale(0.5, -0.5*aspect, 1) * translate(1, -1/aspect, 0) * perspective(fov))
+        from the field of view encoded in the current matrix.  For throughput configurations at resolutions no
+        fixture was exported at (BASELINE config 5: 3840 x 2160); float64 arithmetic, rounded once."""
+        cam = self.pod.camera
+        s2c = np.array(list(cam.sampleToCamera), np.float64).reshape(4, 4)
+        cot = 2.0 / s2c[0, 0]                                         # M^-1[0][0] = 1 / (0.5 * cot)
+        near, far = float(cam.nearClip), float(cam.farClip)
+        aspect = width / float(height)
+        recip = 1.0 / (far - near)
+        persp = np.array([[cot, 0, 0, 0], [0, cot, 0, 0], [0, 0, far * recip, -near * far * recip], [0, 0, 1, 0]], np.float64)
+        scale = np.diag([0.5, -0.5 * aspect, 1.0, 1.0])
+        trans = np.eye(4); trans[0, 3] = 1.0; trans[1, 3] = -1.0 / aspect
+        inv = np.linalg.inv(scale @ trans @ persp)
+        inv[np.abs(inv) < 1e-12] = 0.0
+        inv = inv.astype(np.float32).reshape(-1)
+        for i in range(16):
+            cam.sampleToCamera[i] = inv[i]
+        cam.width, cam.height = width, height
+        cam.invOutputSize[0] = np.float32(1.0) / np.float32(width)
+        cam.invOutputSize[1] = np.float32(1.0) / np.float32(height)
+
     def ray_batch(self):
         """Reference-answered ray batch stored by nori_export --rays (None if absent)."""
         e = self.entries

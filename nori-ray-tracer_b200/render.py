@@ -69,30 +69,46 @@ class RenderThread:
             self._status = 0
 
     # ---- synchronous core -------------------------------------------------------------------
-    def render(self, scene, spp=None, spp_chunk=None, seed=0, distributed=False, progress=None, variance=False):
-        """Render `scene` (a nscene.SceneData); returns (rgb bitmap, film) on rank 0, (None, film) elsewhere."""
+    def render(self, scene, spp=None, spp_chunk=None, seed=0, distributed=False, progress=None, variance=False,
+               chunk_seconds=0.25):
+        """Render `scene` (a nscene.SceneData); returns (rgb bitmap, film) on rank 0, (None, film) elsewhere.
+
+        The spp loop runs in chunks so that stopRendering() and getProgress() act between passes like the
+        reference's per-pass checks (render.cpp:195-197): `spp_chunk` passes per nori_gpu_render call, or
+        (None) as many as take about `chunk_seconds` -- the first chunk is 1 pass, later ones are sized from the
+        measured rate.  One chunk = one wavefront batch, so very small chunks cost throughput (the pool drains
+        once per call); benchmarks pass spp_chunk=spp."""
         g = self.gpu
         spp = scene.sample_count if spp is None else spp
         rank, world = 0, 1
         if distributed:
             import torch.distributed as dist
             rank, world = dist.get_rank(), dist.get_world_size()
+        if variance and world > 1:
+            # the statistic is the running mean after every pass (render.cpp:238-247, SURVEY A.9): it depends on the
+            # order of ALL passes and does not decompose over sample-index shards
+            raise ValueError("variance=True is not available for sharded (distributed) renders")
         begin, count = shard_spp(spp, rank, world)
         g.upload_scene(scene)
         if variance:                                   # the reference's <scene>_variance.exr (render.cpp:263-278)
             g.set_option("variance", 1)
         g.clear_film()
-        chunk = count if not spp_chunk else spp_chunk
+        chunk = max(1, int(spp_chunk)) if spp_chunk else 1
         done = 0
         while done < count:
             self._progress = done / max(count, 1)
             if self._status == 2:                      # render.cpp:196-197
                 break
             n = min(chunk, count - done)
+            t0 = time.perf_counter()
             g.render(begin + done, n, seed)
+            dt = time.perf_counter() - t0
             done += n
+            if not spp_chunk:                          # aim at chunk_seconds per call, at most doubling per step
+                chunk = max(1, min(2 * chunk + 1, int(n * chunk_seconds / max(dt, 1e-6))))
             if progress:
                 progress(done / count)
+        self._progress = done / max(count, 1)
         if distributed and world > 1:
             import torch
             film_t = torch.as_tensor(g.film_device_array(), device=f"cuda:{g.device}")
@@ -101,7 +117,7 @@ class RenderThread:
             torch.cuda.synchronize(g.device)
         film = g.download_film()
         rgb = g.resolve() if rank == 0 else None
-        self.variance_image = g.variance() if variance else None
+        self.variance_image = g.variance() if (variance and done > 0) else None
         return rgb, film
 
     # ---- the reference's asynchronous entry point ---------------------------------------------
