@@ -340,6 +340,12 @@ int nori_gpu_wide_layout(const nori_gpu_bvh_node *nodes, uint32_t n_nodes, uint3
                          uint32_t capacity, uint32_t *n_records_out);
 
 /* sizeof() of every ABI struct as compiled into the library (binding self-check); returns the count. */
+/* Arithmetic self-test (test hook): the library's slow-path-free IEEE sequences -- division and square root for
+ * normal-range operands (camera rays), the reciprocal of the triangle determinant (mesh.cpp:93) -- against the
+ * compiler's correctly rounded operations on n pseudo-random operand pairs with exponents in [-60, 60].
+ * mismatch[0..2] = operands whose division / square root / reciprocal differs in any bit (all must be 0). */
+int nori_gpu_selftest(nori_gpu_ctx *ctx, uint64_t n, uint64_t *mismatch /* [3] */);
+
 int nori_gpu_abi_sizes(uint32_t *out, int n);
 
 int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out);

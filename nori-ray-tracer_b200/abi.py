@@ -121,5 +121,5 @@ ENTRY_POINTS = [
     "nori_gpu_set_option", "nori_gpu_render", "nori_gpu_render_samples", "nori_gpu_clear_film",
     "nori_gpu_download_film", "nori_gpu_upload_film", "nori_gpu_film_device_ptr",
     "nori_gpu_film_dims", "nori_gpu_resolve", "nori_gpu_download_variance", "nori_gpu_trace", "nori_gpu_probe_bsdf", "nori_gpu_probe_emitter", "nori_gpu_pcg32",
-    "nori_gpu_pcg32_uint", "nori_gpu_build_bvh", "nori_gpu_build_bvh_device", "nori_gpu_mesh_area_cdf", "nori_gpu_wide_layout", "nori_gpu_abi_sizes", "nori_gpu_get_stats", "nori_gpu_get_kernel_stats", "nori_gpu_reset_stats", "nori_gpu_synchronize",
+    "nori_gpu_pcg32_uint", "nori_gpu_build_bvh", "nori_gpu_build_bvh_device", "nori_gpu_mesh_area_cdf", "nori_gpu_wide_layout", "nori_gpu_abi_sizes", "nori_gpu_selftest", "nori_gpu_get_stats", "nori_gpu_get_kernel_stats", "nori_gpu_reset_stats", "nori_gpu_synchronize",
 ]

@@ -313,6 +313,26 @@ __global__ void k_probe_emitter(DScene sc, uint32_t emitter, unsigned long long 
     o[12] = ev.x; o[13] = ev.y; o[14] = ev.z;
 }
 
+// nori_gpu_selftest: the slow-path-free IEEE sequences of device_common.cuh / traverse.cuh against the compiler's own
+// __fdiv_rn / __fsqrt_rn / __frcp_rn on pseudo-random operands with exponents in [-60, 60] (pcg32 bit patterns).
+__global__ void k_selftest(unsigned long long n, unsigned long long *mismatch) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pcg32 r; r.seed(i, 12345u);
+    auto operand = [&]() {
+        const uint32_t m = r.nextUInt(), e = 127u - 60u + r.nextUInt() % 121u;
+        return __uint_as_float((m & 0x807fffffu) | (e << 23));
+    };
+    const float a = operand(), b = operand();
+    if (__float_as_uint(xdiv_nr(a, b)) != __float_as_uint(__fdiv_rn(a, b))) atomicAdd(&mismatch[0], 1ull);
+    if (__float_as_uint(xdiv_nr(0.0f, b)) != __float_as_uint(__fdiv_rn(0.0f, b))) atomicAdd(&mismatch[0], 1ull);
+    const V3 v = xdivs_nr(mk(a, 1.0f, -a), b);
+    if (__float_as_uint(v.x) != __float_as_uint(__fdiv_rn(a, b)) || __float_as_uint(v.y) != __float_as_uint(__fdiv_rn(1.0f, b))
+        || __float_as_uint(v.z) != __float_as_uint(__fdiv_rn(-a, b))) atomicAdd(&mismatch[0], 1ull);
+    if (__float_as_uint(xsqrt_nr(fabsf(a))) != __float_as_uint(__fsqrt_rn(fabsf(a)))) atomicAdd(&mismatch[1], 1ull);
+    if (__float_as_uint(rcpNormalRange(b)) != __float_as_uint(__frcp_rn(b))) atomicAdd(&mismatch[2], 1ull);
+}
+
 __global__ void k_fill_u32(uint32_t *p, uint32_t v, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -207,12 +207,24 @@ bool noriBuildWideLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices
     const NodeWords t{w};
     if (!layoutEncodable(t, n_nodes, n_indices)) return false;
     std::vector<uint32_t> slots;                                 // 4 per record: node index or 0xffffffff
+    // Record numbering: the top of the tree breadth-first (the first NORI_WIDE_TOP_RECORDS records: the records
+    // most rays pass through are contiguous, which is what an L2 access-policy window can pin), everything below
+    // depth-first (a subtree's records stay together).  The numbering is only a naming: references carry it.
     std::vector<std::pair<uint32_t, uint32_t>> st; st.reserve(256);   // (binary node that roots a record, record depth)
     std::vector<uint32_t> recOf(n_nodes, 0xffffffffu);
     uint32_t n = 0, maxDepth = 0;
+    size_t head = 0;                                             // breadth-first phase: st is a queue read at `head`
+    bool bfs = true;
     st.push_back({0u, 1u});
-    while (!st.empty()) {
-        const uint32_t i = st.back().first, depth = st.back().second; st.pop_back();
+    while (bfs ? head < st.size() : !st.empty()) {
+        uint32_t i, depth;
+        if (bfs) {
+            i = st[head].first; depth = st[head].second; ++head;
+            if (n + 1 >= NORI_WIDE_TOP_RECORDS) {                // switch: the rest of the queue becomes the depth-first stack
+                st.erase(st.begin(), st.begin() + head); std::reverse(st.begin(), st.end());
+                bfs = false; head = 0;
+            }
+        } else { i = st.back().first; depth = st.back().second; st.pop_back(); }
         if (n >= n_nodes || i + 1 >= n_nodes || t.second(i) >= n_nodes) return false;     // not a tree
         recOf[i] = n++; maxDepth = std::max(maxDepth, depth);
         uint32_t sl[4]; int cnt = 0;
@@ -227,7 +239,8 @@ bool noriBuildWideLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices
             for (uint32_t gc : { c + 1, t.second(c) }) if (!t.empty(gc)) sl[cnt++] = gc;
         }
         for (int k = 0; k < 4; ++k) slots.push_back(k < cnt ? sl[k] : 0xffffffffu);
-        for (int k = cnt - 1; k >= 0; --k) if (!t.leaf(sl[k])) st.push_back({sl[k], depth + 1});
+        if (bfs) { for (int k = 0; k < cnt; ++k) if (!t.leaf(sl[k])) st.push_back({sl[k], depth + 1}); }
+        else for (int k = cnt - 1; k >= 0; --k) if (!t.leaf(sl[k])) st.push_back({sl[k], depth + 1});
     }
     if (3u * maxDepth > maxStack) return false;
     out.assign(32 * (size_t) n, 0u);

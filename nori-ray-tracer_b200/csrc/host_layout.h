@@ -17,7 +17,12 @@
 // own reference.
 bool noriBuildPairLayout(const uint32_t *w, uint32_t n_nodes, uint32_t n_indices, std::vector<uint32_t> &out, uint32_t &rootRef);
 
-// 4-wide records: one 128-byte record (32 words) per group of merged nodes, depth-first order, record 0 = root:
+// records of the 4-wide layout numbered breadth-first from the root before the numbering turns depth-first: 2^19
+// records = 64 MB, the part of the tree an L2 access-policy window can hold (nori_gpu.cu: option "l2_window")
+#define NORI_WIDE_TOP_RECORDS 524288u
+
+// 4-wide records: one 128-byte record (32 words) per group of merged nodes, record 0 = root, the top of the tree
+// breadth-first, the rest depth-first:
 //   slot k = words 8k..8k+7 = {bmin, ref}{bmax, rank}; unused slots hold the empty-leaf reference 0x80000000;
 //   rank = position of the slot's subtree among the record's slots in the reference's depth-first (leaf) order
 //   child reference: bit 31 = leaf (as above); inner: record index

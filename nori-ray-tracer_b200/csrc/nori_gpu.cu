@@ -57,6 +57,8 @@ struct nori_gpu_ctx {
     int64_t opt_wide = 1;              // 1: large-scene kernels walk the 4-wide layout (with the near-first order)
     int64_t opt_traversal = 0;         // 0 auto (by primitive count), 1 plain per-lane loops, 2 warp state machine
     int64_t opt_trace_kernel = 0;      // nori_gpu_trace: 0 k_trace (per-lane loops over the reference nodes), 2 the large-scene render kernels
+    int64_t opt_l2_window = 0;         // MiB of the 4-wide records (top of the tree first) held by an L2 access-policy window; 0 = none
+    size_t nodes4_bytes = 0; bool window_set = false;
 
     nori_gpu_stats stats{};
     nori_gpu_kernel_stats kstats[NORI_K_COUNT]{};
@@ -228,7 +230,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         if (ctx->opt_pool != (1 << 20)) { ctx->opt_pool = 1 << 20; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
         ctx->opt_results_mb = NORI_DEFAULT_RESULTS_MB; ctx->opt_stats = 0; ctx->opt_megakernel = 0; ctx->opt_poll = 8; ctx->opt_emitter_sort = 1;
         ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
-        ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0;
+        ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0; ctx->opt_l2_window = 0;
     }
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
     else if (k == "stats") ctx->opt_stats = value != 0;
@@ -247,6 +249,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     }
     else if (k == "traversal") { REQUIRE(value >= 0 && value <= 2, "traversal must be 0, 1 or 2"); ctx->opt_traversal = value; }
     else if (k == "trace_kernel") { REQUIRE(value == 0 || value == 2, "trace_kernel must be 0 (k_trace) or 2 (k_extend_sm / k_shadow_sm)"); ctx->opt_trace_kernel = value; }
+    else if (k == "l2_window") { REQUIRE(value >= 0 && value <= 1024, "l2_window must be in [0, 1024] MiB"); ctx->opt_l2_window = value; }
     else if (k == "wide") { REQUIRE(value == 0 || value == 1, "wide must be 0 or 1"); ctx->opt_wide = value; }
     else if (k == "order") { REQUIRE(value >= 0 && value <= 2, "order must be 0 (reference child order), 1 (near child first) or 2 (auto)"); ctx->opt_order = value; }
     else if (k == "area_only") ctx->opt_area_only = value != 0;
@@ -426,6 +429,7 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *s) {
     }
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) nodes2.data(), nodes2.size() / 4, &ds.nodes2)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) nodes4.data(), nodes4.size() / 4, &ds.nodes4)) return 1;
+    ctx->nodes4_bytes = nodes4.size() * sizeof(uint32_t);
     static_assert(sizeof(nori_gpu_bvh_node) == 2 * sizeof(uint4), "node layout");
     if (devUpload(ctx, ctx->scene_allocs, (const uint4 *) s->nodes, 2 * (size_t) s->n_nodes, &ds.nodes)) return 1;
     if (devUpload(ctx, ctx->scene_allocs, prims.data(), prims.size(), &ds.prims)) return 1;
@@ -513,6 +517,30 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     ctx->ds.esort = esort ? 1 : 0;
     ctx->ds.area_only = (ctx->opt_area_only && ctx->emitter_type_mask == (1u << NORI_EMITTER_AREA)) ? 1 : 0;
     if (ensurePool(ctx, defer, esort)) return 1;
+    // L2 access-policy window over the head of the 4-wide records (numbered breadth-first from the root, host_bvh.cpp): the
+    // part of a large tree that most rays walk stays resident while leaf-level records and primitives stream through
+    {
+        const bool want = ctx->opt_l2_window > 0 && sm && noriSmLayout(ctx->ds) == 2 && ctx->nodes4_bytes > 0;
+        if (want || ctx->window_set) {
+            cudaStreamAttrValue av{};
+            if (want) {
+                int maxWin = 0, maxPersist = 0;
+                cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+                cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+                size_t bytes = std::min<size_t>((size_t) ctx->opt_l2_window << 20, ctx->nodes4_bytes);
+                bytes = std::min<size_t>(bytes, (size_t) std::max(maxWin, 0));
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t) std::max(maxPersist, 0)));
+                av.accessPolicyWindow.base_ptr = (void *) ctx->ds.nodes4;
+                av.accessPolicyWindow.num_bytes = bytes;
+                av.accessPolicyWindow.hitRatio = maxPersist > 0 ? std::min(1.0f, (float) maxPersist / (float) std::max<size_t>(bytes, 1)) : 0.f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            } else { av.accessPolicyWindow.num_bytes = 0; cudaCtxResetPersistingL2Cache(); }
+            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();                              // a device without the feature renders as before
+            ctx->window_set = want;
+        }
+    }
     // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
     Counters zero{}; zero.total_samples = total;
     *ctx->h_ctr = zero;
@@ -591,7 +619,20 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
     size_t maxLayers = std::max<size_t>(1, ((size_t) ctx->opt_results_mb << 20) / ((size_t) wh * sizeof(float4)));
     maxLayers = std::min<size_t>(maxLayers, 0xfffffff0ull / wh);       // sample ids are 32-bit inside a batch
     REQUIRE(maxLayers >= 1, "render: image too large for a single-layer batch");
-    if (ensureResults(ctx, std::min<size_t>(maxLayers, spp_count) * wh)) return 1;
+    {   // the per-sample buffer takes what the device can spare: at most results_mb, at most 3/4 of the free memory (plus
+        // what the buffer already holds), and half as many layers again whenever the allocation still fails
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const size_t spare = freeB / 4 * 3 + ctx->results_cap * sizeof(float4);
+            maxLayers = std::max<size_t>(1, std::min<size_t>(maxLayers, spare / ((size_t) wh * sizeof(float4))));
+        }
+        maxLayers = std::min<size_t>(maxLayers, spp_count);
+        while (ensureResults(ctx, maxLayers * wh)) {
+            if (maxLayers == 1) return 1;                   // not even one layer fits: the error of ensureResults stands
+            cudaGetLastError(); ctx->err.clear();
+            maxLayers = (maxLayers + 1) / 2;
+        }
+    }
     CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(Counters), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     FilmParams fp{};
@@ -937,6 +978,21 @@ int nori_gpu_probe_bsdf(nori_gpu_ctx *ctx, uint32_t bsdf, uint64_t n, const floa
 int nori_gpu_probe_emitter(nori_gpu_ctx *ctx, uint32_t emitter, uint64_t n, const float *in, float *out) { return probeImpl(ctx, false, emitter, n, in, out); }
 int nori_gpu_pcg32(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, float *out) { return pcgImpl(ctx, initstate, initseq, n, out, nullptr); }
 int nori_gpu_pcg32_uint(nori_gpu_ctx *ctx, uint64_t initstate, uint64_t initseq, uint64_t n, uint32_t *out) { return pcgImpl(ctx, initstate, initseq, n, nullptr, out); }
+
+int nori_gpu_selftest(nori_gpu_ctx *ctx, uint64_t n, uint64_t *mismatch) {
+    REQUIRE(ctx && mismatch, "selftest: null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    if (scratch(ctx, 3 * sizeof(unsigned long long), (void **) &d)) return 1;
+    CK(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (n) k_selftest<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(n, d);
+    CK(cudaGetLastError());
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) mismatch[i] = h[i];
+    return 0;
+}
 
 int nori_gpu_get_stats(nori_gpu_ctx *ctx, nori_gpu_stats *out) {
     REQUIRE(ctx && out, "get_stats: null argument");

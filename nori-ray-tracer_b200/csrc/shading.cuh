@@ -587,7 +587,7 @@ __device__ __forceinline__ V3 xfPoint(const float *m, V3 p) {                // 
     float r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = ((m[4 * i] * p.x + m[4 * i + 1] * p.y) + m[4 * i + 2] * p.z) + m[4 * i + 3] * 1.0f;
-    return xdivs(mk(r[0], r[1], r[2]), r[3]);
+    return xdivs_nr(mk(r[0], r[1], r[2]), r[3]);
 }
 __device__ __forceinline__ V3 xfVector(const float *m, V3 v) {               // transform.h:68-70
     return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
@@ -599,13 +599,15 @@ __device__ __forceinline__ P2 squareToUniformDisk(P2 s) {                    // 
 __device__ __forceinline__ bool hasChromaticAberrations(const nori_gpu_camera &c) {   // advancedCamera.cpp:230-232
     return c.type == NORI_CAMERA_ADVANCED && !(c.chromatic[0] == 0.f && c.chromatic[1] == 0.f && c.chromatic[2] == 0.f);
 }
-// Camera rays are built in the EXACT arithmetic in every build (x* operations, IEEE division / square root): the first
-// vertex of every path -- hit primitive, hit point -- then equals the reference's for the same film sample.
+// Camera rays are built in the EXACT arithmetic in every build (x* operations; IEEE division / square root through the
+// slow-path-free sequences xdiv_nr / xsqrt_nr, whose operands here -- clip distances, homogeneous w, ray lengths -- are of
+// ordinary magnitude): the first vertex of every path -- hit primitive, hit point -- then equals the reference's for the
+// same film sample.
 // perspective.cpp:90-112, thinlens.cpp:126-171, advancedCamera.cpp:133-228.  `weight` is the camera's importance
 // weight: Color3f(1), or the unit colour of `channel` when chromatic aberration is on (advancedCamera.cpp:176-183).
 __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as, int channel, V3 &weight) {
     V3 nearP = xfPoint(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
-    V3 d = xnormalized(nearP);
+    V3 d = xnormalized_nr(nearP);
     weight = mk(1.f);
     Ray ray;
     if (c.type == NORI_CAMERA_ADVANCED) {
@@ -623,15 +625,15 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             }
             const float distortionFactor = r / y;
             nearP.x *= distortionFactor; nearP.y *= distortionFactor;
-            d = xnormalized(nearP);
+            d = xnormalized_nr(nearP);
         }
         float w = 0.0f;
         if (chroma) { w = c.chromatic[channel]; weight = mk(channel == 0 ? 1.f : 0.f, channel == 1 ? 1.f : 0.f, channel == 2 ? 1.f : 0.f); }
-        const float invZ = 1.0f / d.z;
+        const float invZ = xdiv_nr(1.0f, d.z);
         if (c.lensRadius > 0.0f || chroma) {                                  // advancedCamera.cpp:192-216
             P2 disk = squareToUniformDisk(as);
             float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
-            float ft = c.focalDistance / d.z;
+            float ft = xdiv_nr(c.focalDistance, d.z);
             V3 pFocus = xadd(mk(0.f), xscale(d, ft));
             float spx = ps.x - (0.5f * (float) c.width), spy = ps.y - (0.5f * (float) c.height);
             const float mx = (float) max(c.width, c.height);
@@ -640,7 +642,7 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             const float dx = spx * sq * w, dy = spy * sq * w;
             pFocus = xadd(pFocus, mk(-dx, dy, 0.0f));
             V3 o = mk(lx, ly, 0.0f);
-            V3 dir = xnormalized(xsub(pFocus, o));
+            V3 dir = xnormalized_nr(xsub(pFocus, o));
             ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
         } else {
             ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
@@ -648,14 +650,14 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
         ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
         return ray;
     }
-    float invZ = 1.0f / d.z;
+    float invZ = xdiv_nr(1.0f, d.z);
     if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
         P2 disk = squareToConcentricDisk(as);
         float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
-        float ft = c.focalDistance / d.z;
+        float ft = xdiv_nr(c.focalDistance, d.z);
         V3 pFocus = xadd(mk(0.f), xscale(d, ft));
         V3 o = mk(lx, ly, 0.0f);
-        V3 dir = xnormalized(xsub(pFocus, o));
+        V3 dir = xnormalized_nr(xsub(pFocus, o));
         ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
     } else {
         ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
 //   * the stepping loop (smRun) costs two ballots per step; publishing answers and refilling lanes from
 //     the warp's slot chunk happens only once NORI_REFILL_MIN lanes are out of work, so short rays do
 //     not wait for the longest ray of the warp and long rays do not pay for the bookkeeping.
+#ifndef NORI_PREFETCH_CHILDREN
+#define NORI_PREFETCH_CHILDREN 0
+#endif
 #ifndef NORI_LEAF_BURST
 #define NORI_LEAF_BURST 4
 #endif
@@ -324,6 +327,13 @@ __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack
     const uint4 *rec = &sc.nodes4[8 * (size_t) L.cur];
     const uint4 a0 = __ldg(rec), b0 = __ldg(rec + 1), a1 = __ldg(rec + 2), b1 = __ldg(rec + 3);
     const uint4 a2 = __ldg(rec + 4), b2 = __ldg(rec + 5), a3 = __ldg(rec + 6), b3 = __ldg(rec + 7);
+#if NORI_PREFETCH_CHILDREN
+    // experiment: request every inner child's record (one line each) into L2 before the box tests decide which are entered
+    if (!(a0.w & 0x80000000u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes4[8 * (size_t) a0.w]));
+    if (!(a1.w & 0x80000000u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes4[8 * (size_t) a1.w]));
+    if (!(a2.w & 0x80000000u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes4[8 * (size_t) a2.w]));
+    if (!(a3.w & 0x80000000u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes4[8 * (size_t) a3.w]));
+#endif
     if (COUNT) cnt.nodes += (a0.w != 0x80000000u) + (a1.w != 0x80000000u) + (a2.w != 0x80000000u) + (a3.w != 0x80000000u);   // boxes tested
     float n0, n1, n2, n3;
     bool h0, h1, h2, h3;

@@ -50,6 +50,7 @@ def load_library():
         "nori_gpu_pcg32": (C.c_int, [vp, u64, u64, u64, vp]),
         "nori_gpu_pcg32_uint": (C.c_int, [vp, u64, u64, u64, vp]),
         "nori_gpu_abi_sizes": (C.c_int, [C.POINTER(u32), C.c_int]),
+        "nori_gpu_selftest": (C.c_int, [vp, u64, C.POINTER(u64)]),
         "nori_gpu_build_bvh": (C.c_int, [C.POINTER(abi.Shape), u32, vp, vp, vp, C.POINTER(u32), C.c_int]),
         "nori_gpu_build_bvh_device": (C.c_int, [C.c_int, C.POINTER(abi.Shape), u32, vp, vp, vp, C.POINTER(u32), u32, C.POINTER(C.c_float)]),
         "nori_gpu_mesh_area_cdf": (C.c_int, [vp, vp, u32, vp, C.POINTER(C.c_float)]),
@@ -193,6 +194,13 @@ class NoriGpu:
         out = np.empty(n, np.uint32)
         self._check(self.lib.nori_gpu_pcg32_uint(self.ctx, initstate, initseq, n, out.ctypes.data))
         return out
+
+    def selftest(self, n):
+        """(division, square root, reciprocal) operand counts on which the slow-path-free IEEE sequences differ from the
+        compiler's correctly rounded operations; all zero when the library is sound."""
+        out = (C.c_uint64 * 3)()
+        self._check(self.lib.nori_gpu_selftest(self.ctx, n, out))
+        return tuple(int(v) for v in out)
 
     def stats(self):
         s = abi.Stats()

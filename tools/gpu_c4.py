@@ -11,7 +11,7 @@ import os
 builder = os.environ.get('NORI_BUILDER', 'sah'); leaf = int(os.environ.get('NORI_LEAF', '4'))
 t = time.time(); sc, sb = host_scene.heightfield_scene(n=n, integrator=integ, builder=builder, leaf_size=leaf, return_builder=True); print('builder', builder, 'leaf', leaf, 'scene+build s', round(time.time() - t, 2), 'device build ms', sb.build_ms, 'prims', sc.pod.n_indices, 'nodes', sc.pod.n_nodes, flush=True)
 g = NoriGpu(0); t = time.time(); g.upload_scene(sc); print('upload s', round(time.time() - t, 2))
-g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '2')))
+g.set_option('pool', 1 << 22); import os; g.set_option('order', int(os.environ.get('NORI_ORDER', '2'))); g.set_option('l2_window', int(os.environ.get('NORI_L2_WINDOW', '0')))
 for wide in [int(x) for x in os.environ.get('NORI_WIDE', '1').split(',')]:
     g.set_option('wide', wide); print('== wide', wide)
     g.render(0, 2, seed=1)

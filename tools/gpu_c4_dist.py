@@ -1,29 +1,64 @@
-import sys, numpy as np
+"""BASELINE config 4 sweep: the 10 M-triangle height field, path_mis 3840x2160, sharded by sample index over N GPUs.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/gpu_c4_dist.py [spp ...]
+    python tools/gpu_c4_dist.py --devices 0,1,2,3 [spp ...]        (one process: nori_gpu_init_multi, no torch)
+
+For every sample count (default 4 16 64): the job's device time (max over ranks, render + the one 133 MB film reduce),
+Msamples/s, and speed-up / efficiency against the same job on one GPU (every rank times that on its own device).
+The public path: render.RenderThread.render(distributed=True) shards with render.shard_spp exactly like this."""
+import os, sys, json, time, numpy as np
 sys.path.insert(0, '.')
 from __graft_entry__ import import_package
 import_package()
-from nori_ray_tracer_b200 import host_scene, abi
+from nori_ray_tracer_b200 import host_scene, render
 from nori_ray_tracer_b200.gpu import NoriGpu
+
+args = sys.argv[1:]
+devices = None
+if '--devices' in args:
+    i = args.index('--devices'); devices = [int(x) for x in args[i + 1].split(',')]; del args[i:i + 2]
+spps = [int(a) for a in args] or [4, 16, 64]
+W, H = 3840, 2160
 sc = host_scene.heightfield_scene(n=2237)
-g = NoriGpu(0); g.upload_scene(sc)
-cam = sc.pod.camera
-s2c = np.array(cam.sampleToCamera[:], np.float64).reshape(4, 4); c2w = np.array(cam.cameraToWorld[:], np.float64).reshape(4, 4)
-rng = np.random.RandomState(0); N = 400000
-px = rng.rand(N) ; py = rng.rand(N)
-p = np.stack([px, py, np.zeros(N), np.ones(N)], 0); q = s2c @ p; near = (q[:3] / q[3]).T
-d = near / np.linalg.norm(near, axis=1, keepdims=True); dw = (c2w[:3, :3] @ d.T).T; o = c2w[:3, 3]
-rays = np.zeros(N, abi.RAY_DTYPE); rays['o'] = o; rays['d'] = dw; rays['mint'] = 1e-4 / d[:, 2]; rays['maxt'] = 1e4 / d[:, 2]
-h = g.trace(rays, 0)
-nv = h['nodes_visited'].astype(np.int64)
-print('primary: mean', nv.mean(), 'pcts', np.percentile(nv, [50, 90, 99, 99.9, 100]), 'hit frac', (h['shape'] != 0xffffffff).mean(), 'trace ms', g.stats().trace_ms)
-# secondary rays from hit points, random hemisphere directions
-hit = h['shape'] != 0xffffffff
-P = rays['o'][hit] + rays['d'][hit] * h['t'][hit][:, None]
-M = len(P); dd = rng.randn(M, 3); dd /= np.linalg.norm(dd, axis=1, keepdims=True); dd[:, 2] = np.abs(dd[:, 2])
-r2 = np.zeros(M, abi.RAY_DTYPE); r2['o'] = P; r2['d'] = dd; r2['mint'] = 1e-4; r2['maxt'] = np.inf
-h2 = g.trace(r2, 0); nv2 = h2['nodes_visited'].astype(np.int64)
-print('secondary: mean', nv2.mean(), 'pcts', np.percentile(nv2, [50, 90, 99, 99.9, 100]), 'trace ms', g.stats().trace_ms)
-# per-warp max/mean
-for name, v in (('primary', nv), ('secondary', nv2)):
-    w = v[: len(v) // 32 * 32].reshape(-1, 32)
-    print(name, 'mean of warp-max / mean', w.max(1).mean() / v.mean())
+
+if devices is not None:                                     # one process, multi-GPU inside the library
+    g1 = NoriGpu(devices[0]); g1.upload_scene(sc); g1.set_option('pool', 1 << 22); g1.render(0, 2, seed=1)
+    gm = NoriGpu(devices=devices); gm.upload_scene(sc); gm.set_option('pool', 1 << 22); gm.render(0, 2 * len(devices), seed=1)
+    for spp in spps:
+        g1.clear_film(); g1.reset_stats(); g1.render(0, spp, seed=0); t1 = g1.stats().render_ms
+        gm.clear_film(); gm.reset_stats(); gm.render(0, spp, seed=0); st = gm.stats()
+        err = np.abs(gm.download_film() - g1.download_film()).max() / np.abs(g1.download_film()).max()
+        print(json.dumps({'mode': 'nori_gpu_init_multi', 'n_gpus': len(devices), 'spp': spp, 'ms': st.render_ms, 'reduce_ms': st.reduce_ms,
+                          'msamples_per_s': W * H * spp / st.render_ms / 1e3, 'single_gpu_ms': t1, 'speedup': t1 / st.render_ms,
+                          'efficiency': t1 / st.render_ms / len(devices), 'film_max_rel_diff_vs_single': float(err)}), flush=True)
+    sys.exit(0)
+
+import torch, torch.distributed as dist
+local = int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+rank, world = dist.get_rank(), dist.get_world_size()
+g = NoriGpu(local); g.upload_scene(sc); g.set_option('pool', 1 << 22)
+film = torch.as_tensor(g.film_device_array(), device=f'cuda:{local}')
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+def mx(x):
+    t = torch.tensor([x], dtype=torch.float64, device=f'cuda:{local}'); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+def job(spp):
+    b, c = render.shard_spp(spp, rank, world)
+    g.clear_film(); g.render(b, c, seed=0)
+    ms = g.stats().render_ms if c else 0.0
+    ev0.record(); dist.reduce(film, dst=0, op=dist.ReduceOp.SUM); ev1.record(); torch.cuda.synchronize()
+    return ms, ev0.elapsed_time(ev1)
+
+g.render(0, 2, seed=1); job(world)
+for spp in spps:
+    dist.barrier(); torch.cuda.synchronize()
+    r, red = job(spp)
+    tn, tr = mx(r + red), mx(red)
+    g.clear_film(); g.render(0, spp, seed=0); t1 = mx(g.stats().render_ms)
+    if rank == 0:
+        print(json.dumps({'mode': 'torchrun + NCCL reduce', 'n_gpus': world, 'spp': spp, 'ms': tn, 'reduce_ms': tr, 'msamples_per_s': W * H * spp / tn / 1e3,
+                          'single_gpu_ms': t1, 'speedup': t1 / tn, 'efficiency': t1 / tn / world}), flush=True)
+dist.barrier(); dist.destroy_process_group()
