@@ -77,6 +77,7 @@ __device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uin
 // One iteration of renderBlock's loop head (render.cpp:98-124): seed the path's pcg32 stream, draw the
 // film and aperture samples, build the camera ray (of colour channel `channel` when the camera has
 // chromatic aberration, render.cpp:106-121).
+template <bool NR = true>
 __device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, uint32_t sid, int channel, Ray &ray, uint64_t &rngState) {
     const uint32_t k = sid / bt.wh, pix = sid - k * bt.wh;
     const int W = sc.camera.width;
@@ -86,7 +87,7 @@ __device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, 
     P2 ps; ps.x = (float) px + a.x; ps.y = (float) py + a.y;
     P2 ap = rng.next2D();
     V3 weight;
-    ray = cameraRay(sc.camera, ps, ap, channel, weight);
+    ray = cameraRay<NR>(sc.camera, ps, ap, channel, weight);
     rngState = rng.state;
 }
 
@@ -95,6 +96,7 @@ __device__ __forceinline__ void generatePath(const DScene &sc, const Batch &bt, 
 // random stream and summed with the camera's per-channel weights (render.cpp:106-121,
 // advancedCamera.cpp:176-183): the slot is restarted in place with the next channel's camera ray
 // (same film / aperture sample, re-derived from the stream's seed) until the third path has ended.
+template <bool NR = true>
 __device__ __forceinline__ void endOfPath(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
                                           uint32_t sid, V3 rad, uint64_t rngState, uint32_t flags, uint32_t &nDone) {
     if (hasChromaticAberrations(sc.camera)) {
@@ -104,7 +106,7 @@ __device__ __forceinline__ void endOfPath(const DScene &sc, const Pool &pool, co
         if (ch > 0) { const float4 a = pool.acc[slot]; acc = mk(a.x, a.y, a.z) + acc; }
         if (ch < 2) {
             Ray ray; uint64_t unused;
-            generatePath(sc, bt, sid, ch + 1, ray, unused);
+            generatePath<NR>(sc, bt, sid, ch + 1, ray, unused);
             pool.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.f);
             pool.rayO[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
             pool.rayD[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);

@@ -583,11 +583,17 @@ __device__ __forceinline__ int randomEmitter(const DScene &sc, float rnd) {
 }
 
 // ------------------------------------------------------------------------------ cameras
+// NR selects the slow-path-free IEEE sequences (device_common.cuh); NR = false the compiler's own __fdiv_rn / __fsqrt_rn.
+// Same bits either way (nori_gpu_selftest); the state-machine kernels use NR = false: inlined into their refill step the
+// fast sequences cost registers their node / leaf steps need (k_extend_sm spilled, 10M-triangle scene 136 -> 149 ms).
+template <bool NR> __device__ __forceinline__ V3 cnorm(V3 a) { return NR ? xnormalized_nr(a) : xnormalized(a); }
+template <bool NR> __device__ __forceinline__ float cdiv(float a, float b) { return NR ? xdiv_nr(a, b) : __fdiv_rn(a, b); }
+template <bool NR = true>
 __device__ __forceinline__ V3 xfPoint(const float *m, V3 p) {                // transform.h:78-81
     float r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) r[i] = ((m[4 * i] * p.x + m[4 * i + 1] * p.y) + m[4 * i + 2] * p.z) + m[4 * i + 3] * 1.0f;
-    return xdivs_nr(mk(r[0], r[1], r[2]), r[3]);
+    return NR ? xdivs_nr(mk(r[0], r[1], r[2]), r[3]) : xdivs(mk(r[0], r[1], r[2]), r[3]);
 }
 __device__ __forceinline__ V3 xfVector(const float *m, V3 v) {               // transform.h:68-70
     return mk((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
@@ -605,9 +611,10 @@ __device__ __forceinline__ bool hasChromaticAberrations(const nori_gpu_camera &c
 // same film sample.
 // perspective.cpp:90-112, thinlens.cpp:126-171, advancedCamera.cpp:133-228.  `weight` is the camera's importance
 // weight: Color3f(1), or the unit colour of `channel` when chromatic aberration is on (advancedCamera.cpp:176-183).
+template <bool NR = true>
 __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as, int channel, V3 &weight) {
-    V3 nearP = xfPoint(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
-    V3 d = xnormalized_nr(nearP);
+    V3 nearP = xfPoint<NR>(c.sampleToCamera, mk(ps.x * c.invOutputSize[0], ps.y * c.invOutputSize[1], 0.0f));
+    V3 d = cnorm<NR>(nearP);
     weight = mk(1.f);
     Ray ray;
     if (c.type == NORI_CAMERA_ADVANCED) {
@@ -625,15 +632,15 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             }
             const float distortionFactor = r / y;
             nearP.x *= distortionFactor; nearP.y *= distortionFactor;
-            d = xnormalized_nr(nearP);
+            d = cnorm<NR>(nearP);
         }
         float w = 0.0f;
         if (chroma) { w = c.chromatic[channel]; weight = mk(channel == 0 ? 1.f : 0.f, channel == 1 ? 1.f : 0.f, channel == 2 ? 1.f : 0.f); }
-        const float invZ = xdiv_nr(1.0f, d.z);
+        const float invZ = cdiv<NR>(1.0f, d.z);
         if (c.lensRadius > 0.0f || chroma) {                                  // advancedCamera.cpp:192-216
             P2 disk = squareToUniformDisk(as);
             float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
-            float ft = xdiv_nr(c.focalDistance, d.z);
+            float ft = cdiv<NR>(c.focalDistance, d.z);
             V3 pFocus = xadd(mk(0.f), xscale(d, ft));
             float spx = ps.x - (0.5f * (float) c.width), spy = ps.y - (0.5f * (float) c.height);
             const float mx = (float) max(c.width, c.height);
@@ -642,25 +649,25 @@ __device__ __forceinline__ Ray cameraRay(const nori_gpu_camera &c, P2 ps, P2 as,
             const float dx = spx * sq * w, dy = spy * sq * w;
             pFocus = xadd(pFocus, mk(-dx, dy, 0.0f));
             V3 o = mk(lx, ly, 0.0f);
-            V3 dir = xnormalized_nr(xsub(pFocus, o));
-            ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+            V3 dir = cnorm<NR>(xsub(pFocus, o));
+            ray.o = xfPoint<NR>(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
         } else {
-            ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
+            ray.o = xfPoint<NR>(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
         }
         ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
         return ray;
     }
-    float invZ = xdiv_nr(1.0f, d.z);
+    float invZ = cdiv<NR>(1.0f, d.z);
     if (c.type == NORI_CAMERA_THINLENS && c.lensRadius > 0.0f) {
         P2 disk = squareToConcentricDisk(as);
         float lx = c.lensRadius * disk.x, ly = c.lensRadius * disk.y;
-        float ft = xdiv_nr(c.focalDistance, d.z);
+        float ft = cdiv<NR>(c.focalDistance, d.z);
         V3 pFocus = xadd(mk(0.f), xscale(d, ft));
         V3 o = mk(lx, ly, 0.0f);
-        V3 dir = xnormalized_nr(xsub(pFocus, o));
-        ray.o = xfPoint(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
+        V3 dir = cnorm<NR>(xsub(pFocus, o));
+        ray.o = xfPoint<NR>(c.cameraToWorld, o); ray.d = xfVector(c.cameraToWorld, dir);
     } else {
-        ray.o = xfPoint(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
+        ray.o = xfPoint<NR>(c.cameraToWorld, mk(0.f)); ray.d = xfVector(c.cameraToWorld, d);
     }
     ray.mint = c.nearClip * invZ; ray.maxt = c.farClip * invZ;
     return ray;

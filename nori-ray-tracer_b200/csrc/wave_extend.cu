@@ -19,7 +19,7 @@
 // the path.  volumetric.cpp:34-38,147-151: it ends only if it also misses the medium's box
 // (medium.cpp:62-66 returns hitObject without drawing a number); otherwise the free-flight sample may
 // still scatter it, so the slot goes to the miss queue with t = inf (the reference's its.t after a miss).
-template <bool VOL>
+template <bool VOL, bool NR = true>
 __device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot, V3 o, V3 d, uint32_t &nDone) {
     if (VOL) {
         float nearT, farT;
@@ -29,7 +29,7 @@ __device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, cons
         }
     }
     const float4 r = pool.rad[slot];
-    endOfPath(sc, pool, bt, ctr, slot, pool.sid[slot], mk(r.x, r.y, r.z), pool.rng[slot], pool.flags[slot], nDone);
+    endOfPath<NR>(sc, pool, bt, ctr, slot, pool.sid[slot], mk(r.x, r.y, r.z), pool.rng[slot], pool.flags[slot], nDone);
     return -1;
 }
 
@@ -437,7 +437,7 @@ __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 
         // nested slab intervals.  A ray outside rayPlain() can meet a NaN there (origin on a bounding plane, 1/d
         // infinite: bbox.h:347-348 then rejects THAT box), so it walks the reference's own nodes in the reference's
         // order, here and now.
-        L.r.found = traverse<SHADOW, COUNT>(sc, o, d, mint, maxt, L.r.hit, cnt);
+        L.r.found = traverse<SHADOW, COUNT, false, false>(sc, o, d, mint, maxt, L.r.hit, cnt);
         L.st = ST_DONE;
         return;
     }
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
                 if (L.r.found) {
                     pool.hit[L.slot] = make_float4(L.r.hit.t, L.r.hit.u, L.r.hit.v, __uint_as_float(L.r.hit.leafpos));
                     type = sc.shapes[__float_as_uint(__ldg(&sc.prims[3 * L.r.hit.leafpos + 1]).w)].bsdf_type;
-                } else type = missRule<VOL>(sc, pool, bt, ctr, L.slot, L.r.o, L.r.d, nDone);
+                } else type = missRule<VOL, false>(sc, pool, bt, ctr, L.slot, L.r.o, L.r.d, nDone);
             }
 #pragma unroll
             for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
                         if (id >= total) break;
                         const uint32_t s = freeList[j];
                         Ray ray; uint64_t rs;
-                        generatePath(sc, bt, (uint32_t) id, 0, ray, rs);
+                        generatePath<false>(sc, bt, (uint32_t) id, 0, ray, rs);
                         pool.rayO[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
                         pool.rayD[s] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
                         pool.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(128, NORI_SHADOW_SM_BLOCKS(LAY)) k_shadow_sm(D
             L.st = ST_IDLE;
             float4 ra = pool.rad[L.slot];
             if (!L.r.found) { const float4 c = pool.shC[L.slot]; ra.x = __fadd_rn(ra.x, c.x); ra.y = __fadd_rn(ra.y, c.y); ra.z = __fadd_rn(ra.z, c.z); }
-            if (flags & PF_TERMINATE) endOfPath(sc, pool, bt, ctr, L.slot, pool.sid[L.slot], mk(ra.x, ra.y, ra.z), pool.rng[L.slot], flags, nDone);
+            if (flags & PF_TERMINATE) endOfPath<false>(sc, pool, bt, ctr, L.slot, pool.sid[L.slot], mk(ra.x, ra.y, ra.z), pool.rng[L.slot], flags, nDone);
             else {
                 if (!L.r.found) pool.rad[L.slot] = ra;
                 pool.flags[L.slot] = flags & ~PF_SHADOW;
