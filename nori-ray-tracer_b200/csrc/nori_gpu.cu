@@ -50,6 +50,7 @@ struct nori_gpu_ctx {
     int64_t opt_area_only = 1;         // scenes lit by area lights only: shade kernels compiled without the other emitter types
     int64_t opt_film_sep = 1;          // radius-2 filters: film kernel with per-sample tabulated weights (0: generic kernel)
     int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
+    int64_t opt_drain_mode = 0;        // 0: one warp per remaining path (k_drain_warp), 1: one thread per path (k_drain)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
     // 0 reference child order (counters equal the reference's), 1 near child first, 2 auto: near child first when
     // rendering scenes with deep trees, reference order for small scenes and for the nori_gpu_trace test hook
@@ -230,7 +231,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         if (ctx->opt_pool != (1 << 20)) { ctx->opt_pool = 1 << 20; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
         ctx->opt_results_mb = NORI_DEFAULT_RESULTS_MB; ctx->opt_stats = 0; ctx->opt_megakernel = 0; ctx->opt_poll = 8; ctx->opt_emitter_sort = 1;
         ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
-        ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0; ctx->opt_l2_window = 0;
+        ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0; ctx->opt_l2_window = 0; ctx->opt_drain_mode = 0;
     }
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
     else if (k == "stats") ctx->opt_stats = value != 0;
@@ -255,6 +256,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "area_only") ctx->opt_area_only = value != 0;
     else if (k == "emitter_sort") { REQUIRE(value >= 0 && value <= 2, "emitter_sort must be 0 (off), 1 (auto) or 2 (always)"); ctx->opt_emitter_sort = value; }
     else if (k == "film_sep") ctx->opt_film_sep = value != 0;
+    else if (k == "drain_mode") { REQUIRE(value == 0 || value == 1, "drain_mode must be 0 (one warp per path) or 1 (one thread per path)"); ctx->opt_drain_mode = value; }
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
@@ -573,7 +575,8 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
         // drain: no camera path left to start and only a few paths alive => finish them in one launch (mega.cu)
         const unsigned long long live = total - ctx->h_ctr->done;
         if (mode != MODE_VOL && ctx->opt_drain > 0 && ctx->h_ctr->next_sample >= total && live <= (unsigned long long) ctx->opt_drain) {
-            LAUNCH(NORI_K_SINGLE, noriLaunchDrain(mode == MODE_MIS, count, sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
+            // warp mode: 16 CTAs per SM = 64 warps, each scanning its share of the pool in 32-slot segments
+            LAUNCH(NORI_K_SINGLE, noriLaunchDrain(mode == MODE_MIS, count, ctx->opt_drain_mode == 0 ? -(sms * 16) : sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
             CK(cudaGetLastError());
             ctx->stats.iterations += 1;
             break;
