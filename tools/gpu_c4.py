@@ -16,6 +16,7 @@ for wide in [int(x) for x in os.environ.get('NORI_WIDE', '1').split(',')]:
     g.set_option('wide', wide); print('== wide', wide)
     g.render(0, 2, seed=1)
     g.set_option('stats', 1); g.reset_stats(); g.clear_film(); g.render(0, 2, seed=1); s = g.stats(); kc = g.kernel_stats(); g.set_option('stats', 0)
+    print('guard retraces', s.guard_retraces, 'of', kc['extend']['rays'], 'closest-hit queries; deepest stack', s.max_stack_depth)
     print('rays/sample', s.rays / s.samples, 'shadow/sample', s.shadow_rays / s.samples, 'nodes/ray', s.nodes_visited / s.rays, 'prims/ray', s.prims_tested / s.rays)
     for k in ('extend', 'shadow', 'single'):
         c = kc[k]

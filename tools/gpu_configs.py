@@ -27,5 +27,6 @@ run('C3 disney+microfacet+envmap+thinlens path_mis', golden('c3_project', 800, 6
 for spp in (4, 16, 64):
     if spp == 4: c4 = host_scene.heightfield_scene(n=2237)
     run('C4 10M-triangle height field path_mis', c4, spp)
-run('C5 volumetric + spot + envmap (per-GPU share of a sharded render)', golden('c5_volumetric', 3840, 2880), 128)
+c5 = nscene.load_scene('tests/golden/c5_volumetric.nscene'); c5.set_film(3840, 2160)
+run('C5 volumetric + spot + envmap (per-GPU share of the 8-GPU job: 512 of 4096 spp)', c5, 512)
 run('table (22k triangles) path_mis', golden('table_path_mis', 800, 600), 256)
