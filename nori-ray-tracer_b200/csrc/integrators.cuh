@@ -41,6 +41,7 @@ template <int BSDF, bool MIS, bool AO = false>
 __device__ __forceinline__ void pathVertex(const DScene &sc, const Hit &hit, PathState &st, VertexOut &out) {
     Its its; hitInfo(sc, st.o, st.d, hit, its);
     const DShape &shp = sc.shapes[its.shape];
+    NORI_CHECK(shp.bsdf >= 0 && shp.emitter < (int32_t) sc.n_emitters);
     const nori_gpu_bsdf &bsdf = sc.bsdfs[shp.bsdf];
     const uint32_t inFlags = st.flags;
     uint32_t flags = 0;

@@ -55,6 +55,7 @@ struct Batch {
     uint64_t seed;            // initstate of sample k is seed + k
     uint32_t spp_first;       // first absolute sample index of this batch
     uint32_t wh;              // W*H
+    uint32_t capacity;        // samples the results buffer holds (assert-enabled build)
 };
 
 __device__ __forceinline__ void warpAdd(unsigned long long *dst, uint32_t v) {
@@ -69,6 +70,7 @@ __device__ __forceinline__ void warpMax(uint32_t *dst, uint32_t v) {
 
 __device__ __forceinline__ void finalizePath(const Batch &bt, Counters *ctr, uint32_t sid, V3 rad) {
     bool ok = validColor(rad);
+    NORI_CHECK(sid < bt.capacity);
     bt.results[sid] = ok ? make_float4(rad.x, rad.y, rad.z, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (!ok) atomicAdd(&ctr->invalid, 1ull);
 }

@@ -644,7 +644,7 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
     memcpy(fp.table, ctx->filter.table, sizeof(fp.table));
     for (uint32_t done = 0; done < spp_count;) {
         uint32_t n = (uint32_t) std::min<size_t>(maxLayers, spp_count - done);
-        Batch bt{}; bt.results = ctx->results; bt.seed = seed; bt.spp_first = spp_begin + done; bt.wh = wh;
+        Batch bt{}; bt.results = ctx->results; bt.seed = seed; bt.spp_first = spp_begin + done; bt.wh = wh; bt.capacity = (uint32_t) std::min<size_t>(ctx->results_cap, 0xffffffffu);
         if (traceBatch(ctx, bt, n)) return 1;
         if (out_rgba) {
             CK(cudaMemcpyAsync(out_rgba + (size_t) done * wh * 4, ctx->results, (size_t) n * wh * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -717,7 +717,7 @@ static int traceThroughRenderKernels(nori_gpu_ctx *ctx, const nori_gpu_ray *rays
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridShadow = sms * std::max(1, noriShadowSmOccupancy(count, lay));
-    Batch bt{}; bt.results = ctx->results; bt.seed = 0; bt.spp_first = 0; bt.wh = P;
+    Batch bt{}; bt.results = ctx->results; bt.seed = 0; bt.spp_first = 0; bt.wh = P; bt.capacity = (uint32_t) std::min<size_t>(ctx->results_cap, 0xffffffffu);
     float msTotal = 0.f;
     ctx->last_wave = true; ctx->last_defer = true;
     for (uint64_t done = 0; done < n; done += P) {

@@ -57,13 +57,16 @@ __device__ __forceinline__ V3 imageEval(const DImage &im, P2 uv) {
 
 // mesh.cpp:122-170, sphere.cpp:78-93
 __device__ __forceinline__ void hitInfo(const DScene &sc, V3 o, V3 d, const Hit &h, Its &its) {
+    NORI_CHECK(h.leafpos < sc.n_prims);
     const float4 r0 = __ldg(&sc.prims[3 * h.leafpos]);
     const float4 r1 = __ldg(&sc.prims[3 * h.leafpos + 1]);
     const float4 r2 = __ldg(&sc.prims[3 * h.leafpos + 2]);
     its.shape = (int) __float_as_uint(r1.w);
+    NORI_CHECK((uint32_t) its.shape < sc.n_shapes);
     const DShape &m = sc.shapes[its.shape];
     if (__float_as_uint(r2.w) == 0u) {
         const uint32_t prim = __float_as_uint(r0.w);
+        NORI_CHECK(prim < m.n_triangles);
         const float b1 = h.u, b2 = h.v, b0 = 1 - (b1 + b2);
         const uint32_t i0 = __ldg(&m.F[3 * prim]), i1 = __ldg(&m.F[3 * prim + 1]), i2 = __ldg(&m.F[3 * prim + 2]);
         const V3 p0 = ld3(&m.V[3 * i0]), p1 = ld3(&m.V[3 * i1]), p2 = ld3(&m.V[3 * i2]);
@@ -419,6 +422,7 @@ __device__ __forceinline__ uint32_t cdfSampleReuse(const float *cdf, uint32_t nE
     }
     int idx = (int) lo - 1; if (idx < 0) idx = 0;
     if ((uint32_t) idx > nEntries - 2) idx = (int) nEntries - 2;
+    NORI_CHECK(nEntries >= 2 && idx >= 0 && (uint32_t) idx + 1 < nEntries);
     float c0 = __ldg(&cdf[idx]), c1 = __ldg(&cdf[idx + 1]);
     s = fdiv(s - c0, c1 - c0);
     return (uint32_t) idx;

@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, 
             qb = __shfl_sync(0xffffffffu, qb, 0);
             for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
                 const uint32_t m = __shfl_sync(0xffffffffu, masks, round), b = __shfl_sync(0xffffffffu, before, round);
-                if ((m >> lane) & 1u) pool.queue[t][qb + b + __popc(m & ((1u << lane) - 1u))] = base + round * 32u + lane;
+                if ((m >> lane) & 1u) {
+                    NORI_CHECK(qb + b + __popc(m & ((1u << lane) - 1u)) < pool.P && base + round * 32u + lane < pool.P);
+                    pool.queue[t][qb + b + __popc(m & ((1u << lane) - 1u))] = base + round * 32u + lane;
+                }
             }
         }
         __syncwarp();
@@ -197,7 +200,7 @@ struct LaneTrav {
 struct LaneStack {
     uint32_t *sh;                       // &s_stack[0][tid]; entry e at sh[e * 128]
     uint32_t ovf[64 - NORI_SM_STACK];
-    __device__ __forceinline__ void push(uint32_t sp, uint32_t v) { if (sp < NORI_SM_STACK) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK] = v; }
+    __device__ __forceinline__ void push(uint32_t sp, uint32_t v) { NORI_CHECK(sp < 64); if (sp < NORI_SM_STACK) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK] = v; }
     __device__ __forceinline__ uint32_t pop(uint32_t sp) const { return sp < NORI_SM_STACK ? sh[sp * 128u] : ovf[sp - NORI_SM_STACK]; }
 };
 
@@ -221,6 +224,7 @@ struct LaneStack2 {
     uint2 *sh;                          // &s_stack2[0][tid]; entry e at sh[e * 128]
     uint2 ovf[NORI_STACK2_MAX - NORI_SM_STACK2];
     __device__ __forceinline__ void push(uint32_t sp, uint32_t ref, float nearT) {
+        NORI_CHECK(sp < NORI_STACK2_MAX);
         const uint2 v = make_uint2(ref, __float_as_uint(nearT));
         if (sp < NORI_SM_STACK2) sh[sp * 128u] = v; else ovf[sp - NORI_SM_STACK2] = v;
     }
@@ -387,6 +391,7 @@ template <int LAY, bool SHADOW, bool COUNT>
 __device__ __forceinline__ void smPrim2(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint32_t i = L.leafI;
+    NORI_CHECK(i < sc.n_prims);
     const float4 r0 = __ldg(&sc.prims[3 * i]);
     const float4 r1 = __ldg(&sc.prims[3 * i + 1]);
     const float4 r2 = __ldg(&sc.prims[3 * i + 2]);
@@ -479,6 +484,7 @@ template <bool SHADOW, bool COUNT>
 __device__ __forceinline__ void smPrim(const DScene &sc, const float4 *rayD, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint32_t i = L.leafI;
+    NORI_CHECK(i < sc.n_prims);
     const float4 r0 = __ldg(&sc.prims[3 * i]);
     const float4 r1 = __ldg(&sc.prims[3 * i + 1]);
     const float4 r2 = __ldg(&sc.prims[3 * i + 2]);
@@ -563,7 +569,7 @@ __global__ void __launch_bounds__(128, NORI_EXT_SM_BLOCKS(LAY)) k_extend_sm(DSce
                 uint32_t qb = 0; const int leader = __ffs(m) - 1;
                 if ((int) lane == leader) qb = atomicAdd(&ctr->qcount[par][t], (uint32_t) __popc(m));
                 qb = __shfl_sync(0xffffffffu, qb, leader);
-                if (type == t) pool.queue[t][qb + __popc(m & ltMask)] = L.slot;
+                if (type == t) { NORI_CHECK(qb + __popc(m & ltMask) < pool.P && L.slot < pool.P); pool.queue[t][qb + __popc(m & ltMask)] = L.slot; }
             }
         }
         // ---- refill idle lanes from the warp's chunk of pool slots

@@ -16,8 +16,10 @@
 template <int BSDF, int MODE, bool COUNT, bool DEFER, bool AO>
 __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t slot,
                                           uint32_t &nDone, uint32_t &nShadow, uint32_t &nClosest, TraceCounters &cnt) {
+    NORI_CHECK(slot < pool.P);
     const float4 ro = pool.rayO[slot], rd = pool.rayD[slot], hh = pool.hit[slot], th = pool.thr[slot], ra = pool.rad[slot];
     const uint32_t sid = pool.sid[slot];
+    NORI_CHECK(sid != NORI_FREE_SLOT);
     PathState st;
     st.o = mk(ro.x, ro.y, ro.z); st.d = mk(rd.x, rd.y, rd.z);
     st.thr = mk(th.x, th.y, th.z); st.pdf_mat = th.w; st.rad = mk(ra.x, ra.y, ra.z);
