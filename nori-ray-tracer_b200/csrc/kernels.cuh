@@ -16,6 +16,9 @@
 //   k_mega       one thread per sample for the short integrators (normals, av, direct*, volumetric)
 //   k_trace / k_pcg32*   the ABI's test hooks
 #pragma once
+#ifndef NORI_PERLIN_VARIANT
+#define NORI_PERLIN_VARIANT 0
+#endif
 #include "integrators.cuh"
 #include "host_layout.h"        // NORI_STACK2_MAX
 
@@ -128,6 +131,30 @@ enum { MODE_MATS = 0, MODE_MIS = 1, MODE_VOL = 2 };
 
 // ---- host-side launchers; each group of kernels lives in its own translation unit so that the
 // library builds in parallel (wave_extend.cu, wave_shade.cu x3 modes, mega.cu, nori_gpu.cu)
+//
+// The wavefront kernels exist TWICE: the regular set knows triangles and spheres; the set compiled with
+// -DNORI_PERLIN_VARIANT=1 (wave_*_p.o: same sources, NORI_WITH_PERLIN on, every kernel and launcher renamed below) also
+// knows the Perlin-noise sphere (perlinnoise.cpp) and renders the scenes that contain one.  Two sets because the
+// shape's code inside the traversal loops -- even as an out-of-line call that is never taken -- costs the scenes
+// WITHOUT such a shape 30 % (traverse.cuh).
+#if NORI_PERLIN_VARIANT
+#define k_extend k_extend_perlin
+#define k_extend_sm k_extend_sm_perlin
+#define k_shadow_sm k_shadow_sm_perlin
+#define k_shade k_shade_perlin
+#define k_rebin k_rebin_perlin
+#define k_drain k_drain_perlin
+#define k_drain_warp k_drain_warp_perlin
+#define noriPickExtend noriPickExtendPerlin
+#define noriLaunchShadeMats noriLaunchShadeMatsPerlin
+#define noriLaunchShadeMisDeferred noriLaunchShadeMisDeferredPerlin
+#define noriLaunchShadowSm noriLaunchShadowSmPerlin
+#define noriShadowSmOccupancy noriShadowSmOccupancyPerlin
+#define noriLaunchShadeMis noriLaunchShadeMisPerlin
+#define noriLaunchShadeVol noriLaunchShadeVolPerlin
+#define noriLaunchRebin noriLaunchRebinPerlin
+#define noriLaunchDrain noriLaunchDrainPerlin
+#endif
 typedef void (*ExtendKernel)(DScene, Pool, Batch, Counters *, uint32_t);
 ExtendKernel noriPickExtend(bool stateMachine, bool count, bool vol, int layout);   // layout: 0 reference nodes, 1 child-box pairs, 2 4-wide
 void noriLaunchShadeMats(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
@@ -140,3 +167,27 @@ void noriLaunchShadeVol(bool count, int grid, cudaStream_t st, const DScene &sc,
 void noriLaunchRebin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
 void noriLaunchDrain(bool mis, bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr);
 void noriLaunchMega(bool count, unsigned grid, cudaStream_t st, const DScene &sc, const Batch &bt, Counters *ctr, unsigned long long total);
+#if !NORI_PERLIN_VARIANT
+// the Perlin-aware set (see above)
+ExtendKernel noriPickExtendPerlin(bool stateMachine, bool count, bool vol, int layout);
+void noriLaunchShadeMatsPerlin(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchShadeMisDeferredPerlin(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchShadowSmPerlin(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+int noriShadowSmOccupancyPerlin(bool count, int layout);
+void noriLaunchShadeMisPerlin(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchShadeVolPerlin(bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchRebinPerlin(int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr, uint32_t it);
+void noriLaunchDrainPerlin(bool mis, bool count, int grid, cudaStream_t st, const DScene &sc, const Pool &pool, const Batch &bt, Counters *ctr);
+#endif
+// one set of wavefront entry points (regular / Perlin-aware), picked per scene by nori_gpu.cu
+struct WaveKernels {
+    ExtendKernel (*pickExtend)(bool, bool, bool, int);
+    void (*shadeMats)(bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    void (*shadeMisDeferred)(bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    void (*shadowSm)(bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    int (*shadowSmOccupancy)(bool, int);
+    void (*shadeMis)(bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    void (*shadeVol)(bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    void (*rebin)(int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *, uint32_t);
+    void (*drain)(bool, bool, int, cudaStream_t, const DScene &, const Pool &, const Batch &, Counters *);
+};

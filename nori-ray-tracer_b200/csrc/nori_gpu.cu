@@ -491,6 +491,12 @@ static int ensureResults(nori_gpu_ctx *ctx, size_t n) {
     return 0;
 }
 
+static const WaveKernels kWave = {noriPickExtend, noriLaunchShadeMats, noriLaunchShadeMisDeferred, noriLaunchShadowSm, noriShadowSmOccupancy,
+                                  noriLaunchShadeMis, noriLaunchShadeVol, noriLaunchRebin, noriLaunchDrain};
+static const WaveKernels kWavePerlin = {noriPickExtendPerlin, noriLaunchShadeMatsPerlin, noriLaunchShadeMisDeferredPerlin, noriLaunchShadowSmPerlin,
+                                        noriShadowSmOccupancyPerlin, noriLaunchShadeMisPerlin, noriLaunchShadeVolPerlin, noriLaunchRebinPerlin,
+                                        noriLaunchDrainPerlin};
+
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
 static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const unsigned long long total = (unsigned long long) nLayers * bt.wh;
@@ -498,9 +504,10 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const int integ = ctx->ds.integrator;
     ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
     ctx->ds.wide = ctx->opt_wide ? 1 : 0;
-    // scenes with a Perlin-noise sphere are rendered by the one-thread-per-sample kernel (traverse.cuh: NORI_WITH_PERLIN)
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
-                      && !ctx->opt_megakernel && !ctx->has_perlin;
+                      && !ctx->opt_megakernel;
+    // scenes with a Perlin-noise sphere run the Perlin-aware set of the same kernels (kernels.cuh)
+    const WaveKernels &wk = ctx->has_perlin ? kWavePerlin : kWave;
     if (!wave) {
         const unsigned grid = (unsigned) ((total + 127) / 128);
         LAUNCH(NORI_K_SINGLE, noriLaunchMega(count, grid, ctx->stream, ctx->ds, bt, ctx->ctr, total));
@@ -549,23 +556,23 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const ExtendKernel kext = noriPickExtend(sm, count, mode == MODE_VOL, noriSmLayout(ctx->ds));
+    const ExtendKernel kext = wk.pickExtend(sm, count, mode == MODE_VOL, noriSmLayout(ctx->ds));
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
-    const int gridShadow = defer ? sms * std::max(1, noriShadowSmOccupancy(count, noriSmLayout(ctx->ds))) : 0;
+    const int gridShadow = defer ? sms * std::max(1, wk.shadowSmOccupancy(count, noriSmLayout(ctx->ds))) : 0;
     ctx->last_wave = true; ctx->last_defer = defer;
     uint32_t it = 0;
     while (true) {
         for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
             LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            if (esort) LAUNCH(NORI_K_GENERATE, noriLaunchRebin((int) ((ctx->pool.P + 1023u) / 1024u), ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            if (esort) LAUNCH(NORI_K_GENERATE, wk.rebin((int) ((ctx->pool.P + 1023u) / 1024u), ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             if (defer) {
-                LAUNCH(NORI_K_SHADE, noriLaunchShadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-                LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            } else if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, noriLaunchShadeMats(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            else LAUNCH(NORI_K_SHADE, noriLaunchShadeVol(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+                LAUNCH(NORI_K_SHADE, wk.shadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+                LAUNCH(NORI_K_SHADOW, wk.shadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            } else if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, wk.shadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, wk.shadeMats(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+            else LAUNCH(NORI_K_SHADE, wk.shadeVol(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
             ctx->stats.iterations += 1;
         }
         CK(cudaGetLastError());
@@ -576,7 +583,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
         const unsigned long long live = total - ctx->h_ctr->done;
         if (mode != MODE_VOL && ctx->opt_drain > 0 && ctx->h_ctr->next_sample >= total && live <= (unsigned long long) ctx->opt_drain) {
             // warp mode: 16 CTAs per SM = 64 warps, each scanning its share of the pool in 32-slot segments
-            LAUNCH(NORI_K_SINGLE, noriLaunchDrain(mode == MODE_MIS, count, ctx->opt_drain_mode == 0 ? -(sms * 16) : sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
+            LAUNCH(NORI_K_SINGLE, wk.drain(mode == MODE_MIS, count, ctx->opt_drain_mode == 0 ? -(sms * 16) : sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
             CK(cudaGetLastError());
             ctx->stats.iterations += 1;
             break;
@@ -713,10 +720,11 @@ static int traceThroughRenderKernels(nori_gpu_ctx *ctx, const nori_gpu_ray *rays
     ds.camera.type = NORI_CAMERA_PERSPECTIVE;              // a miss ends the path here: no per-channel restarts (kernels.cuh: endOfPath)
     const int lay = noriSmLayout(ds);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const ExtendKernel kext = noriPickExtend(true, count, false, lay);
+    const WaveKernels &wk = ctx->has_perlin ? kWavePerlin : kWave;
+    const ExtendKernel kext = wk.pickExtend(true, count, false, lay);
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
-    const int gridE = sms * std::max(1, occE), gridShadow = sms * std::max(1, noriShadowSmOccupancy(count, lay));
+    const int gridE = sms * std::max(1, occE), gridShadow = sms * std::max(1, wk.shadowSmOccupancy(count, lay));
     Batch bt{}; bt.results = ctx->results; bt.seed = 0; bt.spp_first = 0; bt.wh = P; bt.capacity = (uint32_t) std::min<size_t>(ctx->results_cap, 0xffffffffu);
     float msTotal = 0.f;
     ctx->last_wave = true; ctx->last_defer = true;
@@ -728,7 +736,7 @@ static int traceThroughRenderKernels(nori_gpu_ctx *ctx, const nori_gpu_ray *rays
         if (shadow) k_trace_load<true><<<gridP, 256, 0, ctx->stream>>>(ctx->pool, dr, nb);
         else k_trace_load<false><<<gridP, 256, 0, ctx->stream>>>(ctx->pool, dr, nb);
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        if (shadow) LAUNCH(NORI_K_SHADOW, noriLaunchShadowSm(count, gridShadow, ctx->stream, ds, ctx->pool, bt, ctx->ctr, 0));
+        if (shadow) LAUNCH(NORI_K_SHADOW, wk.shadowSm(count, gridShadow, ctx->stream, ds, ctx->pool, bt, ctx->ctr, 0));
         else LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ds, ctx->pool, bt, ctx->ctr, 0)));
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         if (shadow) k_trace_store<true><<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ds, ctx->pool, nb, dh);
