@@ -110,26 +110,32 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
 // reads and the reference's `value * wx * wy` products per candidate sample.  A weight of 0 adds +0 to the
 // sums, which leaves them bit-identical to skipping the sample (invalid samples are staged as zeros already).
 // Shared memory per CTA: (32+2*HALO)^2 x (16 + 8*(2*HALO+1)) bytes = 72.6 KB for the default Gaussian.
+// Round 2: TWO film pixels per thread (vertical neighbours; 32 x 16 threads per 32 x 32 tile).  The two pixels share four
+// of their five sample rows, so a thread reads 30 staged values and 30 + 30 row / 30 column weights for 2 x 25
+// contributions instead of 50 + 100 (shared-memory traffic per film pixel -35 %: the kernel is bound by the shared-memory
+// pipe and by issue slots), and 512 threads stage the 36 x 36 samples in three passes at 84 % occupancy instead of 1024
+// threads in two at 63 %.  Each pixel still adds its contributions row by row, left to right: same bits.
 template <bool VARIANCE, int HALO>
-__global__ void __launch_bounds__(1024) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
+__global__ void __launch_bounds__(512) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
     extern __shared__ float4 s_mem[];
-    constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1;
+    constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1, NT = 512;
     float4 *s_val = s_mem;
     float *s_wx = (float *) (s_mem + nS), *s_wy = s_wx + nS * NW;
     __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
     const int tid = threadIdx.y * T + threadIdx.x;
     if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
     const int b = fp.border;                                           // == HALO
-    const int fx = blockIdx.x * T + threadIdx.x, fy = blockIdx.y * T + threadIdx.y;
+    const int fx = blockIdx.x * T + threadIdx.x, fy0 = blockIdx.y * T + 2 * threadIdx.y;   // film pixels (fx, fy0) and (fx, fy0 + 1)
     const int sx0 = blockIdx.x * T - b - HALO, sy0 = blockIdx.y * T - b - HALO;
     const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float3 vs = make_float3(0.f, 0.f, 0.f), vs2 = make_float3(0.f, 0.f, 0.f);
-    const bool owner = fx < fcols && fy < frows;
-    if (VARIANCE && owner) acc = fp.film[(size_t) fy * fcols + fx];
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    float3 vs0 = make_float3(0.f, 0.f, 0.f), vs20 = vs0, vs1 = vs0, vs21 = vs0;
+    const bool own0 = fx < fcols && fy0 < frows, own1 = fx < fcols && fy0 + 1 < frows;
+    if (VARIANCE && own0) acc0 = fp.film[(size_t) fy0 * fcols + fx];
+    if (VARIANCE && own1) acc1 = fp.film[(size_t) (fy0 + 1) * fcols + fx];
     for (uint32_t k = 0; k < nLayers; ++k) {
         __syncthreads();
-        for (int i = tid; i < nS; i += T * T) {
+        for (int i = tid; i < nS; i += NT) {
             const int ly = i / S, lx = i - ly * S;
             const int sx = sx0 + lx, sy = sy0 + ly;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -160,30 +166,46 @@ __global__ void __launch_bounds__(1024) k_film_sep(FilmParams fp, Batch bt, uint
             for (int j = 0; j < NW; ++j) { s_wx[i * NW + j] = wx[j]; s_wy[i * NW + j] = wy[j]; }
         }
         __syncthreads();
-        if (owner) {
-            const int cx = threadIdx.x + HALO, cy = threadIdx.y + HALO;   // own source pixel (image x = fx - b)
+        if (own0) {
+            const int cx = threadIdx.x + HALO, cy = 2 * threadIdx.y + HALO;    // own source pixel of (fx, fy0)
+            // sample rows cy - HALO .. cy + HALO + 1: row e contributes to pixel 0 with dy = e (e <= HALO) and to pixel 1
+            // with dy = e - 1 (e >= 1 - HALO); each pixel sees its rows in ascending order, its columns left to right
 #pragma unroll
-            for (int dy = -HALO; dy <= HALO; ++dy) {
+            for (int e = -HALO; e <= HALO + 1; ++e) {
 #pragma unroll
                 for (int dx = -HALO; dx <= HALO; ++dx) {
-                    const int i = (cy + dy) * S + (cx + dx);
-                    // this film pixel is column (HALO - dx) of the sample's 2*HALO+1 candidate columns
-                    const float wx = s_wx[i * NW + (HALO - dx)], wy = s_wy[i * NW + (HALO - dy)];
+                    const int i = (cy + e) * S + (cx + dx);
+                    const float wx = s_wx[i * NW + (HALO - dx)];
                     const float4 v = s_val[i];
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
-                    acc.y = __fadd_rn(acc.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
-                    acc.z = __fadd_rn(acc.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
-                    acc.w = __fadd_rn(acc.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                    if (e <= HALO) {
+                        const float wy = s_wy[i * NW + (HALO - e)];
+                        acc0.x = __fadd_rn(acc0.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                        acc0.y = __fadd_rn(acc0.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                        acc0.z = __fadd_rn(acc0.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                        acc0.w = __fadd_rn(acc0.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                    }
+                    if (e >= 1 - HALO) {
+                        const float wy = s_wy[i * NW + (HALO - (e - 1))];
+                        acc1.x = __fadd_rn(acc1.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                        acc1.y = __fadd_rn(acc1.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                        acc1.z = __fadd_rn(acc1.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                        acc1.w = __fadd_rn(acc1.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                    }
                 }
             }
             if (VARIANCE) {                                      // Color4f::divideByFilterWeight (color.h:84-89)
-                const float mx = acc.w != 0.f ? acc.x / acc.w : 0.f, my = acc.w != 0.f ? acc.y / acc.w : 0.f, mz = acc.w != 0.f ? acc.z / acc.w : 0.f;
-                vs.x += mx; vs.y += my; vs.z += mz;
-                vs2.x += mx * mx; vs2.y += my * my; vs2.z += mz * mz;
+                {
+                    const float mx = acc0.w != 0.f ? acc0.x / acc0.w : 0.f, my = acc0.w != 0.f ? acc0.y / acc0.w : 0.f, mz = acc0.w != 0.f ? acc0.z / acc0.w : 0.f;
+                    vs0.x += mx; vs0.y += my; vs0.z += mz; vs20.x += mx * mx; vs20.y += my * my; vs20.z += mz * mz;
+                }
+                if (own1) {
+                    const float mx = acc1.w != 0.f ? acc1.x / acc1.w : 0.f, my = acc1.w != 0.f ? acc1.y / acc1.w : 0.f, mz = acc1.w != 0.f ? acc1.z / acc1.w : 0.f;
+                    vs1.x += mx; vs1.y += my; vs1.z += mz; vs21.x += mx * mx; vs21.y += my * my; vs21.z += mz * mz;
+                }
             }
         }
     }
-    if (owner) {
+    auto flush = [&](int fy, const float4 &acc, const float3 &vs, const float3 &vs2) {
         float4 *dst = &fp.film[(size_t) fy * fcols + fx];
         if (VARIANCE) {
             *dst = acc;
@@ -195,7 +217,9 @@ __global__ void __launch_bounds__(1024) k_film_sep(FilmParams fp, Batch bt, uint
             f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
             *dst = f;
         }
-    }
+    };
+    if (own0) flush(fy0, acc0, vs0, vs20);
+    if (own1) flush(fy0 + 1, acc1, vs1, vs21);
 }
 
 // var = sum2/N - (sum/N)^2 per channel (render.cpp:268-275)
