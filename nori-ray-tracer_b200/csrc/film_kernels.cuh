@@ -110,29 +110,35 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
 // reads and the reference's `value * wx * wy` products per candidate sample.  A weight of 0 adds +0 to the
 // sums, which leaves them bit-identical to skipping the sample (invalid samples are staged as zeros already).
 // Shared memory per CTA: (32+2*HALO)^2 x (16 + 8*(2*HALO+1)) bytes = 72.6 KB for the default Gaussian.
-// Round 2: TWO film pixels per thread (vertical neighbours; 32 x 16 threads per 32 x 32 tile).  The two pixels share four
-// of their five sample rows, so a thread reads 30 staged values and 30 + 30 row / 30 column weights for 2 x 25
-// contributions instead of 50 + 100 (shared-memory traffic per film pixel -35 %: the kernel is bound by the shared-memory
-// pipe and by issue slots), and 512 threads stage the 36 x 36 samples in three passes at 84 % occupancy instead of 1024
-// threads in two at 63 %.  Each pixel still adds its contributions row by row, left to right: same bits.
+// Round 2: NPIX film pixels per thread (a vertical run; 32 x 32/NPIX threads per 32 x 32 tile).  Vertical neighbours share
+// four of their five sample rows, so a thread reads (NPIX + 4) x 5 staged values and column weights for NPIX x 25
+// contributions instead of NPIX x 25 (the kernel is bound by the shared-memory pipe and by issue slots), and fewer threads
+// stage the 36 x 36 samples in more passes at 84 % occupancy instead of 1024 threads in two at 63 %.  Each pixel still adds
+// its contributions row by row, left to right: same bits.
+#ifndef NORI_FILM_NPIX
+#define NORI_FILM_NPIX 2
+#endif
 template <bool VARIANCE, int HALO>
-__global__ void __launch_bounds__(512) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
+__global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
     extern __shared__ float4 s_mem[];
-    constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1, NT = 512;
+    constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1, NPIX = NORI_FILM_NPIX, NT = T * T / NPIX;
     float4 *s_val = s_mem;
     float *s_wx = (float *) (s_mem + nS), *s_wy = s_wx + nS * NW;
     __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
     const int tid = threadIdx.y * T + threadIdx.x;
     if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
     const int b = fp.border;                                           // == HALO
-    const int fx = blockIdx.x * T + threadIdx.x, fy0 = blockIdx.y * T + 2 * threadIdx.y;   // film pixels (fx, fy0) and (fx, fy0 + 1)
+    const int fx = blockIdx.x * T + threadIdx.x, fy0 = blockIdx.y * T + NPIX * threadIdx.y;   // film pixels (fx, fy0 .. fy0 + NPIX - 1)
     const int sx0 = blockIdx.x * T - b - HALO, sy0 = blockIdx.y * T - b - HALO;
     const int fcols = fp.W + 2 * b, frows = fp.H + 2 * b;
-    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-    float3 vs0 = make_float3(0.f, 0.f, 0.f), vs20 = vs0, vs1 = vs0, vs21 = vs0;
-    const bool own0 = fx < fcols && fy0 < frows, own1 = fx < fcols && fy0 + 1 < frows;
-    if (VARIANCE && own0) acc0 = fp.film[(size_t) fy0 * fcols + fx];
-    if (VARIANCE && own1) acc1 = fp.film[(size_t) (fy0 + 1) * fcols + fx];
+    float4 acc[NPIX];
+    float3 vs[NPIX], vs2[NPIX];
+#pragma unroll
+    for (int p = 0; p < NPIX; ++p) {
+        acc[p] = make_float4(0.f, 0.f, 0.f, 0.f); vs[p] = make_float3(0.f, 0.f, 0.f); vs2[p] = vs[p];
+        if (VARIANCE && fx < fcols && fy0 + p < frows) acc[p] = fp.film[(size_t) (fy0 + p) * fcols + fx];
+    }
+    const bool own = fx < fcols && fy0 < frows;                        // at least the first pixel is inside the film
     for (uint32_t k = 0; k < nLayers; ++k) {
         __syncthreads();
         for (int i = tid; i < nS; i += NT) {
@@ -166,60 +172,55 @@ __global__ void __launch_bounds__(512) k_film_sep(FilmParams fp, Batch bt, uint3
             for (int j = 0; j < NW; ++j) { s_wx[i * NW + j] = wx[j]; s_wy[i * NW + j] = wy[j]; }
         }
         __syncthreads();
-        if (own0) {
-            const int cx = threadIdx.x + HALO, cy = 2 * threadIdx.y + HALO;    // own source pixel of (fx, fy0)
-            // sample rows cy - HALO .. cy + HALO + 1: row e contributes to pixel 0 with dy = e (e <= HALO) and to pixel 1
-            // with dy = e - 1 (e >= 1 - HALO); each pixel sees its rows in ascending order, its columns left to right
+        if (own) {
+            const int cx = threadIdx.x + HALO, cy = NPIX * threadIdx.y + HALO;    // own source pixel of (fx, fy0)
+            // sample rows cy - HALO .. cy + HALO + NPIX - 1: row e contributes to pixel p with dy = e - p when |e - p| <= HALO;
+            // each pixel sees its rows in ascending order, its columns left to right
 #pragma unroll
-            for (int e = -HALO; e <= HALO + 1; ++e) {
+            for (int e = -HALO; e <= HALO + NPIX - 1; ++e) {
 #pragma unroll
                 for (int dx = -HALO; dx <= HALO; ++dx) {
                     const int i = (cy + e) * S + (cx + dx);
                     const float wx = s_wx[i * NW + (HALO - dx)];
                     const float4 v = s_val[i];
-                    if (e <= HALO) {
-                        const float wy = s_wy[i * NW + (HALO - e)];
-                        acc0.x = __fadd_rn(acc0.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
-                        acc0.y = __fadd_rn(acc0.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
-                        acc0.z = __fadd_rn(acc0.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
-                        acc0.w = __fadd_rn(acc0.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
-                    }
-                    if (e >= 1 - HALO) {
-                        const float wy = s_wy[i * NW + (HALO - (e - 1))];
-                        acc1.x = __fadd_rn(acc1.x, __fmul_rn(__fmul_rn(v.x, wx), wy));
-                        acc1.y = __fadd_rn(acc1.y, __fmul_rn(__fmul_rn(v.y, wx), wy));
-                        acc1.z = __fadd_rn(acc1.z, __fmul_rn(__fmul_rn(v.z, wx), wy));
-                        acc1.w = __fadd_rn(acc1.w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+#pragma unroll
+                    for (int p = 0; p < NPIX; ++p) {
+                        if (e - p >= -HALO && e - p <= HALO) {
+                            const float wy = s_wy[i * NW + (HALO - (e - p))];
+                            acc[p].x = __fadd_rn(acc[p].x, __fmul_rn(__fmul_rn(v.x, wx), wy));
+                            acc[p].y = __fadd_rn(acc[p].y, __fmul_rn(__fmul_rn(v.y, wx), wy));
+                            acc[p].z = __fadd_rn(acc[p].z, __fmul_rn(__fmul_rn(v.z, wx), wy));
+                            acc[p].w = __fadd_rn(acc[p].w, __fmul_rn(__fmul_rn(v.w, wx), wy));
+                        }
                     }
                 }
             }
             if (VARIANCE) {                                      // Color4f::divideByFilterWeight (color.h:84-89)
-                {
-                    const float mx = acc0.w != 0.f ? acc0.x / acc0.w : 0.f, my = acc0.w != 0.f ? acc0.y / acc0.w : 0.f, mz = acc0.w != 0.f ? acc0.z / acc0.w : 0.f;
-                    vs0.x += mx; vs0.y += my; vs0.z += mz; vs20.x += mx * mx; vs20.y += my * my; vs20.z += mz * mz;
-                }
-                if (own1) {
-                    const float mx = acc1.w != 0.f ? acc1.x / acc1.w : 0.f, my = acc1.w != 0.f ? acc1.y / acc1.w : 0.f, mz = acc1.w != 0.f ? acc1.z / acc1.w : 0.f;
-                    vs1.x += mx; vs1.y += my; vs1.z += mz; vs21.x += mx * mx; vs21.y += my * my; vs21.z += mz * mz;
+#pragma unroll
+                for (int p = 0; p < NPIX; ++p) {
+                    const float4 a = acc[p];
+                    const float mx = a.w != 0.f ? a.x / a.w : 0.f, my = a.w != 0.f ? a.y / a.w : 0.f, mz = a.w != 0.f ? a.z / a.w : 0.f;
+                    vs[p].x += mx; vs[p].y += my; vs[p].z += mz; vs2[p].x += mx * mx; vs2[p].y += my * my; vs2[p].z += mz * mz;
                 }
             }
         }
     }
-    auto flush = [&](int fy, const float4 &acc, const float3 &vs, const float3 &vs2) {
+#pragma unroll
+    for (int p = 0; p < NPIX; ++p) {
+        const int fy = fy0 + p;
+        if (!(fx < fcols && fy < frows)) continue;
         float4 *dst = &fp.film[(size_t) fy * fcols + fx];
         if (VARIANCE) {
-            *dst = acc;
+            *dst = acc[p];
             float4 a = fp.vsum[(size_t) fy * fcols + fx], b2 = fp.vsum2[(size_t) fy * fcols + fx];
-            a.x += vs.x; a.y += vs.y; a.z += vs.z; b2.x += vs2.x; b2.y += vs2.y; b2.z += vs2.z;
+            a.x += vs[p].x; a.y += vs[p].y; a.z += vs[p].z; b2.x += vs2[p].x; b2.y += vs2[p].y; b2.z += vs2[p].z;
             fp.vsum[(size_t) fy * fcols + fx] = a; fp.vsum2[(size_t) fy * fcols + fx] = b2;
         } else {
             float4 f = *dst;
-            f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+            f.x += acc[p].x; f.y += acc[p].y; f.z += acc[p].z; f.w += acc[p].w;
             *dst = f;
         }
-    };
-    if (own0) flush(fy0, acc0, vs0, vs20);
-    if (own1) flush(fy0 + 1, acc1, vs1, vs21);
+    }
 }
 
 // var = sum2/N - (sum/N)^2 per channel (render.cpp:268-275)

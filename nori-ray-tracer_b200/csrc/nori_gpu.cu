@@ -664,10 +664,10 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
                 size_t smem = (size_t) S * S * (sizeof(float4) + 2 * 5 * sizeof(float));
                 if (ctx->opt_variance) {
                     CK(cudaFuncSetAttribute(k_film_sep<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                    LAUNCH(NORI_K_FILM, (k_film_sep<true, 2><<<grid, dim3(32, 16), smem, ctx->stream>>>(fp, bt, n)));
+                    LAUNCH(NORI_K_FILM, (k_film_sep<true, 2><<<grid, dim3(32, 32 / NORI_FILM_NPIX), smem, ctx->stream>>>(fp, bt, n)));
                 } else {
                     CK(cudaFuncSetAttribute(k_film_sep<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                    LAUNCH(NORI_K_FILM, (k_film_sep<false, 2><<<grid, dim3(32, 16), smem, ctx->stream>>>(fp, bt, n)));
+                    LAUNCH(NORI_K_FILM, (k_film_sep<false, 2><<<grid, dim3(32, 32 / NORI_FILM_NPIX), smem, ctx->stream>>>(fp, bt, n)));
                 }
             } else {
                 size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
