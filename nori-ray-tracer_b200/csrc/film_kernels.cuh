@@ -1,6 +1,27 @@
 // film_kernels.cuh -- film accumulation / resolve kernels and the ABI's test-hook kernels (included by nori_gpu.cu only)
 #pragma once
 #include "kernels.cuh"
+#include <cuda.h>               // CUtensorMap (the type only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+// ---- TMA plumbing of the film kernel: one cp.async.bulk.tensor.3d per spp layer brings the (32 + 2 halo)^2 tile of the
+// [layers][H][W] float4 sample tensor into shared memory (out-of-bounds elements arrive as zeros: the image border needs
+// no branches), completion is signalled on an mbarrier; two stages, so layer k + 1 is in flight while layer k is
+// weighted and gathered.
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 :: "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoad3D(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smemAddr(dst)), "l"((uint64_t) map), "r"(smemAddr(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 // ------------------------------------------------------------------------------ film
 struct FilmParams {
@@ -118,15 +139,23 @@ __global__ void __launch_bounds__(1024) k_film(FilmParams fp, Batch bt, uint32_t
 #ifndef NORI_FILM_NPIX
 #define NORI_FILM_NPIX 2
 #endif
-template <bool VARIANCE, int HALO>
-__global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers) {
-    extern __shared__ float4 s_mem[];
+// TMA = true: the sample tile of every layer is brought in by the TMA unit (see above) into one of two stages and read
+// from there by the weighting pass and by the gather -- no per-thread global loads, no copy of the values; `tmap`
+// describes bt.results as a {4 W, H, layers} float tensor with a {4 S, S, 1} box.
+template <bool VARIANCE, int HALO, bool TMA>
+__global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams fp, Batch bt, uint32_t nLayers, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float4 s_mem[];
     constexpr int T = 32, S = T + 2 * HALO, nS = S * S, NW = 2 * HALO + 1, NPIX = NORI_FILM_NPIX, NT = T * T / NPIX;
-    float4 *s_val = s_mem;
-    float *s_wx = (float *) (s_mem + nS), *s_wy = s_wx + nS * NW;
+    float4 *s_val = s_mem;                                             // TMA: two stages of nS values; else one
+    float *s_wx = (float *) (s_mem + (TMA ? 2 : 1) * nS), *s_wy = s_wx + nS * NW;
     __shared__ float s_table[NORI_FILTER_RESOLUTION + 1];
+    __shared__ uint64_t s_bar[2];
     const int tid = threadIdx.y * T + threadIdx.x;
     if (tid <= NORI_FILTER_RESOLUTION) s_table[tid] = fp.table[tid];
+    if (TMA && tid == 0) {
+        mbarInit(&s_bar[0], 1); mbarInit(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int b = fp.border;                                           // == HALO
     const int fx = blockIdx.x * T + threadIdx.x, fy0 = blockIdx.y * T + NPIX * threadIdx.y;   // film pixels (fx, fy0 .. fy0 + NPIX - 1)
     const int sx0 = blockIdx.x * T - b - HALO, sy0 = blockIdx.y * T - b - HALO;
@@ -139,8 +168,20 @@ __global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams f
         if (VARIANCE && fx < fcols && fy0 + p < frows) acc[p] = fp.film[(size_t) (fy0 + p) * fcols + fx];
     }
     const bool own = fx < fcols && fy0 < frows;                        // at least the first pixel is inside the film
+    if (TMA) {
+        __syncthreads();                                               // the barriers are initialised
+        if (tid == 0 && nLayers > 0) { mbarExpectTx(&s_bar[0], nS * 16); tmaLoad3D(s_val, &tmap, &s_bar[0], 4 * sx0, sy0, 0); }
+    }
     for (uint32_t k = 0; k < nLayers; ++k) {
-        __syncthreads();
+        __syncthreads();                                               // everybody is done with layer k - 1: its stage and the weights are free
+        const float4 *tile = s_val + (TMA ? (k & 1u) * nS : 0);
+        if (TMA) {
+            if (tid == 0 && k + 1 < nLayers) {
+                mbarExpectTx(&s_bar[(k + 1) & 1u], nS * 16);
+                tmaLoad3D(s_val + ((k + 1) & 1u) * nS, &tmap, &s_bar[(k + 1) & 1u], 4 * sx0, sy0, (int) (k + 1));
+            }
+            mbarWait(&s_bar[k & 1u], (k >> 1) & 1u);
+        }
         for (int i = tid; i < nS; i += NT) {
             const int ly = i / S, lx = i - ly * S;
             const int sx = sx0 + lx, sy = sy0 + ly;
@@ -150,7 +191,7 @@ __global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams f
             for (int j = 0; j < NW; ++j) { wx[j] = 0.f; wy[j] = 0.f; }
             if (sx >= 0 && sx < fp.W && sy >= 0 && sy < fp.H) {
                 const uint32_t pix = (uint32_t) sy * fp.W + sx;
-                v = bt.results[(size_t) k * bt.wh + pix];
+                if (!TMA) v = bt.results[(size_t) k * bt.wh + pix];
                 Pcg32 rng; rng.seed(bt.seed + bt.spp_first + k, (uint64_t) pix);
                 P2 a = rng.next2D();
                 const float psx = (float) sx + a.x, psy = (float) sy + a.y;
@@ -167,7 +208,7 @@ __global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams f
                     if (!(yb < ylo || yb > yhi)) wy[j] = s_table[(int) __fmul_rn(fabsf(__fsub_rn(yb, py)), fp.lookupFactor)];
                 }
             }
-            s_val[i] = v;
+            if (!TMA) s_val[i] = v;
 #pragma unroll
             for (int j = 0; j < NW; ++j) { s_wx[i * NW + j] = wx[j]; s_wy[i * NW + j] = wy[j]; }
         }
@@ -182,7 +223,7 @@ __global__ void __launch_bounds__(1024 / NORI_FILM_NPIX) k_film_sep(FilmParams f
                 for (int dx = -HALO; dx <= HALO; ++dx) {
                     const int i = (cy + e) * S + (cx + dx);
                     const float wx = s_wx[i * NW + (HALO - dx)];
-                    const float4 v = s_val[i];
+                    const float4 v = tile[i];
 #pragma unroll
                     for (int p = 0; p < NPIX; ++p) {
                         if (e - p >= -HALO && e - p <= HALO) {

@@ -49,6 +49,7 @@ struct nori_gpu_ctx {
     uint32_t n_emitter_types = 0, emitter_type_mask = 0; bool has_envmap = false;
     int64_t opt_area_only = 1;         // scenes lit by area lights only: shade kernels compiled without the other emitter types
     int64_t opt_film_sep = 1;          // radius-2 filters: film kernel with per-sample tabulated weights (0: generic kernel)
+    int64_t opt_film_tma = 1;          // ... whose sample tiles are staged by the TMA unit (0: per-thread loads)
     int64_t opt_drain = 1 << 15;       // finish the batch with k_drain once at most this many paths are alive (0: never)
     int64_t opt_drain_mode = 0;        // 0: one warp per remaining path (k_drain_warp), 1: one thread per path (k_drain)
     int64_t opt_shadow_pass = 0;       // 0 auto (own pass with the state-machine traversal), 1 always, 2 never (inside k_shade)
@@ -230,7 +231,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         // every scheduling option back to its default (tests: a finalizer calls this so that no test leaks its settings)
         if (ctx->opt_pool != (1 << 20)) { ctx->opt_pool = 1 << 20; freeAll(ctx->pool_allocs); ctx->pool = Pool{}; }
         ctx->opt_results_mb = NORI_DEFAULT_RESULTS_MB; ctx->opt_stats = 0; ctx->opt_megakernel = 0; ctx->opt_poll = 8; ctx->opt_emitter_sort = 1;
-        ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
+        ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_film_tma = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
         ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0; ctx->opt_l2_window = 0; ctx->opt_drain_mode = 0;
     }
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
@@ -256,6 +257,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "area_only") ctx->opt_area_only = value != 0;
     else if (k == "emitter_sort") { REQUIRE(value >= 0 && value <= 2, "emitter_sort must be 0 (off), 1 (auto) or 2 (always)"); ctx->opt_emitter_sort = value; }
     else if (k == "film_sep") ctx->opt_film_sep = value != 0;
+    else if (k == "film_tma") ctx->opt_film_tma = value != 0;
     else if (k == "drain_mode") { REQUIRE(value == 0 || value == 1, "drain_mode must be 0 (one warp per path) or 1 (one thread per path)"); ctx->opt_drain_mode = value; }
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
@@ -497,6 +499,27 @@ static const WaveKernels kWavePerlin = {noriPickExtendPerlin, noriLaunchShadeMat
                                         noriShadowSmOccupancyPerlin, noriLaunchShadeMisPerlin, noriLaunchShadeVolPerlin, noriLaunchRebinPerlin,
                                         noriLaunchDrainPerlin};
 
+// Tensor map of the sample buffer for the film kernel's TMA loads: a {4 W, H, layers} float tensor read in boxes of
+// {4 S, S, 1} (one layer of a (32 + 2 halo)^2 pixel tile), zeros outside.  cuTensorMapEncodeTiled is a driver entry point;
+// the library links the runtime only and fetches it here.  Returns false when the driver does not offer it.
+static bool filmTensorMap(CUtensorMap *map, const float4 *results, int W, int H, uint32_t layers, int S) {
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = nullptr; static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (Encode) fn;
+        else cudaGetLastError();
+    }
+    if (!encode || 4 * S > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t) 4 * W, (cuuint64_t) H, (cuuint64_t) layers};
+    const cuuint64_t strides[2] = {(cuuint64_t) W * 16, (cuuint64_t) W * H * 16};
+    const cuuint32_t box[3] = {(cuuint32_t) (4 * S), (cuuint32_t) S, 1u}, estr[3] = {1u, 1u, 1u};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *) results, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Trace all camera paths of one batch; on return (stream-ordered) bt.results holds every sample.
 static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const unsigned long long total = (unsigned long long) nLayers * bt.wh;
@@ -661,14 +684,16 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
             dim3 grid((ctx->W + 2 * ctx->border + 31) / 32, (ctx->H + 2 * ctx->border + 31) / 32);
             if (ctx->opt_variance) { fp.vsum = ctx->vsum; fp.vsum2 = ctx->vsum2; ctx->var_passes += n; }
             if (fp.halo == 2 && ctx->opt_film_sep) {                 // default Gaussian (radius 2): separable weights tabulated per sample
-                size_t smem = (size_t) S * S * (sizeof(float4) + 2 * 5 * sizeof(float));
-                if (ctx->opt_variance) {
-                    CK(cudaFuncSetAttribute(k_film_sep<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                    LAUNCH(NORI_K_FILM, (k_film_sep<true, 2><<<grid, dim3(32, 32 / NORI_FILM_NPIX), smem, ctx->stream>>>(fp, bt, n)));
-                } else {
-                    CK(cudaFuncSetAttribute(k_film_sep<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-                    LAUNCH(NORI_K_FILM, (k_film_sep<false, 2><<<grid, dim3(32, 32 / NORI_FILM_NPIX), smem, ctx->stream>>>(fp, bt, n)));
-                }
+                CUtensorMap tmap{};
+                const bool tma = ctx->opt_film_tma && filmTensorMap(&tmap, ctx->results, ctx->W, ctx->H, n, S);
+                const size_t smem = (size_t) S * S * ((tma ? 2 : 1) * sizeof(float4) + 2 * 5 * sizeof(float));
+                const dim3 blk(32, 32 / NORI_FILM_NPIX);
+#define NORI_FILM_LAUNCH(VAR, TMA) do { \
+                    CK(cudaFuncSetAttribute(k_film_sep<VAR, 2, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+                    LAUNCH(NORI_K_FILM, (k_film_sep<VAR, 2, TMA><<<grid, blk, smem, ctx->stream>>>(fp, bt, n, tmap))); } while (0)
+                if (ctx->opt_variance) { if (tma) NORI_FILM_LAUNCH(true, true); else NORI_FILM_LAUNCH(true, false); }
+                else { if (tma) NORI_FILM_LAUNCH(false, true); else NORI_FILM_LAUNCH(false, false); }
+#undef NORI_FILM_LAUNCH
             } else {
                 size_t smem = (size_t) S * S * (sizeof(float4) + sizeof(float2));
                 if (ctx->opt_variance) {
