@@ -18,6 +18,11 @@ struct PathState {
     uint32_t flags;
     Pcg32 rng;
 };
+// An NEE contribution of exactly (0,0,0) -- a discrete BSDF (mirror / dielectric: eval = 0), a light sample below the
+// surface's horizon, a back-facing emitter -- cannot change the radiance whatever its shadow ray hits (rad + 0 = rad), so
+// the kernels do not trace that ray unless the traversal counters are on (then every query the reference issues is
+// traced, and the counters equal the reference's).  NaN compares unequal: such a contribution is traced and added.
+__device__ __forceinline__ bool nullContribution(float x, float y, float z) { return x == 0.f && y == 0.f && z == 0.f; }
 struct VertexOut {
     Ray shadow; V3 contrib;       // NEE: added to rad iff the shadow ray is unoccluded
     Ray next;                     // extension ray when the path survives
@@ -112,7 +117,8 @@ __device__ V3 liPath(const DScene &sc, Pcg32 &rng, Ray ray, RayStats &rs) {
         if (!closestHit<COUNT>(sc, cur, h, rs)) break;
         VertexOut out;
         pathVertex<-1, MIS>(sc, h, st, out);
-        if ((st.flags & PF_SHADOW) && !anyHit<COUNT>(sc, out.shadow, rs)) st.rad = st.rad + out.contrib;
+        if ((st.flags & PF_SHADOW) && (COUNT || !nullContribution(out.contrib.x, out.contrib.y, out.contrib.z))
+            && !anyHit<COUNT>(sc, out.shadow, rs)) st.rad = st.rad + out.contrib;
         if (st.flags & PF_TERMINATE) break;
         cur = out.next;
     }

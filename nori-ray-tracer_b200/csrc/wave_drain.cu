@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) k_drain(DScene sc, Pool pool, Batch bt, C
                 if (!traverse<false, COUNT>(sc, st.o, st.d, mint, maxt, h, cnt)) break;
                 VertexOut out;
                 pathVertex<-1, MIS>(sc, h, st, out);
-                if (MIS) {
+                if (MIS && (COUNT || !nullContribution(out.contrib.x, out.contrib.y, out.contrib.z))) {
                     Hit sh; ++nShadow;
                     if (!traverse<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
                         st.rad = st.rad + out.contrib;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) k_drain_warp(DScene sc, Pool pool, Batch 
                     if (!traverseWarp<false, COUNT>(sc, st.o, st.d, mint, maxt, h, cnt)) break;
                     VertexOut out;
                     pathVertex<-1, MIS>(sc, h, st, out);
-                    if (MIS) {
+                    if (MIS && (COUNT || !nullContribution(out.contrib.x, out.contrib.y, out.contrib.z))) {   // uniform over the warp
                         Hit sh; if (lane == 0) ++nShadow;
                         if (!traverseWarp<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
                             st.rad = st.rad + out.contrib;

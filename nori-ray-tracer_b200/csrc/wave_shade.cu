@@ -33,17 +33,21 @@ __device__ __forceinline__ void shadeSlot(const DScene &sc, const Pool &pool, co
     } else {
         VertexOut out;
         pathVertex<BSDF, MODE == MODE_MIS, AO>(sc, h, st, out);
+        // a contribution of exactly zero needs no shadow ray (integrators.cuh: nullContribution)
+        const bool needShadow = COUNT || !nullContribution(out.contrib.x, out.contrib.y, out.contrib.z);
         if (DEFER) {
-            pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
-            pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
-            if (!(st.flags & PF_ALIVE)) {                           // the roulette ended the path: k_shadow_sm finalises it
-                pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
-                if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
-                pool.rng[slot] = st.rng.state;
-                pool.flags[slot] = PF_SHADOW | PF_TERMINATE | chBits;
-                return;
-            }
-        } else if (MODE == MODE_MIS) {                              // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
+            if (needShadow) {
+                pool.shD[slot] = make_float4(out.shadow.d.x, out.shadow.d.y, out.shadow.d.z, out.shadow.maxt);
+                pool.shC[slot] = make_float4(out.contrib.x, out.contrib.y, out.contrib.z, 0.f);
+                if (!(st.flags & PF_ALIVE)) {                       // the roulette ended the path: k_shadow_sm finalises it
+                    pool.rayO[slot] = make_float4(out.shadow.o.x, out.shadow.o.y, out.shadow.o.z, NORI_EPS);
+                    if (st.rad.x != ra.x || st.rad.y != ra.y || st.rad.z != ra.z) pool.rad[slot] = make_float4(st.rad.x, st.rad.y, st.rad.z, 0.f);
+                    pool.rng[slot] = st.rng.state;
+                    pool.flags[slot] = PF_SHADOW | PF_TERMINATE | chBits;
+                    return;
+                }
+            } else st.flags &= ~(uint32_t) PF_SHADOW;               // nothing for k_shadow_sm; an ended path is finalised below
+        } else if (MODE == MODE_MIS && needShadow) {                // scene->rayIntersect(eRec.shadowRay), path_mis.cpp:48
             Hit sh; ++nShadow;
             if (!traverse<true, COUNT>(sc, out.shadow.o, out.shadow.d, out.shadow.mint, out.shadow.maxt, sh, cnt))
                 st.rad = st.rad + out.contrib;
