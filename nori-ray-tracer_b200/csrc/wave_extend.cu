@@ -33,8 +33,11 @@ __device__ __forceinline__ int missRule(const DScene &sc, const Pool &pool, cons
     return -1;
 }
 
+#ifndef NORI_EXTEND_MINBLOCKS
+#define NORI_EXTEND_MINBLOCKS 8
+#endif
 template <bool COUNT, bool VOL>
-__global__ void __launch_bounds__(128) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
+__global__ void __launch_bounds__(128, NORI_EXTEND_MINBLOCKS) k_extend(DScene sc, Pool pool, Batch bt, Counters *ctr, uint32_t it) {
     __shared__ uint32_t s_free[4][NORI_FETCH];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, par = it & 1u;
     uint32_t *freeList = s_free[warp];
