@@ -70,3 +70,21 @@ def test_exr_round_trip(tmp_path):
     back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
     if back is not None:                                    # cv2 builds without EXR support return None
         assert np.array_equal(back[..., ::-1], img)
+
+
+def test_set_film_rebuilds_the_camera_matrix_of_the_fixture():
+    """SceneData.set_film (any aspect ratio) rebuilds sampleToCamera like perspective.cpp:53-80: at the fixture's own size it
+    reproduces the matrix the reference computed, and a 16:9 film keeps the horizontal field of view."""
+    import numpy as np
+    from conftest import load_golden_scene
+    sc = load_golden_scene("c5_volumetric")
+    before = np.array(list(sc.pod.camera.sampleToCamera), np.float32)
+    w, h = sc.width, sc.height
+    sc.set_film(w, h)
+    after = np.array(list(sc.pod.camera.sampleToCamera), np.float32)
+    assert np.abs(before - after).max() < 1e-6
+    sc.set_film(3840, 2160)
+    wide = np.array(list(sc.pod.camera.sampleToCamera), np.float32).reshape(4, 4)
+    assert (sc.width, sc.height) == (3840, 2160)
+    assert abs(wide[0, 0] - before.reshape(4, 4)[0, 0]) < 1e-6            # 2 / cot(fov / 2): the horizontal extent
+    assert abs(wide[1, 1] * (3840 / 2160) - wide[0, 0] * -1) < 1e-5       # vertical extent scales with the aspect ratio
