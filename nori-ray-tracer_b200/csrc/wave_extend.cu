@@ -297,7 +297,7 @@ template <bool COUNT>
 __device__ __forceinline__ void smNode2(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint4 *rec = &sc.nodes2[4 * (size_t) (L.cur >> 2)];
-    const uint4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2), d = __ldg(rec + 3);
+    uint4 a, b, c, d; ldgPair(rec, a, b); ldgPair(rec + 2, c, d);
     if (COUNT) cnt.nodes += 2;
     float nearL, nearR;
     bool hitL, hitR;
@@ -332,8 +332,8 @@ template <bool SHADOW, bool COUNT>
 __device__ __forceinline__ void smNode4(const DScene &sc, LaneTrav &L, LaneStack2 &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
     const uint4 *rec = &sc.nodes4[8 * (size_t) L.cur];
-    const uint4 a0 = __ldg(rec), b0 = __ldg(rec + 1), a1 = __ldg(rec + 2), b1 = __ldg(rec + 3);
-    const uint4 a2 = __ldg(rec + 4), b2 = __ldg(rec + 5), a3 = __ldg(rec + 6), b3 = __ldg(rec + 7);
+    uint4 a0, b0, a1, b1, a2, b2, a3, b3;
+    ldgPair(rec, a0, b0); ldgPair(rec + 2, a1, b1); ldgPair(rec + 4, a2, b2); ldgPair(rec + 6, a3, b3);
 #if NORI_PREFETCH_CHILDREN
     // experiment: request every inner child's record (one line each) into L2 before the box tests decide which are entered
     if (!(a0.w & 0x80000000u)) asm volatile("prefetch.global.L2 [%0];" :: "l"(&sc.nodes4[8 * (size_t) a0.w]));
@@ -460,8 +460,7 @@ __device__ __forceinline__ void smStart(const DScene &sc, LaneTrav &L, V3 o, V3 
 template <bool COUNT>
 __device__ __forceinline__ void smNode(const DScene &sc, LaneTrav &L, LaneStack &stack, TraceCounters &cnt) {
     RayTrav &r = L.r;
-    const uint4 n0 = __ldg(&sc.nodes[2 * r.node]);
-    const uint4 n1 = __ldg(&sc.nodes[2 * r.node + 1]);
+    uint4 n0, n1; ldgPair(&sc.nodes[2 * r.node], n0, n1);
     if (COUNT) ++cnt.nodes;
     if (nodeBox(r.plain, r.o, r.d, r.rcp, r.mint, r.cull, n0, n1)) {
         if (!(n0.x & 1u)) {                                      // inner: descend() of traverse.cuh with the sign mask
