@@ -262,7 +262,10 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
  * order "order" selects; 2: the rays are loaded into path-pool slots and answered by the kernels that render large
  * scenes -- the warp-state-machine closest-hit / any-hit kernels with the configured "order" / "wide" layout; per-ray
  * counters are then 0, the totals are in nori_gpu_get_kernel_stats, and any-hit rays start at Epsilon like the NEE
- * rays those kernels trace, arealight.cpp:56). */
+ * rays those kernels trace, arealight.cpp:56),
+ * "wavefronts" (1..4, default 2: the sample layers of a batch are split between that many independent wavefronts --
+ * own part of the pool, own counters, own stream -- whose kernels overlap on the device; the samples, the film and the
+ * counters do not depend on it; "kernel_timing" renders with one). */
 int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value);
 
 /* Render sample indices [spp_begin, spp_begin+spp_count) for every pixel and ACCUMULATE them into

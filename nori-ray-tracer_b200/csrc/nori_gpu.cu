@@ -15,6 +15,7 @@
 #define NORI_DEFAULT_RESULTS_MB 8192
 static std::string g_init_error;
 
+#define NORI_MAX_WAVEFRONTS 4
 struct nori_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -40,6 +41,11 @@ struct nori_gpu_ctx {
     std::vector<void *> pool_allocs;
     float4 *results = nullptr; size_t results_cap = 0;      // in float4 elements
     Counters *ctr = nullptr; Counters *h_ctr = nullptr;      // device / pinned host
+    // concurrent wavefronts (option "wavefronts", traceBatch): wavefront 0 uses `stream` / `ctr` / `h_ctr`, the others these
+    cudaStream_t wf_stream[NORI_MAX_WAVEFRONTS - 1] = {}; Counters *wf_ctr[NORI_MAX_WAVEFRONTS - 1] = {}, *wf_h_ctr[NORI_MAX_WAVEFRONTS - 1] = {};
+    cudaEvent_t wf_done[NORI_MAX_WAVEFRONTS - 1] = {};
+    int wf_used = 1;                                        // wavefronts of the last batch (foldStats adds their counters)
+    int64_t opt_wavefronts = 2;
     float4 *flush_buf = nullptr; size_t flush_n = 0;
     void *scratch = nullptr; size_t scratch_cap = 0;       // staging for resolve / variance / trace / probes / pcg32
 
@@ -200,6 +206,11 @@ void nori_gpu_destroy(nori_gpu_ctx *ctx) {
     cudaFree(ctx->arena);
     cudaFree(ctx->film); cudaFree(ctx->vsum); cudaFree(ctx->vsum2); cudaFree(ctx->results); cudaFree(ctx->ctr); cudaFree(ctx->flush_buf); cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_ctr);
+    for (int j = 0; j < NORI_MAX_WAVEFRONTS - 1; ++j) {
+        if (ctx->wf_stream[j]) cudaStreamDestroy(ctx->wf_stream[j]);
+        if (ctx->wf_done[j]) cudaEventDestroy(ctx->wf_done[j]);
+        cudaFree(ctx->wf_ctr[j]); if (ctx->wf_h_ctr[j]) cudaFreeHost(ctx->wf_h_ctr[j]);
+    }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -233,6 +244,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
         ctx->opt_results_mb = NORI_DEFAULT_RESULTS_MB; ctx->opt_stats = 0; ctx->opt_megakernel = 0; ctx->opt_poll = 8; ctx->opt_emitter_sort = 1;
         ctx->opt_area_only = 1; ctx->opt_film_sep = 1; ctx->opt_film_tma = 1; ctx->opt_drain = 1 << 15; ctx->opt_shadow_pass = 0; ctx->opt_order = 2;
         ctx->opt_wide = 1; ctx->opt_traversal = 0; ctx->opt_trace_kernel = 0; ctx->opt_kernel_timing = 0; ctx->opt_l2_window = 0; ctx->opt_drain_mode = 0;
+        ctx->opt_wavefronts = 2;
     }
     else if (k == "results_mb") { REQUIRE(value >= 16, "results_mb must be >= 16"); ctx->opt_results_mb = value; }
     else if (k == "stats") ctx->opt_stats = value != 0;
@@ -261,6 +273,7 @@ int nori_gpu_set_option(nori_gpu_ctx *ctx, const char *name, int64_t value) {
     else if (k == "drain_mode") { REQUIRE(value == 0 || value == 1, "drain_mode must be 0 (one warp per path) or 1 (one thread per path)"); ctx->opt_drain_mode = value; }
     else if (k == "drain") { REQUIRE(value >= 0, "drain must be >= 0"); ctx->opt_drain = value; }
     else if (k == "shadow_pass") { REQUIRE(value >= 0 && value <= 2, "shadow_pass must be 0 (auto), 1 (own pass) or 2 (inside k_shade)"); ctx->opt_shadow_pass = value; }
+    else if (k == "wavefronts") { REQUIRE(value >= 1 && value <= NORI_MAX_WAVEFRONTS, "wavefronts must be in [1,4]"); ctx->opt_wavefronts = value; }
     else if (k == "poll") { REQUIRE(value >= 1 && value <= 1024, "poll must be in [1,1024]"); ctx->opt_poll = value; }
     else if (k == "flush_l2") {
         // bench helper: overwrite a buffer larger than L2 (value = MiB)
@@ -573,11 +586,49 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
             ctx->window_set = want;
         }
     }
-    // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
-    Counters zero{}; zero.total_samples = total;
-    *ctx->h_ctr = zero;
-    CK(cudaMemcpyAsync(ctx->ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // ---- concurrent wavefronts.  Every kernel launch of the loop below ends with warps finishing unevenly and is followed
+    // by a launch gap and a ramp-up, ~37 us per iteration in which most of the device idles.  The batch's sample layers are
+    // therefore split between up to `wavefronts` independent wavefronts -- each with its own part of the path pool and of the
+    // queues, its own counters, its own stream, and a whole number of layers (its Batch differs in `results`, `spp_first`
+    // only, so the kernels are unchanged and every sample is computed exactly as before) -- and the block scheduler fills the
+    // tail of one wavefront's kernel with the CTAs of the other's.  Per-launch event timing needs the launches serialised:
+    // `kernel_timing` renders with one wavefront.
+    int W = (int) std::min<int64_t>(std::min<int64_t>(ctx->opt_wavefronts, NORI_MAX_WAVEFRONTS), nLayers);
+    if (ctx->opt_kernel_timing) W = 1;
+    while (W > 1 && ((ctx->pool.P / (uint32_t) W) & ~255u) < 4096u) --W;
+    struct Wavefront { Pool pool; Batch bt; Counters *ctr, *h; cudaStream_t st; unsigned long long total; uint32_t it; bool finished; };
+    Wavefront wf[NORI_MAX_WAVEFRONTS];
+    for (int j = 0; j < W; ++j) {
+        Wavefront &w = wf[j];
+        if (j > 0 && !ctx->wf_stream[j - 1]) {
+            CK(cudaStreamCreateWithFlags(&ctx->wf_stream[j - 1], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->wf_done[j - 1], cudaEventDisableTiming));
+            CK(cudaMalloc((void **) &ctx->wf_ctr[j - 1], sizeof(Counters)));
+            CK(cudaMallocHost((void **) &ctx->wf_h_ctr[j - 1], sizeof(Counters)));
+        }
+        w.st = j ? ctx->wf_stream[j - 1] : ctx->stream; w.ctr = j ? ctx->wf_ctr[j - 1] : ctx->ctr; w.h = j ? ctx->wf_h_ctr[j - 1] : ctx->h_ctr;
+        const uint32_t first = (uint32_t) ((unsigned long long) nLayers * j / W), last = (uint32_t) ((unsigned long long) nLayers * (j + 1) / W);
+        w.bt = bt; w.bt.results = bt.results + (size_t) first * bt.wh; w.bt.spp_first = bt.spp_first + first;
+        w.bt.capacity = bt.capacity - (uint32_t) std::min<size_t>((size_t) first * bt.wh, bt.capacity);
+        w.total = (unsigned long long) (last - first) * bt.wh; w.it = 0; w.finished = false;
+        w.pool = ctx->pool;
+        if (W > 1) {                                         // this wavefront's slice of every pool array
+            const uint32_t Pj = (ctx->pool.P / (uint32_t) W) & ~255u;
+            const size_t off = (size_t) j * Pj;
+            Pool &q = w.pool; q.P = Pj;
+            float4 **f4[] = {&q.rayO, &q.rayD, &q.hit, &q.thr, &q.rad, &q.acc, &q.shD, &q.shC};
+            for (auto pp : f4) if (*pp) *pp += off;
+            q.rng += off; q.sid += off; q.flags += off;
+            for (int t = 0; t < NORI_NQ; ++t) q.queue[t] += off;
+            if (q.equeue) q.equeue += (size_t) NORI_NEQ * off;
+        }
+        // per-batch counters (the cumulative ones are folded into ctx->stats by the caller)
+        Counters zero{}; zero.total_samples = w.total;
+        *w.h = zero;
+        CK(cudaMemcpyAsync(w.ctr, w.h, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));                 // everything queued before this batch has finished: the other streams may start
+    ctx->wf_used = W;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const ExtendKernel kext = wk.pickExtend(sm, count, mode == MODE_VOL, noriSmLayout(ctx->ds));
     int occE = 8;
@@ -585,40 +636,62 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
     const int gridShadow = defer ? sms * std::max(1, wk.shadowSmOccupancy(count, noriSmLayout(ctx->ds))) : 0;
     ctx->last_wave = true; ctx->last_defer = defer;
-    uint32_t it = 0;
-    while (true) {
-        for (int i = 0; i < ctx->opt_poll; ++i, ++it) {
-            LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, ctx->stream>>>(ctx->ds, ctx->pool, bt, ctx->ctr, it)));
-            if (esort) LAUNCH(NORI_K_GENERATE, wk.rebin((int) ((ctx->pool.P + 1023u) / 1024u), ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+    // `poll` iterations of one wavefront, then its counters on their way to the host
+    auto enqueue = [&](Wavefront &w) -> int {
+        for (int i = 0; i < ctx->opt_poll; ++i, ++w.it) {
+            LAUNCH(NORI_K_EXTEND, (kext<<<gridE, 128, 0, w.st>>>(ctx->ds, w.pool, w.bt, w.ctr, w.it)));
+            if (esort) LAUNCH(NORI_K_GENERATE, wk.rebin((int) ((w.pool.P + 1023u) / 1024u), w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
             if (defer) {
-                LAUNCH(NORI_K_SHADE, wk.shadeMisDeferred(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-                LAUNCH(NORI_K_SHADOW, wk.shadowSm(count, gridShadow, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            } else if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, wk.shadeMis(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, wk.shadeMats(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
-            else LAUNCH(NORI_K_SHADE, wk.shadeVol(count, gridSh, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr, it));
+                LAUNCH(NORI_K_SHADE, wk.shadeMisDeferred(count, gridSh, w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
+                LAUNCH(NORI_K_SHADOW, wk.shadowSm(count, gridShadow, w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
+            } else if (mode == MODE_MIS) LAUNCH(NORI_K_SHADE, wk.shadeMis(count, gridSh, w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
+            else if (mode == MODE_MATS) LAUNCH(NORI_K_SHADE, wk.shadeMats(count, gridSh, w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
+            else LAUNCH(NORI_K_SHADE, wk.shadeVol(count, gridSh, w.st, ctx->ds, w.pool, w.bt, w.ctr, w.it));
             ctx->stats.iterations += 1;
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_ctr->done >= total) break;
-        // drain: no camera path left to start and only a few paths alive => finish them in one launch (mega.cu)
-        const unsigned long long live = total - ctx->h_ctr->done;
-        if (mode != MODE_VOL && ctx->opt_drain > 0 && ctx->h_ctr->next_sample >= total && live <= (unsigned long long) ctx->opt_drain) {
-            // warp mode: 16 CTAs per SM = 64 warps, each scanning its share of the pool in 32-slot segments
-            LAUNCH(NORI_K_SINGLE, wk.drain(mode == MODE_MIS, count, ctx->opt_drain_mode == 0 ? -(sms * 16) : sms * 8, ctx->stream, ctx->ds, ctx->pool, bt, ctx->ctr));
-            CK(cudaGetLastError());
-            ctx->stats.iterations += 1;
-            break;
+        CK(cudaMemcpyAsync(w.h, w.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, w.st));
+        return 0;
+    };
+    for (int j = 0; j < W; ++j) if (enqueue(wf[j])) return 1;
+    // wait for one wavefront's counters while the others' launches keep the device busy; refill it before waiting for the next
+    for (int left = W; left > 0;) {
+        for (int j = 0; j < W; ++j) {
+            Wavefront &w = wf[j];
+            if (w.finished) continue;
+            CK(cudaStreamSynchronize(w.st));
+            if (w.h->done >= w.total) { w.finished = true; --left; continue; }
+            // drain: no camera path left to start and only a few paths alive => finish them in one launch (mega.cu)
+            const unsigned long long live = w.total - w.h->done;
+            if (mode != MODE_VOL && ctx->opt_drain > 0 && w.h->next_sample >= w.total && live <= (unsigned long long) ctx->opt_drain) {
+                // warp mode: 16 CTAs per SM = 64 warps, each scanning its share of the pool in 32-slot segments
+                LAUNCH(NORI_K_SINGLE, wk.drain(mode == MODE_MIS, count, ctx->opt_drain_mode == 0 ? -(sms * 16) : sms * 8, w.st, ctx->ds, w.pool, w.bt, w.ctr));
+                CK(cudaGetLastError());
+                ctx->stats.iterations += 1;
+                w.finished = true; --left;
+                continue;
+            }
+            if (enqueue(w)) return 1;
         }
+    }
+    for (int j = 1; j < W; ++j) {                           // what follows on the context's stream (film pass, counters) waits for every wavefront
+        CK(cudaEventRecord(ctx->wf_done[j - 1], wf[j].st));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->wf_done[j - 1], 0));
     }
     return 0;
 }
 
 static int foldStats(nori_gpu_ctx *ctx, unsigned long long samples) {
     CK(cudaMemcpyAsync(ctx->h_ctr, ctx->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int j = 1; j < ctx->wf_used; ++j) CK(cudaMemcpyAsync(ctx->wf_h_ctr[j - 1], ctx->wf_ctr[j - 1], sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const Counters &c = *ctx->h_ctr;
+    Counters c = *ctx->h_ctr;
+    for (int j = 1; j < ctx->wf_used; ++j) {                 // the other wavefronts of the batch (traceBatch)
+        const Counters &o = *ctx->wf_h_ctr[j - 1];
+        c.rays_ext += o.rays_ext; c.rays_sh += o.rays_sh; c.rays_sh_closest += o.rays_sh_closest; c.nodes_ext += o.nodes_ext; c.nodes_sh += o.nodes_sh;
+        c.prims_ext += o.prims_ext; c.prims_sh += o.prims_sh; c.invalid += o.invalid; c.guard_redo += o.guard_redo; c.max_stack = std::max(c.max_stack, o.max_stack);
+    }
+    ctx->wf_used = 1;
     ctx->stats.samples += samples;
     ctx->stats.rays += c.rays_ext + c.rays_sh + c.rays_sh_closest; ctx->stats.shadow_rays += c.rays_sh;
     ctx->stats.nodes_visited += c.nodes_ext + c.nodes_sh; ctx->stats.prims_tested += c.prims_ext + c.prims_sh;
