@@ -728,7 +728,8 @@ static int renderImpl(nori_gpu_ctx *ctx, uint32_t spp_begin, uint32_t spp_count,
     {   // the per-sample buffer takes what the device can spare: at most results_mb, at most 3/4 of the free memory (plus
         // what the buffer already holds), and half as many layers again whenever the allocation still fails
         size_t freeB = 0, totalB = 0;
-        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+        const bool fits = std::min<size_t>(maxLayers, spp_count) * wh <= ctx->results_cap;   // (the query costs up to a millisecond: only when the buffer must grow)
+        if (!fits && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
             const size_t spare = freeB / 4 * 3 + ctx->results_cap * sizeof(float4);
             maxLayers = std::max<size_t>(1, std::min<size_t>(maxLayers, spare / ((size_t) wh * sizeof(float4))));
         }
