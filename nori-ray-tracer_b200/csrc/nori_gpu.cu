@@ -538,6 +538,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const unsigned long long total = (unsigned long long) nLayers * bt.wh;
     const bool count = ctx->opt_stats != 0;
     const int integ = ctx->ds.integrator;
+    ctx->wf_used = 1;                                       // (a batch that failed half-way must not leave its wavefronts to the next foldStats)
     ctx->ds.ordered = ctx->opt_order == 1 || (ctx->opt_order == 2 && ctx->ds.n_prims > 4096);
     ctx->ds.wide = ctx->opt_wide ? 1 : 0;
     const bool wave = (integ == NORI_INTEGRATOR_PATH_MIS || integ == NORI_INTEGRATOR_PATH_MATS || integ == NORI_INTEGRATOR_VOLUMETRIC)
