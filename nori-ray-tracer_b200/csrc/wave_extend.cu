@@ -3,9 +3,11 @@
 #include "kernels.cuh"
 
 #ifndef NORI_EXTEND_PIPELINE
-#define NORI_EXTEND_PIPELINE 0
+#define NORI_EXTEND_PIPELINE 1   // k_extend requests the next round's flags and ray before it traverses the current one
 #endif
-#define NORI_FETCH 256u      // pool slots claimed per warp per atomic (8 rounds of 32)
+#ifndef NORI_FETCH
+#define NORI_FETCH 128u      // pool slots claimed per warp per atomic (4 rounds of 32); with two concurrent wavefronts, Cornell box:
+#endif                       // 64: 214.2, 128: 205.7, 256: 207.2, 512: 209.3 ms; 128 + the pipeline: 204.5 ms (10 M triangles 400.5 -> 397.8)
 
 // ------------------------------------------------------------------------------ extend (+ regeneration)
 // Persistent warps claim NORI_FETCH consecutive pool slots at a time and run three phases on them:
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(128, NORI_EXTEND_MINBLOCKS) k_extend(DScene sc
         // the handful of queue counters the hottest instruction of the kernel: ~11 % of its stall samples)
 #pragma unroll
         for (int t = 0; t < (VOL ? NORI_NQ : NORI_BSDF_COUNT); ++t) {
-            uint32_t masks = 0, total = 0, before = 0;                   // lane r (< 8) keeps round r's ballot
+            uint32_t masks = 0, total = 0, before = 0;                   // lane r (< NORI_FETCH / 32) keeps round r's ballot
             for (uint32_t round = 0; round < NORI_FETCH / 32u; ++round) {
                 const uint32_t m = __ballot_sync(0xffffffffu, freeList[round * 32u + lane] == (uint32_t) t);
                 if (lane == round) { masks = m; before = total; }
