@@ -264,7 +264,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (headline: 1024)")
-    ap.add_argument("--pool", type=int, default=1 << 23, help="path-pool slots (8 Mi: 201 wavefront iterations per step instead of 385 at 4 Mi, -3 %% time)")
+    ap.add_argument("--pool", type=int, default=6 << 20, help="path-pool slots, shared by the two concurrent wavefronts (final kernels: 4 Mi 205.7, "
+                                                              "5 Mi 203.3, 6 Mi 202.3, 8 Mi 204.0, 10 Mi 206.3, 12 Mi 207.8 ms per step)")
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of one bounded reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-scene", action="store_true", help="skip the 10M-triangle measurements (roofline falls back to roofline_c2's accounting)")

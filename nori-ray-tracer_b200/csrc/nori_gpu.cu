@@ -16,6 +16,9 @@
 static std::string g_init_error;
 
 #define NORI_MAX_WAVEFRONTS 4
+#ifndef NORI_SHADE_GRID_PER_SM
+#define NORI_SHADE_GRID_PER_SM 16         // CTAs of k_shade per SM (two rounds of the 8 resident ones)
+#endif
 struct nori_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -634,7 +637,7 @@ static int traceBatch(nori_gpu_ctx *ctx, const Batch &bt, uint32_t nLayers) {
     const ExtendKernel kext = wk.pickExtend(sm, count, mode == MODE_VOL, noriSmLayout(ctx->ds));
     int occE = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occE, kext, 128, 0);
-    const int gridE = sms * std::max(1, occE), gridSh = sms * 16;
+    const int gridE = sms * std::max(1, occE), gridSh = sms * NORI_SHADE_GRID_PER_SM;
     const int gridShadow = defer ? sms * std::max(1, wk.shadowSmOccupancy(count, noriSmLayout(ctx->ds))) : 0;
     ctx->last_wave = true; ctx->last_defer = defer;
     // `poll` iterations of one wavefront, then its counters on their way to the host
