@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(128, NORI_EXTEND_MINBLOCKS) k_extend(DScene sc
 #define NORI_LEAF_MIN 12
 #endif
 #ifndef NORI_REFILL_MIN
-#define NORI_REFILL_MIN 12
+#define NORI_REFILL_MIN 12       // with 128-slot chunks (10 M triangles, 16 spp, two wavefronts): 8: 407.4, 12: 397.7, 16: 394.8, 20: 398.1, 24: 416.8 ms;
+                                 // 16 is slower with one wavefront (k_extend_sm alone 1.29 vs 1.31 Grays/s): 12 kept
 #endif
 // resident CTAs per SM asked of the compiler (register cap = 65536 / (128 * blocks)); LAY: 0 reference nodes,
 // 1 child-box pairs, 2 4-wide records
