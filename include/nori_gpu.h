@@ -239,9 +239,10 @@ const char *nori_gpu_last_error(const nori_gpu_ctx *ctx);   /* ctx may be NULL: 
  * the film. */
 int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
 
-/* Tunables: "pool" (resident path slots), "spp_chunk" (samples per pixel per film batch),
+/* Tunables: "pool" (resident path slots), "results_mb" (MiB of the per-sample buffer: bounds the sample layers of one film batch),
  * "stats" (1: count node visits / primitive tests), "kernel_timing" (1: CUDA events around every
- * launch), "megakernel" (1: one thread per sample for every integrator), "poll", "results_mb",
+ * launch), "megakernel" (1: one thread per sample for every integrator), "poll" (wavefront iterations between two looks at the
+ * device counters), "variance" (1: the running-mean variance statistic of render.cpp:238-278, see nori_gpu_download_variance),
  * "flush_l2" (bench only: overwrite that many MiB to evict L2), "order" (0: the reference's child
  * order, left child first, bvh.cpp:430-433 -- node-visit / primitive-test counters equal the
  * reference's; 1: the child on the ray's side of the node's split axis first -- same hits, same
@@ -263,6 +264,11 @@ int nori_gpu_upload_scene(nori_gpu_ctx *ctx, const nori_gpu_scene *scene);
  * scenes -- the warp-state-machine closest-hit / any-hit kernels with the configured "order" / "wide" layout; per-ray
  * counters are then 0, the totals are in nori_gpu_get_kernel_stats, and any-hit rays start at Epsilon like the NEE
  * rays those kernels trace, arealight.cpp:56),
+ * "drain_mode" (0 (default): the tail by one warp per remaining path, 1: one thread per path),
+ * "film_sep" (default 1: radius-2 filters use the film kernel with per-sample tabulated row / column weights; 0: the generic one),
+ * "film_tma" (default 1: that kernel's sample tiles are staged by the TMA unit; 0: per-thread loads),
+ * "l2_window" (MiB of the 4-wide records held by an L2 access-policy window; default 0),
+ * "reset_options" (every scheduling option back to its default),
  * "wavefronts" (1..4, default 2: the sample layers of a batch are split between that many independent wavefronts --
  * own part of the pool, own counters, own stream -- whose kernels overlap on the device; the samples, the film and the
  * counters do not depend on it; "kernel_timing" renders with one). */

@@ -55,3 +55,19 @@ def test_product_never_touches_the_oracle():
         src = open(f).read()
         code = "\n".join(l for l in src.splitlines() if not l.strip().startswith(("#", "//", "*", '"""')))
         assert not re.search(r"\b(import|from)\s+oracle|oracle_binding|libnori_oracle|nori_oracle_", code), f
+
+
+def test_every_option_is_documented():
+    """nori_gpu_set_option's names (csrc/nori_gpu.cu) are the ones include/nori_gpu.h and INTEGRATION.md describe -- no
+    undocumented knob, no documented knob the library does not know."""
+    import re
+    src = open(os.path.join(ROOT, "nori-ray-tracer_b200", "csrc", "nori_gpu.cu")).read()
+    opts = set(re.findall(r'k == "([a-z0-9_]+)"', src))
+    assert len(opts) >= 20
+    hdr = open(os.path.join(ROOT, "include", "nori_gpu.h")).read()
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert not [o for o in opts if f'"{o}"' not in hdr], [o for o in opts if f'"{o}"' not in hdr]
+    assert not [o for o in opts if f"`{o}`" not in integ], [o for o in opts if f"`{o}`" not in integ]
+    block = hdr[hdr.index("/* Tunables:"):hdr.index("int nori_gpu_set_option")]
+    documented = set(re.findall(r'"([a-z0-9_]+)" \(', block))
+    assert documented <= opts, documented - opts
